@@ -1,0 +1,413 @@
+// SMPL forward + analytic backward for all bodies of a rank.
+//
+// Reference path replaced: SMPL.forward / lbs (mhmocap/smpl.py:297-399, 490-576) and its autograd,
+// as evaluated by __eval_batch_optimized_variables (mhmocap/optimizer.py:678-707) and the
+// full-sequence forwards at optimizer.py:385-389, 565-570.  Parameters are constant inside a cycle, so
+// SMPL is evaluated ONCE per person-frame per cycle and feeds every loss term.
+//
+// Stages (one kernel each):
+//   shape_prep   v_shaped = v_template + shapedirs.beta ; J = J_regressor.v_shaped (closed form)   smpl.py:532-535
+//   pose_prep    Rodrigues x22, pose feature, kinematic chain, A = G - [0 | G.R J]                   smpl.py:541-547, 692-746
+//   gemm_fwd     v_posed = v_shaped + pose_feature . posedirs   (189 live rows)                      smpl.py:549-558
+//   skin_fwd     v = sum_j W_ij (A_j [v_posed;1]) ; V = scale v + T ; J17 ; lowest vertex            smpl.py:564-574, 375-377 ; optimizer.py:487, 702-703
+//   skin_bwd     dL/dV -> dL/dv_posed, dL/dA (warp-shuffle segmented reduction per joint), dL/dT, dL/dscale
+//   gemm_bwd     dL/dpose_feature, dL/dbeta(shape) = dv_posed . [posedirs ; shapedirs]^T   (split-K partials)
+//   pose_bwd     chain / Rodrigues backward -> dL/dtheta ; dL/dJ -> dL/dbeta
+#include "mh_ctx.h"
+
+#define V_ 6890
+
+// -------------------------------------------------------------------------------------------------
+__global__ void k_shape_prep(const float* __restrict__ betas, int rows, const float* __restrict__ vt,
+                             const float* __restrict__ pext, float* __restrict__ vshaped) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= MH_LD3V) return;
+    float acc = vt[c];
+    const float* b = betas + (size_t)r * MH_NBETA;
+#pragma unroll
+    for (int l = 0; l < MH_NBETA; ++l) acc += b[l] * pext[(size_t)(MH_KPF + l) * MH_LD3V + c];
+    vshaped[(size_t)r * MH_LD3V + c] = acc;
+}
+
+__global__ void k_joint_prep(const float* __restrict__ betas, int rows, const float* __restrict__ Jt,
+                             const float* __restrict__ Js, float* __restrict__ Jrest) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * 72) return;
+    const int r = i / 72, e = i % 72;
+    float acc = Jt[e];
+#pragma unroll
+    for (int l = 0; l < MH_NBETA; ++l) acc += Js[e * MH_NBETA + l] * betas[r * MH_NBETA + l];
+    Jrest[i] = acc;
+}
+
+// one thread per body
+__global__ void k_pose_prep(const float* __restrict__ theta, const float* __restrict__ Jrest, int nbodies, int N,
+                            int per_body_shape, float* __restrict__ A, float* __restrict__ pf) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbodies) return;
+    const int row = per_body_shape ? b : (b % N);
+    float th[72], J[72], Al[288], pfl[207];
+    for (int i = 0; i < 72; ++i) { th[i] = theta[(size_t)b * 72 + i]; J[i] = Jrest[(size_t)row * 72 + i]; }
+    mh_pose_forward(th, J, Al, pfl, nullptr);
+    for (int i = 0; i < 288; ++i) A[(size_t)b * 288 + i] = Al[i];
+    for (int i = 0; i < MH_KPF; ++i) pf[(size_t)b * MH_KPF + i] = (i < MH_NPF_LIVE) ? pfl[i] : 0.0f;
+}
+
+// -------------------------------------------------------------------------------------------------
+// C[m][n] = sum_k A[m][k] B[k][n] + Vs[row(m)][n]    M = bodies, N = MH_LD3V, K = MH_KPF
+// tile 128 x 64 x 16, 256 threads, 8 x 4 outputs per thread
+#define GF_BM 128
+#define GF_BN 64
+#define GF_BK 16
+__global__ void __launch_bounds__(256) k_gemm_fwd(const float* __restrict__ Am, const float* __restrict__ Bm,
+                                                  const float* __restrict__ Vs, float* __restrict__ C, int M, int Npers,
+                                                  int per_body_shape) {
+    __shared__ __align__(16) float As[GF_BK][GF_BM];
+    __shared__ __align__(16) float Bs[GF_BK][GF_BN];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * GF_BN, m0 = blockIdx.y * GF_BM;
+    const int ty = tid / 16, tx = tid % 16;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    float4 ra[2], rb;
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * 256;
+            const int m = idx / 4, k4 = (idx % 4) * 4;
+            ra[i] = (m0 + m < M) ? *reinterpret_cast<const float4*>(Am + (size_t)(m0 + m) * MH_KPF + k0 + k4)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int k = tid / 16, n4 = (tid % 16) * 4;
+        rb = *reinterpret_cast<const float4*>(Bm + (size_t)(k0 + k) * MH_LD3V + n0 + n4);
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * 256;
+            const int m = idx / 4, k4 = (idx % 4) * 4;
+            As[k4 + 0][m] = ra[i].x; As[k4 + 1][m] = ra[i].y; As[k4 + 2][m] = ra[i].z; As[k4 + 3][m] = ra[i].w;
+        }
+        const int k = tid / 16, n4 = (tid % 16) * 4;
+        *reinterpret_cast<float4*>(&Bs[k][n4]) = rb;
+    };
+    gload(0);
+    for (int k0 = 0; k0 < MH_KPF; k0 += GF_BK) {
+        sstore();
+        __syncthreads();
+        if (k0 + GF_BK < MH_KPF) gload(k0 + GF_BK);
+#pragma unroll
+        for (int k = 0; k < GF_BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+        const int row = per_body_shape ? m : (m % Npers);
+        const float4 vs = *reinterpret_cast<const float4*>(Vs + (size_t)row * MH_LD3V + n0 + tx * 4);
+        float4 o = make_float4(acc[i][0] + vs.x, acc[i][1] + vs.y, acc[i][2] + vs.z, acc[i][3] + vs.w);
+        *reinterpret_cast<float4*>(C + (size_t)m * MH_LD3V + n0 + tx * 4) = o;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// one CTA per body
+__global__ void __launch_bounds__(256) k_skin_fwd(const float* __restrict__ vposed, const float* __restrict__ A,
+                                                  const uint8_t* __restrict__ wj, const float* __restrict__ ww, int KW,
+                                                  const float* __restrict__ trans, const float* __restrict__ xscale, int N,
+                                                  const int* __restrict__ rptr, const int* __restrict__ rvert,
+                                                  const float* __restrict__ rw, float* __restrict__ verts,
+                                                  float* __restrict__ j17, int* __restrict__ lowidx, int first_body) {
+    const int b = first_body + blockIdx.x;
+    __shared__ float sA[288];
+    __shared__ float sred[8];
+    __shared__ int sredi[8];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 288; i += 256) sA[i] = A[(size_t)b * 288 + i];
+    const float s = xscale ? powf(1.1f, xscale[b % N]) : 1.0f;            // optimizer.py:681
+    const float t0 = trans ? trans[(size_t)b * 3] : 0.f, t1 = trans ? trans[(size_t)b * 3 + 1] : 0.f,
+                t2 = trans ? trans[(size_t)b * 3 + 2] : 0.f;
+    __syncthreads();
+    const float* vp = vposed + (size_t)b * MH_LD3V;
+    float* vo = verts + (size_t)b * MH_LD3V;
+    float besty = -INFINITY;
+    int besti = 0x7fffffff;
+    for (int v = tid; v < V_; v += 256) {
+        float Tm[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Tm[e] = 0.f;
+        for (int q = 0; q < KW; ++q) {
+            const float w = ww[(size_t)v * KW + q];
+            const float* a = sA + 12 * wj[(size_t)v * KW + q];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) Tm[e] = fmaf(w, a[e], Tm[e]);
+        }
+        const float x = vp[3 * v], y = vp[3 * v + 1], z = vp[3 * v + 2];
+        const float ox = Tm[0] * x + Tm[1] * y + Tm[2] * z + Tm[3];
+        const float oy = Tm[4] * x + Tm[5] * y + Tm[6] * z + Tm[7];
+        const float oz = Tm[8] * x + Tm[9] * y + Tm[10] * z + Tm[11];
+        const float X = s * ox + t0, Y = s * oy + t1, Z = s * oz + t2;     // optimizer.py:702
+        vo[3 * v] = X; vo[3 * v + 1] = Y; vo[3 * v + 2] = Z;
+        if (Y > besty) { besty = Y; besti = v; }
+    }
+    // block argmax of Y (lowest vertex, Y points down; optimizer.py:487), first index on ties
+    for (int o = 16; o > 0; o >>= 1) {
+        const float oy = __shfl_down_sync(0xffffffffu, besty, o);
+        const int oi = __shfl_down_sync(0xffffffffu, besti, o);
+        if (oy > besty || (oy == besty && oi < besti)) { besty = oy; besti = oi; }
+    }
+    if ((tid & 31) == 0) { sred[tid >> 5] = besty; sredi[tid >> 5] = besti; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (sred[w] > besty || (sred[w] == besty && sredi[w] < besti)) { besty = sred[w]; besti = sredi[w]; }
+        if (lowidx) lowidx[b] = besti;
+    }
+    if (!j17) return;
+    // regressed joints: J17 = scale * (R17 . v_local) + T  ==  R17 . V + T (1 - rowsum)   (smpl.py:375-377, optimizer.py:703)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int k = warp; k < MH_NJR; k += 8) {
+        float ax = 0.f, ay = 0.f, az = 0.f, sw = 0.f;
+        for (int e = rptr[k] + lane; e < rptr[k + 1]; e += 32) {
+            const int v = rvert[e];
+            const float w = rw[e];
+            ax = fmaf(w, vo[3 * v], ax); ay = fmaf(w, vo[3 * v + 1], ay); az = fmaf(w, vo[3 * v + 2], az);
+            sw += w;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            ax += __shfl_down_sync(0xffffffffu, ax, o); ay += __shfl_down_sync(0xffffffffu, ay, o);
+            az += __shfl_down_sync(0xffffffffu, az, o); sw += __shfl_down_sync(0xffffffffu, sw, o);
+        }
+        if (lane == 0) {
+            float* o = j17 + ((size_t)b * MH_NJR + k) * 3;
+            o[0] = ax + t0 * (1.0f - sw); o[1] = ay + t1 * (1.0f - sw); o[2] = az + t2 * (1.0f - sw);
+        }
+    }
+}
+
+int mh_smpl_forward_all(mh_ctx* c, int first_body, int n_bodies, bool per_body_shape, const float* betas_dev,
+                        const float* theta_dev, const float* trans_dev, const float* xscale_dev, float* verts_out,
+                        float* j17_out, int* lowidx_out, cudaStream_t st) {
+    // theta_dev / trans_dev / outputs are indexed by ABSOLUTE body (first_body .. first_body + n_bodies)
+    const int rows = per_body_shape ? (first_body + n_bodies) : c->d.N;
+    if (rows > c->vshaped_rows) MH_FAIL(c, MH_E_ARG, "smpl forward: %d shape rows exceed capacity %lld", rows, (long long)c->vshaped_rows);
+    k_shape_prep<<<dim3(mh_cdiv(MH_LD3V, 256), rows), 256, 0, st>>>(betas_dev, rows, c->vtemplate, c->pext, c->vshaped);
+    MH_LAUNCHED(c);
+    k_joint_prep<<<mh_cdiv(rows * 72, 128), 128, 0, st>>>(betas_dev, rows, c->Jt, c->Js, c->Jrest);
+    MH_LAUNCHED(c);
+    const int nb = first_body + n_bodies;
+    k_pose_prep<<<mh_cdiv(nb, 64), 64, 0, st>>>(theta_dev, c->Jrest, nb, c->d.N, per_body_shape ? 1 : 0, c->A, c->pf);
+    MH_LAUNCHED(c);
+    k_gemm_fwd<<<dim3(MH_LD3V / GF_BN, mh_cdiv(nb, GF_BM)), 256, 0, st>>>(c->pf, c->pext, c->vshaped, c->vposed, nb, c->d.N,
+                                                                          per_body_shape ? 1 : 0);
+    MH_LAUNCHED(c);
+    k_skin_fwd<<<n_bodies, 256, 0, st>>>(c->vposed, c->A, c->wj, c->ww, c->KW, trans_dev, xscale_dev, c->d.N, c->rptr,
+                                         c->rvert, c->rw, verts_out, j17_out, lowidx_out, first_body);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward
+// -------------------------------------------------------------------------------------------------
+// one CTA per LOCAL body.  dverts (dL/dV) is overwritten in place by dL/dv_posed.
+__global__ void __launch_bounds__(256) k_skin_bwd(float* __restrict__ dverts, const float* __restrict__ vposed,
+                                                  const float* __restrict__ A, const uint8_t* __restrict__ wj,
+                                                  const float* __restrict__ ww, int KW, const int* __restrict__ jptr,
+                                                  const int* __restrict__ jvert, const float* __restrict__ jw,
+                                                  const float* __restrict__ xscale, int N, float* __restrict__ dA,
+                                                  float* __restrict__ gT, int first_body) {
+    const int b = first_body + blockIdx.x;
+    __shared__ float sA[288];
+    __shared__ float sred[8][4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 288; i += 256) sA[i] = A[(size_t)b * 288 + i];
+    const float s = powf(1.1f, xscale[b % N]);
+    float* dv = dverts + (size_t)b * MH_LD3V;
+    const float* vp = vposed + (size_t)b * MH_LD3V;
+    // phase 1: dA_j = sum_i W_ij (s dV_i) [v_posed_i ; 1]^T   -- segmented warp-shuffle reduction per joint
+    for (int j = warp; j < MH_NJ; j += 8) {
+        float acc[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+        for (int e = jptr[j] + lane; e < jptr[j + 1]; e += 32) {
+            const int v = jvert[e];
+            const float w = jw[e] * s;
+            const float g0 = w * dv[3 * v], g1 = w * dv[3 * v + 1], g2 = w * dv[3 * v + 2];
+            const float x = vp[3 * v], y = vp[3 * v + 1], z = vp[3 * v + 2];
+            acc[0] = fmaf(g0, x, acc[0]); acc[1] = fmaf(g0, y, acc[1]); acc[2] = fmaf(g0, z, acc[2]); acc[3] += g0;
+            acc[4] = fmaf(g1, x, acc[4]); acc[5] = fmaf(g1, y, acc[5]); acc[6] = fmaf(g1, z, acc[6]); acc[7] += g1;
+            acc[8] = fmaf(g2, x, acc[8]); acc[9] = fmaf(g2, y, acc[9]); acc[10] = fmaf(g2, z, acc[10]); acc[11] += g2;
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e)
+            for (int o = 16; o > 0; o >>= 1) acc[e] += __shfl_down_sync(0xffffffffu, acc[e], o);
+        if (lane == 0)
+            for (int e = 0; e < 12; ++e) dA[((size_t)b * MH_NJ + j) * 12 + e] = acc[e];
+    }
+    __syncthreads();
+    // phase 2: per vertex  dv_posed = (sum_j W_ij A_j.R)^T (s dV) ; sum dV ; sum <dV, v_local>
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, ss = 0.f;
+    for (int v = tid; v < V_; v += 256) {
+        float Tm[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Tm[e] = 0.f;
+        for (int q = 0; q < KW; ++q) {
+            const float w = ww[(size_t)v * KW + q];
+            const float* a = sA + 12 * wj[(size_t)v * KW + q];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) Tm[e] = fmaf(w, a[e], Tm[e]);
+        }
+        const float d0 = dv[3 * v], d1 = dv[3 * v + 1], d2 = dv[3 * v + 2];
+        const float x = vp[3 * v], y = vp[3 * v + 1], z = vp[3 * v + 2];
+        const float lx = Tm[0] * x + Tm[1] * y + Tm[2] * z + Tm[3];
+        const float ly = Tm[4] * x + Tm[5] * y + Tm[6] * z + Tm[7];
+        const float lz = Tm[8] * x + Tm[9] * y + Tm[10] * z + Tm[11];
+        s0 += d0; s1 += d1; s2 += d2; ss += d0 * lx + d1 * ly + d2 * lz;
+        const float g0 = s * d0, g1 = s * d1, g2 = s * d2;
+        dv[3 * v] = Tm[0] * g0 + Tm[4] * g1 + Tm[8] * g2;
+        dv[3 * v + 1] = Tm[1] * g0 + Tm[5] * g1 + Tm[9] * g2;
+        dv[3 * v + 2] = Tm[2] * g0 + Tm[6] * g1 + Tm[10] * g2;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, o); s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o); ss += __shfl_down_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) { sred[warp][0] = s0; sred[warp][1] = s1; sred[warp][2] = s2; sred[warp][3] = ss; }
+    __syncthreads();
+    if (tid < 4) {
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += sred[w][tid];
+        gT[(size_t)b * 4 + tid] = a;
+    }
+}
+
+// D_part[ks][m][n] = sum_{k in split ks} E[m][k] Bext[n][k]      M = local bodies, N = MH_NEXT, K = MH_LD3V
+#define GB_BM 64
+#define GB_BK 16
+#define GB_KLEN (MH_LD3V / MH_KSPLIT)
+static_assert(MH_LD3V % MH_KSPLIT == 0 && GB_KLEN % GB_BK == 0, "split-K must tile the padded row");
+__global__ void __launch_bounds__(256) k_gemm_bwd(const float* __restrict__ E, const float* __restrict__ Bext,
+                                                  float* __restrict__ Dpart, int M, int first_body, int nb_total) {
+    __shared__ __align__(16) float As[GB_BK][GB_BM];
+    __shared__ float Bs[GB_BK][MH_NEXT + 1];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * GB_BM;
+    const int ks = blockIdx.y;
+    const int kbeg = ks * GB_KLEN;
+    const int ty = tid / 32, tx = tid % 32;
+    float acc[8][7];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
+    for (int k0 = kbeg; k0 < kbeg + GB_KLEN; k0 += GB_BK) {
+        {
+            const int m = tid / 4, k4 = (tid % 4) * 4;
+            float4 a = (m0 + m < M) ? *reinterpret_cast<const float4*>(E + (size_t)(first_body + m0 + m) * MH_LD3V + k0 + k4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            As[k4][m] = a.x; As[k4 + 1][m] = a.y; As[k4 + 2][m] = a.z; As[k4 + 3][m] = a.w;
+        }
+        for (int idx = tid; idx < MH_NEXT * 4; idx += 256) {
+            const int n = idx / 4, k4 = (idx % 4) * 4;
+            const float4 bq = *reinterpret_cast<const float4*>(Bext + (size_t)n * MH_LD3V + k0 + k4);
+            Bs[k4][n] = bq.x; Bs[k4 + 1][n] = bq.y; Bs[k4 + 2][n] = bq.z; Bs[k4 + 3][n] = bq.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GB_BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) bv[j] = (tx + 32 * j < MH_NEXT) ? Bs[k][tx + 32 * j] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 7; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= M) continue;
+        float* o = Dpart + ((size_t)ks * nb_total + first_body + m) * MH_NEXT;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (tx + 32 * j < MH_NEXT) o[tx + 32 * j] = acc[i][j];
+    }
+}
+
+__global__ void k_reduce_partials(const float* __restrict__ Dpart, float* __restrict__ D, int first_body, int M, int nb_total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * MH_NEXT) return;
+    const int64_t o = (int64_t)first_body * MH_NEXT + i;
+    float a = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < MH_KSPLIT; ++ks) a += Dpart[(size_t)ks * nb_total * MH_NEXT + o];
+    D[o] = a;       // D aliases split 0 after the reduction? no: separate region, see caller
+}
+
+// one thread per local body: chain + Rodrigues backward, gradients into the flat gradient buffer
+__global__ void k_pose_bwd(const float* __restrict__ theta_all, const float* __restrict__ Jrest, const float* __restrict__ dA,
+                           const float* __restrict__ dpf, const float* __restrict__ gT, const float* __restrict__ Js,
+                           const float* __restrict__ xscale, int N, int T, float* __restrict__ g_trans,
+                           float* __restrict__ g_theta, float* __restrict__ g_betas, float* __restrict__ g_xscale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // local person-frame index t*N + n
+    if (i >= T * N) return;
+    const int b = i + N;                                      // slot-major body index (slot 0 is the halo)
+    const int n = i % N;
+    float th[72], J[72], dAl[288], dpfl[207], dth[72], dJ[72];
+    for (int e = 0; e < 72; ++e) { th[e] = theta_all[(size_t)b * 72 + e]; J[e] = Jrest[(size_t)n * 72 + e]; }
+    for (int e = 0; e < 288; ++e) dAl[e] = dA[(size_t)b * 288 + e];
+    const float* dp = dpf + (size_t)b * MH_NEXT;
+    for (int e = 0; e < 207; ++e) dpfl[e] = (e < MH_NPF_LIVE) ? dp[e] : 0.f;
+    mh_pose_backward(th, J, dAl, dpfl, dth, dJ);
+    for (int e = 0; e < 72; ++e) g_theta[(size_t)i * 72 + e] += dth[e];
+    g_trans[(size_t)i * 3] += gT[(size_t)b * 4]; g_trans[(size_t)i * 3 + 1] += gT[(size_t)b * 4 + 1];
+    g_trans[(size_t)i * 3 + 2] += gT[(size_t)b * 4 + 2];
+    // beta: shape-blend path (rows 192..201 of the extended basis) + rest-joint path
+    for (int l = 0; l < MH_NBETA; ++l) {
+        float a = dp[MH_KPF + l];
+        for (int e = 0; e < 72; ++e) a = fmaf(Js[e * MH_NBETA + l], dJ[e], a);
+        atomicAdd(g_betas + n * MH_NBETA + l, a);
+    }
+    const float s = powf(1.1f, xscale[n]);
+    atomicAdd(g_xscale + n, 0.09531017980432493f * s * gT[(size_t)b * 4 + 3]);     // d(1.1^x)/dx = ln(1.1) 1.1^x
+}
+
+int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st) {
+    const int N = c->d.N, T = c->d.T;
+    const int M = T * N, first = N;
+    const float* xs = c->params + c->off[MH_P_XSCALE];
+    k_skin_bwd<<<M, 256, 0, st>>>(c->dverts, c->vposed, c->A, c->wj, c->ww, c->KW, c->jptr, c->jvert, c->jw, xs, N, c->dA,
+                                  c->gT, first);
+    MH_LAUNCHED(c);
+    k_gemm_bwd<<<dim3(mh_cdiv(M, GB_BM), MH_KSPLIT), 256, 0, st>>>(c->dverts, c->pext, c->dpf_part, M, first, c->nb);
+    MH_LAUNCHED(c);
+    float* dpf = c->dpf_part + (size_t)MH_KSPLIT * c->nb * MH_NEXT;       // reduced copy lives after the partials
+    k_reduce_partials<<<mh_cdiv((int64_t)M * MH_NEXT, 256), 256, 0, st>>>(c->dpf_part, dpf, first, M, c->nb);
+    MH_LAUNCHED(c);
+    k_pose_bwd<<<mh_cdiv(M, 32), 32, 0, st>>>(c->theta_all, c->Jrest, c->dA, dpf, c->gT, c->Js, xs, N, T,
+                                              c->grads + c->off[MH_P_POSES_T], c->grads + c->off[MH_P_POSES_SMPL],
+                                              c->grads + c->off[MH_P_BETAS], c->grads + c->off[MH_P_XSCALE]);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
