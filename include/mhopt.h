@@ -98,8 +98,9 @@ enum {
     MH_BUF_CARRY_OUT = 3,  /* One-Euro state after this rank's last frame: x_prev, dx_prev for T and verts */
     MH_BUF_CARRY_IN = 4,   /* same layout, state handed over by the previous rank */
     MH_BUF_GRADS = 5,      /* the whole flat gradient buffer (tests) */
-    MH_BUF_VERTS = 6,      /* (T+2, N, V, 3) posed vertices of the last forward incl. halo slots (tests) */
-    MH_BUF_FILTERED = 7    /* (T+2, N, V, 3) filtered vertices (optimizer.py:390-392) incl. halo slots */
+    MH_BUF_VERTS = 6,      /* (T+2, N, 20672) posed vertices of the last forward incl. halo slots; rows padded to 20672 floats */
+    MH_BUF_FILTERED = 7,   /* (T+2, N, 20672) filtered vertices (optimizer.py:390-392) incl. halo slots; rows padded to 20672 floats */
+    MH_BUF_PARAMS = 8      /* flat parameter buffer [poses_T | poses_smpl | zmin_lin | zmax_lin | betas | xscale] */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -108,17 +109,25 @@ void mh_destroy(mh_ctx* ctx);
 const char* mh_last_error(const mh_ctx* ctx);
 const char* mh_version(void);
 
+/* frames per dataloader batch: SEMANTIC (optimizer.py:512-518, 526, 531-542); may be changed before fit() */
+int mh_set_batch(mh_ctx* ctx, int32_t B);
+
 /* ---- constant inputs ------------------------------------------------------------------------- */
 /* SMPLOptimizerBase.__init__ (optimizer.py:64-75): uploads the model and builds the sparse forms. */
 int mh_set_model(mh_ctx* ctx, const mh_model* model_host);
 /* cam_K (optimizer.py:193-200), the PyTorch3D NDC matrix of transforms.py:222-255 (optimizer.py:206), Kd (:200) */
 int mh_set_camera(mh_ctx* ctx, const float K3x3_host[9], const float Kndc4x4_host[16], const float* Kd5_host_or_null);
 int mh_set_coefs(mh_ctx* ctx, const mh_coefs* coefs);
+/* pose17j_weights AFTER the normalisation of optimizer.py:127-130 (17 floats; default all 1) */
+int mh_set_joint_weights(mh_ctx* ctx, const float* w17_host);
+/* 0: xscale_factor is fixed (scale_factor given to init_optimized_variables, optimizer.py:279-282, 350-353) */
+int mh_set_optimize_scale(mh_ctx* ctx, int32_t on);
 
 /* One dataloader batch (optimizer.py:394-400; keys of datautils.py:630-641), frames
  * [t_local0, t_local0 + count): depths (count,H,W), seg_mask (count,N,H,W), pose2d (count,N,17,3),
  * poses_smpl reference (count,N,72), valid_smpl (count,N) already thresholded > 0.7 (optimizer.py:299).
- * HOST pointers; the copy is asynchronous on `stream` (keep the buffers alive until it completes). */
+ * HOST pointers; the copy is asynchronous on `stream` (keep the buffers alive until it completes).
+ * depths_host / seg_host may be NULL (planes already on the device, e.g. after mh_synth_planes). */
 int mh_ingest_frames(mh_ctx* ctx, int32_t t_local0, int32_t count, const float* depths_host,
                      const float* seg_host, const float* pose2d_host, const float* theta_ref_host,
                      const float* valid_host, void* stream);
@@ -153,7 +162,7 @@ int mh_init_begin(mh_ctx* ctx, const float* pose2d_host, const float* theta_host
                   float joints_thr, void* stream);
 /* one Adam iteration on poses_T (lr, betas (0.5,0.5), eps 1e-6; bias-corrected); writes loss_2d into
  * losses[MH_L_INIT_2D] (sum of squares over local frames; the caller divides by T_total*N*17*2). */
-int mh_init_grads(mh_ctx* ctx, void* stream);
+int mh_init_grads(mh_ctx* ctx, int32_t use_halo_prev, int32_t use_halo_next, void* stream);
 int mh_init_update(mh_ctx* ctx, float lr, int32_t step_1based, void* stream);
 
 /* ---- hot loop B: one cycle of fit() (optimizer.py:375-593) ------------------------------------- */
@@ -173,10 +182,18 @@ int mh_read_losses(mh_ctx* ctx, float* out16_host, void* stream);
 int mh_refresh_filters(mh_ctx* ctx, float min_cutoff1, float beta1, float min_cutoff2, float beta2,
                        float frame_rate, int32_t first, void* stream);
 int mh_clear_filters(mh_ctx* ctx);
+/* marks MH_BUF_FILTERED as valid / invalid when the caller filled it through the device view (teacher-forced tests) */
+int mh_refresh_filters_flag(mh_ctx* ctx, int32_t on);
+/* SMPLDepthSequenceOptimizer.one_euro_filter (optimizer.py:664-675) of a HOST array (T, row_elems); blocking */
+int mh_one_euro_filter(mh_ctx* ctx, const float* x_host, float* y_host, int32_t T, int64_t row_elems, float min_cutoff,
+                       float beta, float frame_rate);
 
 /* ---- scene-geometry inputs (optimizer.py:425-426, 578-584) ------------------------------------- */
 /* per-frame scene depth 1 / target_disp for the current parameters, into a HOST buffer (count,H,W); blocking */
 int mh_scene_depths(mh_ctx* ctx, int32_t t_local0, int32_t count, float* out_host);
+
+/* SMPL forward of every local person-frame with the current parameters into MH_BUF_VERTS (no losses) */
+int mh_forward_only(mh_ctx* ctx, void* stream);
 
 /* ---- debugging / input synthesis ---------------------------------------------------------------- */
 /* renders person n of local frame t with the current parameters: zbuf[...,0] (depth raster, optimizer.py:429-431)

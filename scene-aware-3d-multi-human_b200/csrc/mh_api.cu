@@ -1,0 +1,735 @@
+// C ABI of libmhopt.so (include/mhopt.h): context lifetime, model / camera / frame ingest, parameter
+// access, the fused optimiser updates and the per-cycle entry points.
+//
+// Reference code replaced (paths relative to the reference repo): SMPLOptimizerBase.__init__ and
+// SMPLDepthSequenceOptimizer.__init__ / init_optimized_variables / fit / get_optimized_variables
+// (mhmocap/optimizer.py:35-131, 150-321, 324-602, 619-636); torch.optim.RMSprop / Adam as instantiated at
+// optimizer.py:355-356, 738-739.
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "mh_ctx.h"
+
+#define API_BEGIN(ctx) if (!(ctx)) return MH_E_ARG; cudaSetDevice((ctx)->d.device)
+
+template <typename T>
+static int dev_alloc(mh_ctx* c, T** p, int64_t n) {
+    *p = nullptr;
+    if (n <= 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, (size_t)n * sizeof(T));
+    if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "cudaMalloc(%lld bytes): %s", (long long)(n * sizeof(T)), cudaGetErrorString(e));
+    e = cudaMemset(*p, 0, (size_t)n * sizeof(T));
+    if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
+    c->allocs.push_back((void*)*p);
+    return MH_OK;
+}
+
+template <typename T>
+static int upload(mh_ctx* c, T** p, const std::vector<T>& h) {
+    MH_TRY(dev_alloc(c, p, (int64_t)h.size()));
+    if (!h.empty()) MH_CUDA(c, cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return MH_OK;
+}
+
+extern "C" const char* mh_version(void) { return "mhopt-b200 0.1 (sm_100a)"; }
+
+extern "C" const char* mh_last_error(const mh_ctx* c) { return c ? c->err : "null context"; }
+
+extern "C" int64_t mh_launch_count(const mh_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int mh_set_batch(mh_ctx* c, int32_t B) {
+    if (!c) return MH_E_ARG;
+    const mh_dims& d = c->d;
+    if (B < 1) MH_FAIL(c, MH_E_ARG, "mh_set_batch: batch size %d", B);
+    // foot-sliding pairs never cross a batch (optimizer.py:512-518): shard edges must coincide with batch edges
+    if (d.t0 % B != 0) MH_FAIL(c, MH_E_ARG, "shard start %d is not a multiple of the batch size %d", d.t0, B);
+    if (d.t0 + d.T != d.T_total && d.T % B != 0) MH_FAIL(c, MH_E_ARG, "inner shard length %d is not a multiple of the batch size %d", d.T, B);
+    c->d.B = B;
+    return MH_OK;
+}
+
+extern "C" int mh_create(mh_ctx** out, const mh_dims* dims) {
+    if (!out || !dims) return MH_E_ARG;
+    *out = nullptr;
+    mh_ctx* c = new mh_ctx();
+    c->d = *dims;
+    c->err[0] = 0;
+    c->launches = 0;
+    c->model_set = c->camera_set = c->coefs_set = c->ingested = c->has_filters = c->init_ready = false;
+    c->optim_scale = true;
+    c->rs = nullptr;
+    c->M = 0;
+    for (int k = 0; k < MH_NJR; ++k) c->w17[k] = 1.0f;
+    *out = c;     // returned even on failure so that the caller can read the error text, then mh_destroy
+    const mh_dims& d = c->d;
+    if (d.T < 1 || d.N < 1 || d.N > MH_MAXN || d.H < 1 || d.W < 1 || d.V != MH_V || d.F != MH_F || d.B < 1 || d.world < 1 ||
+        d.rank < 0 || d.rank >= d.world || d.t0 < 0 || d.t0 + d.T > d.T_total || d.M_max < 0)
+        MH_FAIL(c, MH_E_ARG, "mh_create: bad dims (T=%d N=%d H=%d W=%d V=%d F=%d B=%d rank=%d/%d t0=%d T_total=%d)", d.T, d.N, d.H,
+                d.W, d.V, d.F, d.B, d.rank, d.world, d.t0, d.T_total);
+    MH_TRY(mh_set_batch(c, d.B));
+    MH_CUDA(c, cudaSetDevice(d.device));
+    cudaDeviceProp prop;
+    MH_CUDA(c, cudaGetDeviceProperties(&prop, d.device));
+    c->num_sms = prop.multiProcessorCount;
+    c->Ts = d.T + 2;
+    c->nb = c->Ts * d.N;
+    const int64_t TN = (int64_t)d.T * d.N, HW = (int64_t)d.H * d.W, nb = c->nb;
+    // parameter layout
+    int64_t o = 0;
+    c->off[MH_P_POSES_T] = o;    c->cnt[MH_P_POSES_T] = TN * 3;     o += TN * 3;
+    c->off[MH_P_POSES_SMPL] = o; c->cnt[MH_P_POSES_SMPL] = TN * 72; o += TN * 72;
+    c->off[MH_P_ZMIN_LIN] = o;   c->cnt[MH_P_ZMIN_LIN] = d.T;       o += d.T;
+    c->off[MH_P_ZMAX_LIN] = o;   c->cnt[MH_P_ZMAX_LIN] = d.T;       o += d.T;
+    c->off[MH_P_BETAS] = o;      c->cnt[MH_P_BETAS] = d.N * 10;     o += d.N * 10;
+    c->off[MH_P_XSCALE] = o;     c->cnt[MH_P_XSCALE] = d.N;         o += d.N;
+    c->off[MH_P_BETAS_REF] = -1; c->cnt[MH_P_BETAS_REF] = d.N * 10;
+    c->n_params = o;
+    MH_TRY(dev_alloc(c, &c->params, o));
+    MH_TRY(dev_alloc(c, &c->grads, o + MH_L_COUNT));
+    MH_TRY(dev_alloc(c, &c->sqavg, o));
+    MH_TRY(dev_alloc(c, &c->mom, o));
+    MH_TRY(dev_alloc(c, &c->betas_ref, d.N * 10));
+    MH_TRY(dev_alloc(c, &c->halo_send, 2 * d.N * MH_HALO));
+    MH_TRY(dev_alloc(c, &c->halo_recv, 2 * d.N * MH_HALO));
+    MH_TRY(dev_alloc(c, &c->depth, d.T * HW));
+    MH_TRY(dev_alloc(c, &c->cbits, d.T * HW));
+    MH_TRY(dev_alloc(c, &c->ebits, d.T * HW));
+    c->stage = nullptr; c->stage_floats = 0;
+    MH_TRY(dev_alloc(c, &c->pose2d, TN * 17 * 3));
+    MH_TRY(dev_alloc(c, &c->theta_ref, TN * 72));
+    MH_TRY(dev_alloc(c, &c->valid, TN));
+    MH_TRY(dev_alloc(c, &c->maskarea, TN));
+    MH_TRY(dev_alloc(c, &c->pose2d_valid, TN));
+    MH_TRY(dev_alloc(c, &c->mask_valid, TN));
+    MH_TRY(dev_alloc(c, &c->devflags, 8));
+    MH_TRY(dev_alloc(c, &c->init_j17, TN * 17 * 3));
+    MH_TRY(dev_alloc(c, &c->init_vis, TN * 17));
+    MH_TRY(dev_alloc(c, &c->adam_m, TN * 3));
+    MH_TRY(dev_alloc(c, &c->adam_v, TN * 3));
+    MH_TRY(dev_alloc(c, &c->theta_all, nb * 72));
+    MH_TRY(dev_alloc(c, &c->trans_all, nb * 3));
+    MH_TRY(dev_alloc(c, &c->vshaped, (int64_t)d.N * MH_LD3V));
+    MH_TRY(dev_alloc(c, &c->Jrest, nb * 72));
+    MH_TRY(dev_alloc(c, &c->A, nb * 288));
+    MH_TRY(dev_alloc(c, &c->pf, nb * MH_KPF));
+    MH_TRY(dev_alloc(c, &c->vposed, nb * MH_LD3V));
+    MH_TRY(dev_alloc(c, &c->verts, nb * MH_LD3V));
+    MH_TRY(dev_alloc(c, &c->dverts, nb * MH_LD3V));
+    MH_TRY(dev_alloc(c, &c->filtered, nb * MH_LD3V));
+    MH_TRY(dev_alloc(c, &c->j17, nb * 17 * 3));
+    MH_TRY(dev_alloc(c, &c->gj17, nb * 17 * 3));
+    MH_TRY(dev_alloc(c, &c->lowidx, nb));
+    MH_TRY(dev_alloc(c, &c->dA, nb * 288));
+    MH_TRY(dev_alloc(c, &c->gT, nb * 4));
+    MH_TRY(dev_alloc(c, &c->dpf_part, (int64_t)(MH_KSPLIT + 1) * nb * MH_NEXT));
+    MH_TRY(dev_alloc(c, &c->order, TN));
+    MH_TRY(dev_alloc(c, &c->premask, TN));
+    MH_TRY(dev_alloc(c, &c->dirty, d.T));
+    MH_TRY(dev_alloc(c, &c->rankcnt, (int64_t)d.T * (d.N + 1)));
+    MH_TRY(dev_alloc(c, &c->pfout, TN * PF_COUNT));
+    MH_TRY(dev_alloc(c, &c->scene, std::max<int64_t>(d.M_max, 1) * 3));
+    MH_TRY(dev_alloc(c, &c->contact, TN * 4));
+    c->carry_floats = 2 * ((int64_t)d.N * MH_LD3V + d.N * 3);
+    MH_TRY(dev_alloc(c, &c->carry_in, c->carry_floats));
+    MH_TRY(dev_alloc(c, &c->carry_out, c->carry_floats));
+    MH_TRY(dev_alloc(c, &c->transfilt, TN * 3));
+    MH_TRY(dev_alloc(c, &c->pix_x, d.W));
+    MH_TRY(dev_alloc(c, &c->pix_y, d.H));
+    // order starts as "unknown" so that the first prepass recomputes every frame
+    MH_CUDA(c, cudaMemset(c->order, 0xff, TN * sizeof(int)));
+    MH_TRY(mh_render_alloc(c));
+    MH_CUDA(c, cudaDeviceSynchronize());
+    return MH_OK;
+}
+
+extern "C" void mh_destroy(mh_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->d.device);
+    cudaDeviceSynchronize();
+    mh_render_free(c);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->stage) cudaFree(c->stage);
+    delete c;
+}
+
+// ---- model --------------------------------------------------------------------------------------
+extern "C" int mh_set_model(mh_ctx* c, const mh_model* m) {
+    API_BEGIN(c);
+    if (!m || !m->v_template || !m->shapedirs || !m->posedirs || !m->J_regressor || !m->lbs_weights || !m->parents || !m->faces ||
+        !m->reg17)
+        MH_FAIL(c, MH_E_ARG, "mh_set_model: null buffer");
+    static const int want[MH_NJ] = MH_PARENTS;
+    for (int j = 0; j < MH_NJ; ++j)
+        if (m->parents[j] != want[j]) MH_FAIL(c, MH_E_ARG, "mh_set_model: parents[%d] = %d, the SMPL tree has %d", j, m->parents[j], want[j]);
+    const int V = MH_V;
+    // extended basis: rows 0..188 live posedirs, 192..201 shapedirs (transposed to (l, 3v+k))
+    std::vector<float> pext((size_t)MH_NEXT * MH_LD3V, 0.f);
+    for (int r = 0; r < MH_NPF_LIVE; ++r) memcpy(&pext[(size_t)r * MH_LD3V], m->posedirs + (size_t)r * 3 * V, sizeof(float) * 3 * V);
+    for (int v = 0; v < V; ++v)
+        for (int k = 0; k < 3; ++k)
+            for (int l = 0; l < MH_NBETA; ++l) pext[(size_t)(MH_KPF + l) * MH_LD3V + 3 * v + k] = m->shapedirs[((size_t)v * 3 + k) * MH_NBETA + l];
+    std::vector<float> vt(MH_LD3V, 0.f);
+    memcpy(vt.data(), m->v_template, sizeof(float) * 3 * V);
+    // closed form of the rest joints: J = J_regressor.v_template + (J_regressor.shapedirs).beta  (smpl.py:532-535)
+    std::vector<float> Jt(72, 0.f), Js(720, 0.f);
+    for (int j = 0; j < MH_NJ; ++j) {
+        double at[3] = {0, 0, 0};
+        double as[3][MH_NBETA] = {{0}};
+        for (int v = 0; v < V; ++v) {
+            const float w = m->J_regressor[(size_t)j * V + v];
+            if (w == 0.f) continue;
+            for (int k = 0; k < 3; ++k) {
+                at[k] += (double)w * m->v_template[3 * v + k];
+                for (int l = 0; l < MH_NBETA; ++l) as[k][l] += (double)w * m->shapedirs[((size_t)v * 3 + k) * MH_NBETA + l];
+            }
+        }
+        for (int k = 0; k < 3; ++k) {
+            Jt[3 * j + k] = (float)at[k];
+            for (int l = 0; l < MH_NBETA; ++l) Js[(3 * j + k) * MH_NBETA + l] = (float)as[k][l];
+        }
+    }
+    // sparse skinning weights (exact: zero weights contribute nothing)
+    int KW = 1;
+    for (int v = 0; v < V; ++v) {
+        int n = 0;
+        for (int j = 0; j < MH_NJ; ++j) n += (m->lbs_weights[(size_t)v * MH_NJ + j] != 0.f);
+        KW = std::max(KW, n);
+    }
+    std::vector<uint8_t> wj((size_t)V * KW, 0);
+    std::vector<float> ww((size_t)V * KW, 0.f);
+    std::vector<int> jptr(MH_NJ + 1, 0), jvert;
+    std::vector<float> jw;
+    for (int v = 0; v < V; ++v) {
+        int q = 0;
+        for (int j = 0; j < MH_NJ; ++j) {
+            const float w = m->lbs_weights[(size_t)v * MH_NJ + j];
+            if (w != 0.f) { wj[(size_t)v * KW + q] = (uint8_t)j; ww[(size_t)v * KW + q] = w; ++q; }
+        }
+    }
+    for (int j = 0; j < MH_NJ; ++j) {
+        for (int v = 0; v < V; ++v) {
+            const float w = m->lbs_weights[(size_t)v * MH_NJ + j];
+            if (w != 0.f) { jvert.push_back(v); jw.push_back(w); }
+        }
+        jptr[j + 1] = (int)jvert.size();
+    }
+    // 17-joint regressor: CSR (joint -> vertices) and CSC (vertex -> joints)
+    std::vector<int> rptr(MH_NJR + 1, 0), rvert, cptr(V + 1, 0), cjoint;
+    std::vector<float> rw, cw;
+    for (int k = 0; k < MH_NJR; ++k) {
+        for (int v = 0; v < V; ++v) {
+            const float w = m->reg17[(size_t)k * V + v];
+            if (w != 0.f) { rvert.push_back(v); rw.push_back(w); }
+        }
+        rptr[k + 1] = (int)rvert.size();
+    }
+    for (int v = 0; v < V; ++v) {
+        for (int k = 0; k < MH_NJR; ++k) {
+            const float w = m->reg17[(size_t)k * V + v];
+            if (w != 0.f) { cjoint.push_back(k); cw.push_back(w); }
+        }
+        cptr[v + 1] = (int)cjoint.size();
+    }
+    for (int f = 0; f < MH_F * 3; ++f)
+        if (m->faces[f] < 0 || m->faces[f] >= V) MH_FAIL(c, MH_E_ARG, "mh_set_model: face index %d out of range", m->faces[f]);
+    std::vector<int32_t> faces(m->faces, m->faces + (size_t)MH_F * 3);
+    c->KW = KW; c->jnnz = (int)jvert.size(); c->rnnz = (int)rvert.size();
+    MH_TRY(upload(c, &c->pext, pext));
+    MH_TRY(upload(c, &c->vtemplate, vt));
+    MH_TRY(upload(c, &c->Jt, Jt));
+    MH_TRY(upload(c, &c->Js, Js));
+    MH_TRY(upload(c, &c->wj, wj));
+    MH_TRY(upload(c, &c->ww, ww));
+    MH_TRY(upload(c, &c->jptr, jptr));
+    MH_TRY(upload(c, &c->jvert, jvert));
+    MH_TRY(upload(c, &c->jw, jw));
+    MH_TRY(upload(c, &c->rptr, rptr));
+    MH_TRY(upload(c, &c->rvert, rvert));
+    MH_TRY(upload(c, &c->rw, rw));
+    MH_TRY(upload(c, &c->cptr, cptr));
+    MH_TRY(upload(c, &c->cjoint, cjoint));
+    MH_TRY(upload(c, &c->cw, cw));
+    MH_TRY(upload(c, &c->faces, faces));
+    c->model_set = true;
+    return MH_OK;
+}
+
+// NDC coordinate of pixel-centre index i on an axis of S1 pixels (S2 = the other axis): PyTorch3D's
+// non-square convention, evaluated in fp32 exactly like oracle.raster.pixel_centers_ndc.
+static float ndc_center(int i, int S1, int S2) {
+    const float r = (S1 > S2) ? (float)(2.0 * S1 / S2) : 2.0f;
+    const float half = r / 2.0f;
+    const float a = r * (float)i;
+    const float b = a + half;
+    const float q = b / (float)S1;
+    return -half + q;
+}
+
+extern "C" int mh_set_camera(mh_ctx* c, const float K[9], const float Kndc[16], const float* Kd) {
+    API_BEGIN(c);
+    if (!K || !Kndc) MH_FAIL(c, MH_E_ARG, "mh_set_camera: null matrix");
+    memcpy(c->K, K, sizeof(float) * 9);
+    memcpy(c->Kndc, Kndc, sizeof(float) * 16);
+    c->has_kd = Kd != nullptr;
+    if (Kd) memcpy(c->Kd, Kd, sizeof(float) * 5);
+    const int W = c->d.W, H = c->d.H;
+    std::vector<float> px(W), py(H);
+    for (int x = 0; x < W; ++x) px[x] = ndc_center(W - 1 - x, W, H);
+    for (int y = 0; y < H; ++y) py[y] = ndc_center(H - 1 - y, H, W);
+    MH_CUDA(c, cudaMemcpy(c->pix_x, px.data(), sizeof(float) * W, cudaMemcpyHostToDevice));
+    MH_CUDA(c, cudaMemcpy(c->pix_y, py.data(), sizeof(float) * H, cudaMemcpyHostToDevice));
+    c->camera_set = true;
+    return MH_OK;
+}
+
+extern "C" int mh_set_joint_weights(mh_ctx* c, const float* w) {
+    API_BEGIN(c);
+    if (!w) MH_FAIL(c, MH_E_ARG, "mh_set_joint_weights: null");
+    memcpy(c->w17, w, sizeof(c->w17));
+    return MH_OK;
+}
+
+extern "C" int mh_set_coefs(mh_ctx* c, const mh_coefs* k) {
+    API_BEGIN(c);
+    if (!k) MH_FAIL(c, MH_E_ARG, "mh_set_coefs: null");
+    c->c = *k;
+    c->coefs_set = true;
+    return MH_OK;
+}
+
+// ---- frames -------------------------------------------------------------------------------------
+extern "C" int mh_ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* depths, const float* seg, const float* pose2d,
+                                const float* theta_ref, const float* valid, void* stream) {
+    API_BEGIN(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const mh_dims& d = c->d;
+    if (t0 < 0 || count < 1 || t0 + count > d.T) MH_FAIL(c, MH_E_ARG, "mh_ingest_frames: frames [%d, %d) outside [0, %d)", t0, t0 + count, d.T);
+    if (!pose2d || !theta_ref || !valid) MH_FAIL(c, MH_E_ARG, "mh_ingest_frames: null buffer");
+    const int64_t HW = (int64_t)d.H * d.W, need = (int64_t)count * d.N * HW;
+    if (seg && need > c->stage_floats) {
+        MH_CUDA(c, cudaStreamSynchronize(st));
+        if (c->stage) cudaFree(c->stage);
+        c->stage = nullptr; c->stage_floats = 0;
+        MH_CUDA(c, cudaMalloc((void**)&c->stage, need * sizeof(float)));
+        c->stage_floats = need;
+    }
+    if (depths) MH_CUDA(c, cudaMemcpyAsync(c->depth + (int64_t)t0 * HW, depths, sizeof(float) * count * HW, cudaMemcpyHostToDevice, st));
+    if (seg) MH_CUDA(c, cudaMemcpyAsync(c->stage, seg, sizeof(float) * need, cudaMemcpyHostToDevice, st));
+    MH_CUDA(c, cudaMemcpyAsync(c->pose2d + (int64_t)t0 * d.N * 51, pose2d, sizeof(float) * count * d.N * 51, cudaMemcpyHostToDevice, st));
+    MH_CUDA(c, cudaMemcpyAsync(c->theta_ref + (int64_t)t0 * d.N * 72, theta_ref, sizeof(float) * count * d.N * 72, cudaMemcpyHostToDevice, st));
+    MH_CUDA(c, cudaMemcpyAsync(c->valid + (int64_t)t0 * d.N, valid, sizeof(float) * count * d.N, cudaMemcpyHostToDevice, st));
+    if (seg) MH_TRY(mh_ingest_compact(c, t0, count, st));
+    return MH_OK;
+}
+
+extern "C" int mh_finalize_ingest(mh_ctx* c, void* stream) {
+    API_BEGIN(c);
+    if (!c->coefs_set) MH_FAIL(c, MH_E_STATE, "mh_finalize_ingest: mh_set_coefs first (the joint confidence threshold is needed)");
+    cudaStream_t st = (cudaStream_t)stream;
+    MH_TRY(mh_ingest_derive(c, st));
+    int flags[8];
+    MH_CUDA(c, cudaMemcpyAsync(flags, c->devflags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    MH_CUDA(c, cudaStreamSynchronize(st));
+    if (flags[0]) MH_FAIL(c, MH_E_ARG, "ingest: seg_mask holds values other than 0 / 1 (instance masks must be binary, utils.py:329-331)");
+    c->ingested = true;
+    return MH_OK;
+}
+
+extern "C" int mh_set_scene(mh_ctx* c, const float* pcd, int64_t M, void* stream) {
+    API_BEGIN(c);
+    if (M < 0 || M > c->d.M_max) MH_FAIL(c, MH_E_CAPACITY, "mh_set_scene: %lld points exceed M_max = %lld", (long long)M, (long long)c->d.M_max);
+    if (M > 0 && M < MH_KNN) MH_FAIL(c, MH_E_ARG, "mh_set_scene: the contact term needs at least %d scene points", MH_KNN);
+    if (M > 0) {
+        if (!pcd) MH_FAIL(c, MH_E_ARG, "mh_set_scene: null cloud");
+        MH_CUDA(c, cudaMemcpyAsync(c->scene, pcd, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    }
+    c->M = M;
+    return MH_OK;
+}
+
+extern "C" int mh_set_scene_from_depth(mh_ctx* c, const float* depth_host, const uint8_t* mask_host, void* stream) {
+    API_BEGIN(c);
+    if (!c->camera_set) MH_FAIL(c, MH_E_STATE, "mh_set_scene_from_depth: mh_set_camera first");
+    if (!depth_host || !mask_host) MH_FAIL(c, MH_E_ARG, "mh_set_scene_from_depth: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t HW = (int64_t)c->d.H * c->d.W;
+    float* dd; uint8_t* dm;
+    MH_CUDA(c, cudaMalloc((void**)&dd, HW * sizeof(float)));
+    MH_CUDA(c, cudaMalloc((void**)&dm, HW));
+    int r = MH_OK;
+    if (cudaMemcpyAsync(dd, depth_host, HW * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(dm, mask_host, HW, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "mh_set_scene_from_depth: copy failed");
+        r = MH_E_CUDA;
+    }
+    if (r == MH_OK) r = mh_scene_from_depth(c, dd, dm, st);
+    cudaStreamSynchronize(st);
+    cudaFree(dd); cudaFree(dm);
+    return r;
+}
+
+// ---- parameters ---------------------------------------------------------------------------------
+static int param_ptr(mh_ctx* c, int which, int64_t count, float** p, bool grad) {
+    if (which < 0 || which >= MH_P_COUNT) MH_FAIL(c, MH_E_ARG, "unknown parameter id %d", which);
+    if (count != c->cnt[which]) MH_FAIL(c, MH_E_ARG, "parameter %d holds %lld floats, caller passed %lld", which, (long long)c->cnt[which], (long long)count);
+    if (which == MH_P_BETAS_REF) {
+        if (grad) MH_FAIL(c, MH_E_ARG, "betas_ref has no gradient");
+        *p = c->betas_ref;
+    } else {
+        *p = (grad ? c->grads : c->params) + c->off[which];
+    }
+    return MH_OK;
+}
+
+extern "C" int mh_set_param(mh_ctx* c, int which, const float* src, int64_t count, void* stream) {
+    API_BEGIN(c);
+    float* p;
+    MH_TRY(param_ptr(c, which, count, &p, false));
+    if (!src) MH_FAIL(c, MH_E_ARG, "mh_set_param: null source");
+    MH_CUDA(c, cudaMemcpyAsync(p, src, sizeof(float) * count, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return MH_OK;
+}
+
+extern "C" int mh_get_param(mh_ctx* c, int which, float* dst, int64_t count) {
+    API_BEGIN(c);
+    float* p;
+    MH_TRY(param_ptr(c, which, count, &p, false));
+    MH_CUDA(c, cudaDeviceSynchronize());
+    MH_CUDA(c, cudaMemcpy(dst, p, sizeof(float) * count, cudaMemcpyDeviceToHost));
+    return MH_OK;
+}
+
+extern "C" int mh_get_grad(mh_ctx* c, int which, float* dst, int64_t count) {
+    API_BEGIN(c);
+    float* p;
+    MH_TRY(param_ptr(c, which, count, &p, true));
+    MH_CUDA(c, cudaDeviceSynchronize());
+    MH_CUDA(c, cudaMemcpy(dst, p, sizeof(float) * count, cudaMemcpyDeviceToHost));
+    return MH_OK;
+}
+
+extern "C" int mh_set_optimize_scale(mh_ctx* c, int32_t on) {
+    API_BEGIN(c);
+    c->optim_scale = on != 0;
+    return MH_OK;
+}
+
+extern "C" int mh_device_view(mh_ctx* c, int which, void** ptr, int64_t* n) {
+    API_BEGIN(c);
+    if (!ptr || !n) MH_FAIL(c, MH_E_ARG, "mh_device_view: null output");
+    const mh_dims& d = c->d;
+    switch (which) {
+        case MH_BUF_SHARED: *ptr = c->grads + c->off[MH_P_BETAS]; *n = d.N * 11 + MH_L_COUNT; break;
+        case MH_BUF_HALO_SEND: *ptr = c->halo_send; *n = 2 * d.N * MH_HALO; break;
+        case MH_BUF_HALO_RECV: *ptr = c->halo_recv; *n = 2 * d.N * MH_HALO; break;
+        case MH_BUF_CARRY_OUT: *ptr = c->carry_out; *n = c->carry_floats; break;
+        case MH_BUF_CARRY_IN: *ptr = c->carry_in; *n = c->carry_floats; break;
+        case MH_BUF_GRADS: *ptr = c->grads; *n = c->n_params + MH_L_COUNT; break;
+        case MH_BUF_VERTS: *ptr = c->verts; *n = (int64_t)c->nb * MH_LD3V; break;
+        case MH_BUF_FILTERED: *ptr = c->filtered; *n = (int64_t)c->nb * MH_LD3V; break;
+        case MH_BUF_PARAMS: *ptr = c->params; *n = c->n_params; break;
+        default: MH_FAIL(c, MH_E_ARG, "mh_device_view: unknown buffer %d", which);
+    }
+    return MH_OK;
+}
+
+// ---- fused optimiser updates -----------------------------------------------------------------------
+// torch.optim.RMSprop(lr, alpha=.5, eps=1e-8, momentum=.9, centered=False) (optimizer.py:355):
+//   v <- alpha v + (1 - alpha) g^2 ; buf <- mu buf + g / (sqrt(v) + eps) ; p <- p - lr buf
+__global__ void k_rmsprop(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, float* __restrict__ buf,
+                          int64_t n, int64_t skip_lo, int64_t skip_hi, float lr, float alpha, float mu, float eps) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (i >= skip_lo && i < skip_hi)) return;
+    const float gi = g[i];
+    const float vi = v[i] * alpha + (1.0f - alpha) * gi * gi;
+    const float bi = buf[i] * mu + gi / (sqrtf(vi) + eps);
+    v[i] = vi; buf[i] = bi;
+    p[i] = p[i] - lr * bi;
+}
+
+// torch.optim.Adam(lr, betas=(b1, b2), eps) with bias correction (optimizer.py:738)
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                       float step_size, float b1, float b2, float inv_sqrt_bc2, float eps) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i];
+    const float mi = m[i] + (1.0f - b1) * (gi - m[i]);          // lerp_
+    const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+}
+
+extern "C" int mh_reset_optimizer(mh_ctx* c, void* stream) {
+    API_BEGIN(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    MH_CUDA(c, cudaMemsetAsync(c->sqavg, 0, sizeof(float) * c->n_params, st));
+    MH_CUDA(c, cudaMemsetAsync(c->mom, 0, sizeof(float) * c->n_params, st));
+    return MH_OK;
+}
+
+extern "C" int mh_fit_update(mh_ctx* c, float lr, void* stream) {
+    API_BEGIN(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t lo = 0, hi = 0;
+    if (!c->optim_scale) { lo = c->off[MH_P_XSCALE]; hi = lo + c->d.N; }      // "Not optimizing scale_factor" (optimizer.py:350-353)
+    k_rmsprop<<<mh_cdiv(c->n_params, 256), 256, 0, st>>>(c->params, c->grads, c->sqavg, c->mom, c->n_params, lo, hi, lr, 0.5f, 0.9f, 1e-8f);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+extern "C" int mh_init_update(mh_ctx* c, float lr, int32_t step, void* stream) {
+    API_BEGIN(c);
+    if (step < 1) MH_FAIL(c, MH_E_ARG, "mh_init_update: step is 1-based");
+    cudaStream_t st = (cudaStream_t)stream;
+    const double b1 = 0.5, b2 = 0.5;
+    const double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
+    const int64_t n = c->cnt[MH_P_POSES_T];
+    k_adam<<<mh_cdiv(n, 256), 256, 0, st>>>(c->params + c->off[MH_P_POSES_T], c->grads + c->off[MH_P_POSES_T], c->adam_m, c->adam_v, n,
+                                            (float)(lr / bc1), (float)b1, (float)b2, (float)(1.0 / sqrt(bc2)), 1e-6f);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+// ---- SMPL forward utility -----------------------------------------------------------------------
+extern "C" int mh_smpl_forward(mh_ctx* c, const float* betas, const float* theta, int64_t nbodies, float* verts, float* joints17) {
+    API_BEGIN(c);
+    if (!c->model_set) MH_FAIL(c, MH_E_STATE, "mh_smpl_forward: mh_set_model first");
+    if (!betas || !theta || nbodies < 1) MH_FAIL(c, MH_E_ARG, "mh_smpl_forward: bad arguments");
+    cudaStream_t st = 0;
+    // scratch: the per-iteration arrays of the context (overwritten by the next cycle anyway); per-body shapes live in `dverts`
+    const int64_t chunk = c->nb;
+    float* dbetas;
+    MH_CUDA(c, cudaMalloc((void**)&dbetas, sizeof(float) * chunk * 10));
+    std::vector<float> hv;
+    int r = MH_OK;
+    for (int64_t s = 0; s < nbodies && r == MH_OK; s += chunk) {
+        const int n = (int)std::min<int64_t>(chunk, nbodies - s);
+        cudaMemcpyAsync(dbetas, betas + s * 10, sizeof(float) * n * 10, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(c->theta_all, theta + s * 72, sizeof(float) * n * 72, cudaMemcpyHostToDevice, st);
+        MhSmplArgs a = {dbetas, n, 1, c->theta_all, nullptr, nullptr, n, c->d.N, c->dverts, c->Jrest, c->A, c->pf, c->vposed,
+                        c->verts, c->j17, nullptr};
+        r = mh_smpl_forward_run(c, a, st);
+        if (r != MH_OK) break;
+        if (verts) {
+            if (cudaMemcpy2DAsync(verts + s * 3 * MH_V, sizeof(float) * 3 * MH_V, c->verts, sizeof(float) * MH_LD3V, sizeof(float) * 3 * MH_V, n,
+                                  cudaMemcpyDeviceToHost, st) != cudaSuccess) r = MH_E_CUDA;
+        }
+        if (joints17 && cudaMemcpyAsync(joints17 + s * 51, c->j17, sizeof(float) * n * 51, cudaMemcpyDeviceToHost, st) != cudaSuccess) r = MH_E_CUDA;
+        if (cudaStreamSynchronize(st) != cudaSuccess) r = MH_E_CUDA;
+    }
+    cudaFree(dbetas);
+    if (r == MH_E_CUDA && !c->err[0]) snprintf(c->err, sizeof(c->err), "mh_smpl_forward: %s", cudaGetErrorString(cudaGetLastError()));
+    return r;
+}
+
+// ---- hot loop A ---------------------------------------------------------------------------------
+__global__ void k_init_fill(float* __restrict__ poses_T, int64_t n, const float* __restrict__ pose2d, float* __restrict__ vis, int64_t nj,
+                            float thr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) poses_T[i] = (i % 3 == 2) ? 1.0f : 0.0f;                              // optimizer.py:729
+    if (i < nj) vis[i] = pose2d[i * 3 + 2] > thr ? 1.0f : 0.0f;                       // optimizer.py:735
+}
+
+extern "C" int mh_init_begin(mh_ctx* c, const float* pose2d, const float* theta, const float* betas, float joints_thr, void* stream) {
+    API_BEGIN(c);
+    if (!c->model_set || !c->camera_set || !c->coefs_set) MH_FAIL(c, MH_E_STATE, "mh_init_begin: set model, camera and coefficients first");
+    if (!pose2d || !theta || !betas) MH_FAIL(c, MH_E_ARG, "mh_init_begin: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const mh_dims& d = c->d;
+    const int TN = d.T * d.N;
+    float* dbetas;
+    MH_CUDA(c, cudaMalloc((void**)&dbetas, sizeof(float) * TN * 10));
+    MH_CUDA(c, cudaMemcpyAsync(dbetas, betas, sizeof(float) * TN * 10, cudaMemcpyHostToDevice, st));
+    MH_CUDA(c, cudaMemcpyAsync(c->theta_all, theta, sizeof(float) * TN * 72, cudaMemcpyHostToDevice, st));
+    MH_CUDA(c, cudaMemcpyAsync(c->pose2d, pose2d, sizeof(float) * TN * 51, cudaMemcpyHostToDevice, st));
+    // the regressed joints do not depend on the optimised translation: evaluate SMPL once (the reference
+    // re-evaluates it every iteration, optimizer.py:746-748) with the PER-FRAME betas (optimizer.py:733)
+    MhSmplArgs a = {dbetas, TN, 1, c->theta_all, nullptr, nullptr, TN, d.N, c->dverts, c->Jrest, c->A, c->pf, c->vposed, c->verts,
+                    c->init_j17, nullptr};
+    int r = mh_smpl_forward_run(c, a, st);
+    if (r == MH_OK) {
+        k_init_fill<<<mh_cdiv((int64_t)TN * 17, 256), 256, 0, st>>>(c->params + c->off[MH_P_POSES_T], (int64_t)TN * 3, c->pose2d, c->init_vis,
+                                                                  (int64_t)TN * 17, joints_thr);
+        c->launches++;
+        cudaMemsetAsync(c->adam_m, 0, sizeof(float) * TN * 3, st);
+        cudaMemsetAsync(c->adam_v, 0, sizeof(float) * TN * 3, st);
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(dbetas);
+    if (r != MH_OK) return r;
+    MH_CUDA(c, cudaGetLastError());
+    c->init_ready = true;
+    return MH_OK;
+}
+
+extern "C" int mh_init_grads(mh_ctx* c, int32_t use_prev, int32_t use_next, void* stream) {
+    API_BEGIN(c);
+    if (!c->init_ready) MH_FAIL(c, MH_E_STATE, "mh_init_grads: mh_init_begin first");
+    return mh_init_iter_grads(c, use_prev, use_next, (cudaStream_t)stream);
+}
+
+// ---- hot loop B ---------------------------------------------------------------------------------
+__global__ void k_halo_pack(const float* __restrict__ theta, const float* __restrict__ trans, int T, int N, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * N * MH_HALO) return;
+    const int side = i / (N * MH_HALO), r = i % (N * MH_HALO), n = r / MH_HALO, e = r % MH_HALO;
+    const int t = side == 0 ? 0 : T - 1;
+    out[i] = e < 72 ? theta[((size_t)t * N + n) * 72 + e] : trans[((size_t)t * N + n) * 3 + (e - 72)];
+}
+
+extern "C" int mh_halo_pack(mh_ctx* c, void* stream) {
+    API_BEGIN(c);
+    const mh_dims& d = c->d;
+    k_halo_pack<<<mh_cdiv(2 * d.N * MH_HALO, 128), 128, 0, (cudaStream_t)stream>>>(c->params + c->off[MH_P_POSES_SMPL],
+                                                                                  c->params + c->off[MH_P_POSES_T], d.T, d.N, c->halo_send);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+extern "C" int mh_fit_grads(mh_ctx* c, int32_t use_prev, int32_t use_next, void* stream) {
+    API_BEGIN(c);
+    if (!c->model_set || !c->camera_set || !c->coefs_set || !c->ingested)
+        MH_FAIL(c, MH_E_STATE, "mh_fit_grads: set model, camera, coefficients and ingest the frames first");
+    cudaStream_t st = (cudaStream_t)stream;
+    const mh_dims& d = c->d;
+    if (d.t0 == 0) use_prev = 0;
+    if (d.t0 + d.T == d.T_total) use_next = 0;
+    MH_CUDA(c, cudaMemsetAsync(c->grads, 0, sizeof(float) * (c->n_params + MH_L_COUNT), st));
+    MH_TRY(mh_terms_gather(c, use_prev, use_next, st));
+    MhSmplArgs a = {c->params + c->off[MH_P_BETAS], d.N, 0, c->theta_all, c->trans_all, c->params + c->off[MH_P_XSCALE], c->nb, d.N,
+                    c->vshaped, c->Jrest, c->A, c->pf, c->vposed, c->verts, c->j17, c->lowidx};
+    MH_TRY(mh_smpl_forward_run(c, a, st));
+    MH_TRY(mh_terms_pre_raster(c, use_prev, use_next, st));
+    if (c->c.depth != 0.f || c->c.silhouette != 0.f) {
+        MH_TRY(mh_render_prepass(c, st));
+        MH_TRY(mh_render_all(c, st));
+    }
+    MH_TRY(mh_smpl_backward_all(c, st));
+    MH_TRY(mh_terms_post(c, st));
+    return MH_OK;
+}
+
+extern "C" int mh_read_losses(mh_ctx* c, float* out, void* stream) {
+    API_BEGIN(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    int flags[8];
+    MH_CUDA(c, cudaMemcpyAsync(out, c->grads + c->n_params, sizeof(float) * MH_L_COUNT, cudaMemcpyDeviceToHost, st));
+    MH_CUDA(c, cudaMemcpyAsync(flags, c->devflags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    MH_CUDA(c, cudaStreamSynchronize(st));
+    if (flags[1]) MH_FAIL(c, MH_E_CAPACITY, "render: a body exceeded the raster tile / bin capacity (%d)", flags[1]);
+    return MH_OK;
+}
+
+// ---- filters ------------------------------------------------------------------------------------
+extern "C" int mh_refresh_filters(mh_ctx* c, float mc1, float b1, float mc2, float b2, float frame_rate, int32_t first, void* stream) {
+    API_BEGIN(c);
+    MH_TRY(mh_filter_run(c, mc1, b1, mc2, b2, frame_rate, first, (cudaStream_t)stream));
+    c->has_filters = true;
+    return MH_OK;
+}
+
+extern "C" int mh_refresh_filters_flag(mh_ctx* c, int32_t on) {
+    API_BEGIN(c);
+    c->has_filters = on != 0;
+    return MH_OK;
+}
+
+extern "C" int mh_clear_filters(mh_ctx* c) {
+    API_BEGIN(c);
+    c->has_filters = false;
+    return MH_OK;
+}
+
+// ---- scene depths -------------------------------------------------------------------------------
+__global__ void k_scene_depths(const float* __restrict__ depth, const float* __restrict__ zmin_lin, const float* __restrict__ zmax_lin,
+                               int64_t HW, float* __restrict__ out) {
+    const int t = blockIdx.y;
+    // min_z = softplus(zmin_lin) ; max_z = min_z + 1 + softplus(zmax_lin)   (optimizer.py:683-688, transforms.py:296)
+    const float minz = logf(1.0f + expf(zmin_lin[t]));
+    const float maxz = minz + 1.0f + logf(1.0f + expf(zmax_lin[t]));
+    const float a = 1.0f / minz - 1.0f / maxz, b = 1.0f / maxz;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)t * HW + i] = 1.0f / (depth[(int64_t)t * HW + i] * a + b);           // optimizer.py:425-426
+}
+
+extern "C" int mh_scene_depths(mh_ctx* c, int32_t t0, int32_t count, float* out_host) {
+    API_BEGIN(c);
+    const mh_dims& d = c->d;
+    if (t0 < 0 || count < 1 || t0 + count > d.T || !out_host) MH_FAIL(c, MH_E_ARG, "mh_scene_depths: bad range");
+    const int64_t HW = (int64_t)d.H * d.W;
+    float* tmp;
+    MH_CUDA(c, cudaMalloc((void**)&tmp, sizeof(float) * count * HW));
+    k_scene_depths<<<dim3(mh_cdiv(HW, 1024), count), 256>>>(c->depth + (int64_t)t0 * HW, c->params + c->off[MH_P_ZMIN_LIN] + t0,
+                                                            c->params + c->off[MH_P_ZMAX_LIN] + t0, HW, tmp);
+    c->launches++;
+    cudaError_t e = cudaMemcpy(out_host, tmp, sizeof(float) * count * HW, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    MH_CUDA(c, e);
+    return MH_OK;
+}
+
+// ---- debugging / synthesis ------------------------------------------------------------------------
+extern "C" int mh_debug_render(mh_ctx* c, int32_t t, int32_t n, float* zbuf_host, float* alpha_host) {
+    API_BEGIN(c);
+    const mh_dims& d = c->d;
+    if (t < 0 || t >= d.T || n < 0 || n >= d.N) MH_FAIL(c, MH_E_ARG, "mh_debug_render: bad index");
+    const int64_t HW = (int64_t)d.H * d.W;
+    float* tmp;
+    MH_CUDA(c, cudaMalloc((void**)&tmp, sizeof(float) * 2 * HW));
+    int r = mh_render_debug(c, t, n, tmp, tmp + HW, 0);
+    if (r == MH_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess && zbuf_host) e = cudaMemcpy(zbuf_host, tmp, sizeof(float) * HW, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && alpha_host) e = cudaMemcpy(alpha_host, tmp + HW, sizeof(float) * HW, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "mh_debug_render: %s", cudaGetErrorString(e)); r = MH_E_CUDA; }
+    }
+    cudaFree(tmp);
+    return r;
+}
+
+extern "C" int mh_forward_only(mh_ctx* c, void* stream) {
+    API_BEGIN(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const mh_dims& d = c->d;
+    MH_TRY(mh_terms_gather(c, 0, 0, st));
+    MhSmplArgs a = {c->params + c->off[MH_P_BETAS], d.N, 0, c->theta_all, c->trans_all, c->params + c->off[MH_P_XSCALE], c->nb, d.N,
+                    c->vshaped, c->Jrest, c->A, c->pf, c->vposed, c->verts, c->j17, c->lowidx};
+    return mh_smpl_forward_run(c, a, st);
+}
+
+extern "C" int mh_synth_planes(mh_ctx* c, float y_ground, float z_wall, void* stream) {
+    API_BEGIN(c);
+    if (!c->model_set || !c->camera_set || !c->coefs_set) MH_FAIL(c, MH_E_STATE, "mh_synth_planes: set model, camera and coefficients first");
+    cudaStream_t st = (cudaStream_t)stream;
+    MH_TRY(mh_forward_only(c, st));
+    MH_TRY(mh_render_synth(c, y_ground, z_wall, st));
+    return MH_OK;
+}
+
+extern "C" int mh_read_planes(mh_ctx* c, int32_t t0, int32_t count, float* depths_host, float* seg_host) {
+    API_BEGIN(c);
+    const mh_dims& d = c->d;
+    if (t0 < 0 || count < 1 || t0 + count > d.T) MH_FAIL(c, MH_E_ARG, "mh_read_planes: bad range");
+    const int64_t HW = (int64_t)d.H * d.W;
+    MH_CUDA(c, cudaDeviceSynchronize());
+    if (depths_host) MH_CUDA(c, cudaMemcpy(depths_host, c->depth + (int64_t)t0 * HW, sizeof(float) * count * HW, cudaMemcpyDeviceToHost));
+    if (seg_host) {
+        float* tmp;
+        MH_CUDA(c, cudaMalloc((void**)&tmp, sizeof(float) * d.N * HW));
+        int r = MH_OK;
+        for (int t = t0; t < t0 + count && r == MH_OK; ++t) {
+            r = mh_expand_planes(c, t, tmp, 0);
+            if (r == MH_OK && cudaMemcpy(seg_host + (int64_t)(t - t0) * d.N * HW, tmp, sizeof(float) * d.N * HW, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                snprintf(c->err, sizeof(c->err), "mh_read_planes: copy failed");
+                r = MH_E_CUDA;
+            }
+        }
+        cudaFree(tmp);
+        return r;
+    }
+    return MH_OK;
+}

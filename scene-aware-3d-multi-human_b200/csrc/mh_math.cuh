@@ -247,89 +247,128 @@ MH_HD void mh_project_bwd(const float P[3], const float* K, const float* Kd, flo
 
 // ---------------------------------------------------------------------------
 // Face evaluation (PyTorch3D naive semantics, Appendix A of SURVEY.md).
-// A face record holds NDC xy of the three vertices, view z, and reciprocals
-// that are uniform per face.
+//
+// The FORWARD arithmetic mirrors oracle/raster.py operation by operation (every
+// product, sum and quotient individually rounded, no FMA contraction, true
+// divisions) so that the discrete decisions -- inside test, blur-radius test,
+// nearest-first ordering -- are bit-identical to the oracle's.  MH_MUL / MH_ADD /
+// MH_SUB / MH_DIV are the non-contractable forms on the device; the host build
+// is compiled with -ffp-contract=off.
 // ---------------------------------------------------------------------------
-struct MhFace {            // 64 bytes
-    float x0, y0, x1, y1;
-    float x2, y2, z0, z1;
-    float z2, inv_den, il01, il02;     // inv_den = 1 / (area + 1e-8) ; il = 1 / |edge|^2 (0 if degenerate)
-    float il12, zlo, flags, pad;       // zlo = min z ; flags: bit0 = skip face entirely
+#ifdef __CUDA_ARCH__
+#define MH_MUL(a, b) __fmul_rn((a), (b))
+#define MH_ADD(a, b) __fadd_rn((a), (b))
+#define MH_SUB(a, b) __fsub_rn((a), (b))
+#define MH_DIV(a, b) __fdiv_rn((a), (b))
+#else
+#define MH_MUL(a, b) ((a) * (b))
+#define MH_ADD(a, b) ((a) + (b))
+#define MH_SUB(a, b) ((a) - (b))
+#define MH_DIV(a, b) ((a) / (b))
+#endif
+
+// world (camera-space metres) -> (x_ndc, y_ndc, z_view): R = diag(-1,-1,1), T = 0, then the NDC calibration
+// (optimizer.py:204-207; oracle.raster.world_to_ndc)
+MH_HD void mh_world_to_ndc(const float P[3], float k00, float k02, float k11, float k12, float o[3]) {
+    const float xv = -P[0], yv = -P[1], zv = P[2];
+    o[0] = MH_DIV(MH_ADD(MH_MUL(k00, xv), MH_MUL(k02, zv)), zv);
+    o[1] = MH_DIV(MH_ADD(MH_MUL(k11, yv), MH_MUL(k12, zv)), zv);
+    o[2] = zv;
+}
+
+struct MhEdge { float bax, bay, safe; int deg; };     // b - a, |b - a|^2 (1 when degenerate), degenerate flag
+
+struct MhFace {
+    float x0, y0, x1, y1, x2, y2, z0, z1, z2;
+    float den;                 // area + 1e-8
+    MhEdge e01, e02, e12;
+    float xmin, xmax, ymin, ymax;   // bbox inflated by sqrt(blur radius) of the DEPTH raster
+    int skip;                  // max z < 0 or |area| <= 1e-8
 };
 
 MH_HD float mh_edge(float px, float py, float ax, float ay, float bx, float by) {
-    return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
+    return MH_SUB(MH_MUL(MH_SUB(px, ax), MH_SUB(by, ay)), MH_MUL(MH_SUB(py, ay), MH_SUB(bx, ax)));
 }
 
-MH_HD void mh_face_setup(const float v0[3], const float v1[3], const float v2[3], MhFace* f) {
+MH_HD void mh_edge_setup(float ax, float ay, float bx, float by, MhEdge* e) {
+    e->bax = MH_SUB(bx, ax); e->bay = MH_SUB(by, ay);
+    const float l2 = MH_ADD(MH_MUL(e->bax, e->bax), MH_MUL(e->bay, e->bay));
+    e->deg = l2 <= MH_KEPS;
+    e->safe = e->deg ? 1.0f : l2;
+}
+
+MH_HD void mh_face_setup(const float v0[3], const float v1[3], const float v2[3], float r_inflate, MhFace* f) {
     f->x0 = v0[0]; f->y0 = v0[1]; f->x1 = v1[0]; f->y1 = v1[1]; f->x2 = v2[0]; f->y2 = v2[1];
     f->z0 = v0[2]; f->z1 = v1[2]; f->z2 = v2[2];
     const float area = mh_edge(v2[0], v2[1], v0[0], v0[1], v1[0], v1[1]);
-    f->inv_den = 1.0f / (area + MH_KEPS);
-    const float l01 = (v1[0] - v0[0]) * (v1[0] - v0[0]) + (v1[1] - v0[1]) * (v1[1] - v0[1]);
-    const float l02 = (v2[0] - v0[0]) * (v2[0] - v0[0]) + (v2[1] - v0[1]) * (v2[1] - v0[1]);
-    const float l12 = (v2[0] - v1[0]) * (v2[0] - v1[0]) + (v2[1] - v1[1]) * (v2[1] - v1[1]);
-    f->il01 = l01 <= MH_KEPS ? 0.0f : 1.0f / l01;
-    f->il02 = l02 <= MH_KEPS ? 0.0f : 1.0f / l02;
-    f->il12 = l12 <= MH_KEPS ? 0.0f : 1.0f / l12;
-    f->zlo = fminf(v0[2], fminf(v1[2], v2[2]));
+    f->den = MH_ADD(area, MH_KEPS);
+    mh_edge_setup(v0[0], v0[1], v1[0], v1[1], &f->e01);
+    mh_edge_setup(v0[0], v0[1], v2[0], v2[1], &f->e02);
+    mh_edge_setup(v1[0], v1[1], v2[0], v2[1], &f->e12);
+    f->xmin = MH_SUB(fminf(fminf(v0[0], v1[0]), v2[0]), r_inflate);
+    f->xmax = MH_ADD(fmaxf(fmaxf(v0[0], v1[0]), v2[0]), r_inflate);
+    f->ymin = MH_SUB(fminf(fminf(v0[1], v1[1]), v2[1]), r_inflate);
+    f->ymax = MH_ADD(fmaxf(fmaxf(v0[1], v1[1]), v2[1]), r_inflate);
     const float zmax = fmaxf(v0[2], fmaxf(v1[2], v2[2]));
     const bool zero_area = (area <= MH_KEPS) && (area >= -MH_KEPS);
-    f->flags = (zmax < 0.0f || zero_area) ? 1.0f : 0.0f;
-    f->pad = 0.0f;
+    f->skip = (zmax < 0.0f || zero_area || !(zmax == zmax)) ? 1 : 0;
 }
 
-// squared distance from p to segment (a, b); il = 1/|b-a|^2 or 0 when degenerate
-// (then the distance to endpoint b is returned, as upstream).  t_out = clamped parameter.
-MH_HD float mh_seg_dist(float px, float py, float ax, float ay, float bx, float by, float il, float* t_out) {
-    const float bax = bx - ax, bay = by - ay;
-    const float dax = px - ax, day = py - ay;
-    float t = (bax * dax + bay * day) * il;
-    t = fminf(fmaxf(t, 0.0f), 1.0f);
-    if (il == 0.0f) t = 1.0f;
-    const float qx = dax - t * bax, qy = day - t * bay;
+MH_HD float mh_clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+// squared distance from p to segment (a, b) (degenerate segments: distance to endpoint b, as upstream);
+// t_out = clamped parameter (1 when degenerate).
+MH_HD float mh_seg_dist(float px, float py, float ax, float ay, float bx, float by, const MhEdge& e, float* t_out) {
+    if (e.deg) {
+        *t_out = 1.0f;
+        const float dx = MH_SUB(px, bx), dy = MH_SUB(py, by);
+        return MH_ADD(MH_MUL(dx, dx), MH_MUL(dy, dy));
+    }
+    float t = MH_DIV(MH_ADD(MH_MUL(e.bax, MH_SUB(px, ax)), MH_MUL(e.bay, MH_SUB(py, ay))), e.safe);
+    t = mh_clamp01(t);
+    const float qx = MH_ADD(ax, MH_MUL(t, e.bax)), qy = MH_ADD(ay, MH_MUL(t, e.bay));
+    const float dx = MH_SUB(px, qx), dy = MH_SUB(py, qy);
     *t_out = t;
-    return qx * qx + qy * qy;
+    return MH_ADD(MH_MUL(dx, dx), MH_MUL(dy, dy));
 }
 
 struct MhFrag {
     float pz;        // clipped-barycentric depth
     float dist;      // unsigned squared distance to the nearest edge
     bool inside;
-    float w0, w1, w2;   // unclipped barycentrics
 };
 
-// returns false when the (pixel, face) pair is rejected before the blur test
+// false when the pixel is outside the inflated bbox or the clipped depth is negative
 MH_HD bool mh_face_eval(const MhFace& f, float px, float py, MhFrag* o) {
-    const float e0 = mh_edge(px, py, f.x1, f.y1, f.x2, f.y2);
-    const float e1 = mh_edge(px, py, f.x2, f.y2, f.x0, f.y0);
-    const float e2 = mh_edge(px, py, f.x0, f.y0, f.x1, f.y1);
-    const float w0 = e0 * f.inv_den, w1 = e1 * f.inv_den, w2 = e2 * f.inv_den;
-    const float c0 = fminf(fmaxf(w0, 0.0f), 1.0f), c1 = fminf(fmaxf(w1, 0.0f), 1.0f), c2 = fminf(fmaxf(w2, 0.0f), 1.0f);
-    const float bs = fmaxf(c0 + c1 + c2, 1e-5f);
-    const float pz = (c0 * f.z0 + c1 * f.z1 + c2 * f.z2) / bs;
+    if (px > f.xmax || px < f.xmin || py > f.ymax || py < f.ymin) return false;
+    const float w0 = MH_DIV(mh_edge(px, py, f.x1, f.y1, f.x2, f.y2), f.den);
+    const float w1 = MH_DIV(mh_edge(px, py, f.x2, f.y2, f.x0, f.y0), f.den);
+    const float w2 = MH_DIV(mh_edge(px, py, f.x0, f.y0, f.x1, f.y1), f.den);
+    float c0 = mh_clamp01(w0), c1 = mh_clamp01(w1), c2 = mh_clamp01(w2);
+    const float bs = fmaxf(MH_ADD(MH_ADD(c0, c1), c2), 1e-5f);
+    c0 = MH_DIV(c0, bs); c1 = MH_DIV(c1, bs); c2 = MH_DIV(c2, bs);
+    const float pz = MH_ADD(MH_ADD(MH_MUL(c0, f.z0), MH_MUL(c1, f.z1)), MH_MUL(c2, f.z2));
     float t;
-    const float d01 = mh_seg_dist(px, py, f.x0, f.y0, f.x1, f.y1, f.il01, &t);
-    const float d02 = mh_seg_dist(px, py, f.x0, f.y0, f.x2, f.y2, f.il02, &t);
-    const float d12 = mh_seg_dist(px, py, f.x1, f.y1, f.x2, f.y2, f.il12, &t);
+    const float d01 = mh_seg_dist(px, py, f.x0, f.y0, f.x1, f.y1, f.e01, &t);
+    const float d02 = mh_seg_dist(px, py, f.x0, f.y0, f.x2, f.y2, f.e02, &t);
+    const float d12 = mh_seg_dist(px, py, f.x1, f.y1, f.x2, f.y2, f.e12, &t);
     o->pz = pz;
     o->dist = fminf(fminf(d01, d02), d12);
     o->inside = (w0 > 0.0f) && (w1 > 0.0f) && (w2 > 0.0f);
-    o->w0 = w0; o->w1 = w1; o->w2 = w2;
     return pz >= 0.0f;
 }
 
-// Backward of one fragment.  gz = dL/d(pz) (0 if unused), gd = dL/d(signed dist) (0 if unused).
+// Backward of one fragment.  gz = dL/d(pz) (0 if unused), gd = dL/d(UNSIGNED dist) (0 if unused).
 // Accumulates into g[9] = d/d(x0,y0,z0,x1,y1,z1,x2,y2,z2) (NDC xy, view z).
 MH_HD void mh_face_bwd(const MhFace& f, float px, float py, float gz, float gd, float g[9]) {
     if (gz != 0.0f) {
-        const float den = 1.0f / f.inv_den;
+        const float inv_den = 1.0f / f.den;
         const float e0 = mh_edge(px, py, f.x1, f.y1, f.x2, f.y2);
         const float e1 = mh_edge(px, py, f.x2, f.y2, f.x0, f.y0);
         const float e2 = mh_edge(px, py, f.x0, f.y0, f.x1, f.y1);
-        const float w[3] = {e0 * f.inv_den, e1 * f.inv_den, e2 * f.inv_den};
+        const float w[3] = {e0 * inv_den, e1 * inv_den, e2 * inv_den};
         float c[3];
-        for (int i = 0; i < 3; ++i) c[i] = fminf(fmaxf(w[i], 0.0f), 1.0f);
+        for (int i = 0; i < 3; ++i) c[i] = mh_clamp01(w[i]);
         const float sum = c[0] + c[1] + c[2];
         const float bs = fmaxf(sum, 1e-5f);
         const float z[3] = {f.z0, f.z1, f.z2};
@@ -344,9 +383,8 @@ MH_HD void mh_face_bwd(const MhFace& f, float px, float py, float gz, float gd, 
         float dw[3];
         for (int i = 0; i < 3; ++i) dw[i] = (w[i] >= 0.0f && w[i] <= 1.0f) ? dc[i] : 0.0f;
         // w_i = e_i / den
-        const float de0 = dw[0] * f.inv_den, de1 = dw[1] * f.inv_den, de2 = dw[2] * f.inv_den;
-        const float dden = -(dw[0] * w[0] + dw[1] * w[1] + dw[2] * w[2]) * f.inv_den;
-        (void)den;
+        const float de0 = dw[0] * inv_den, de1 = dw[1] * inv_den, de2 = dw[2] * inv_den;
+        const float dden = -(dw[0] * w[0] + dw[1] * w[1] + dw[2] * w[2]) * inv_den;
         // e(p,a,b): d/dax = py - by ; d/day = bx - px ; d/dbx = -(py - ay) ; d/dby = px - ax
         // e0 = e(p, v1, v2)
         g[3] += de0 * (py - f.y2); g[4] += de0 * (f.x2 - px); g[6] += de0 * -(py - f.y1); g[7] += de0 * (px - f.x1);
@@ -361,10 +399,10 @@ MH_HD void mh_face_bwd(const MhFace& f, float px, float py, float gz, float gd, 
     }
     if (gd != 0.0f) {
         float t01, t02, t12;
-        const float d01 = mh_seg_dist(px, py, f.x0, f.y0, f.x1, f.y1, f.il01, &t01);
-        const float d02 = mh_seg_dist(px, py, f.x0, f.y0, f.x2, f.y2, f.il02, &t02);
-        const float d12 = mh_seg_dist(px, py, f.x1, f.y1, f.x2, f.y2, f.il12, &t12);
-        // nearest edge (first minimum in the order 01, 02, 12, as torch.minimum chains resolve ties)
+        const float d01 = mh_seg_dist(px, py, f.x0, f.y0, f.x1, f.y1, f.e01, &t01);
+        const float d02 = mh_seg_dist(px, py, f.x0, f.y0, f.x2, f.y2, f.e02, &t02);
+        const float d12 = mh_seg_dist(px, py, f.x1, f.y1, f.x2, f.y2, f.e12, &t12);
+        // nearest edge (first minimum in the order 01, 02, 12)
         int ia, ib; float ax, ay, bx, by, t;
         if (d01 <= d02 && d01 <= d12) { ia = 0; ib = 1; ax = f.x0; ay = f.y0; bx = f.x1; by = f.y1; t = t01; }
         else if (d02 <= d12)          { ia = 0; ib = 2; ax = f.x0; ay = f.y0; bx = f.x2; by = f.y2; t = t02; }

@@ -1,0 +1,482 @@
+// Differentiable mesh rasterisation of every local person-frame, fused with the depth and silhouette
+// terms and their analytic backward.
+//
+// Reference path replaced (mhmocap/optimizer.py): the two PyTorch3D rasterisations per batch -- depth
+// (faces_per_pixel 8, blur 1e-4, :211-218, 428-431) and soft silhouette (faces_per_pixel 4, blur 2e-5,
+// SoftSilhouetteShader, :221-232, 447-448) -- the erosion / validity masks (:432-438), the average
+// log-disparity loss (:440-442, losses.py:19-30), the occlusion-ordered masked-MSE silhouette loss with its
+// per-person-frame host sync (:450-475, losses.py:33-40) and PyTorch3D's atomic-add raster backward.
+// PyTorch3D semantics: SURVEY.md Appendix A / oracle/raster.py (parity unpinned upstream).
+//
+// One persistent CTA per SM walks the person-frames.  Per body:
+//   P0  the body's 6890 absolute vertices are staged into shared memory with one TMA bulk copy
+//       (cp.async.bulk + mbarrier) and converted in place to NDC;
+//   P1  faces are binned to 16x16-pixel tiles (count, scan, fill) - lists in a per-CTA global scratch;
+//   P2  every tile: each thread owns one pixel and walks the tile's faces (staged 128 at a time in shared
+//       memory), keeping the nearest depth fragment and the 4 nearest silhouette fragments; both rasters
+//       share one face evaluation;
+//   P3  per pixel: depth-loss sums, silhouette alpha, loss and its backward (shared-memory atomics into a
+//       per-body gradient array); depth winners go to a compact list because their gradient scale needs
+//       the whole-image sums;
+//   P4  block reduction of the sums, depth backward over the winner list;
+//   P5  NDC gradients are chained to camera space and added to dL/dV.
+// Everything outside the tiles a body touches contributes a mesh-independent constant that the prepass
+// (mh_planes.cu) keeps per (frame, order position).
+#include "mh_ctx.h"
+
+#define RT 16
+#define R_THREADS 256
+#define R_MAXBINS 4096
+#define R_CHUNK 128
+
+struct MhRenderScratch {
+    uint16_t* binlist; int bincap;
+    int* wpix; int* wface; float* wz; int wcap;
+    int nctas;
+    size_t smem;
+    int* counter;
+};
+
+struct RenderParams {
+    const float* verts; float* dverts; const int32_t* faces;
+    const float* pix_x; const float* pix_y;
+    const float* depth; const uint32_t* cbits; const uint32_t* ebits;
+    const int* order; const uint32_t* premask; const int* rankcnt;
+    const uint8_t* pose2d_valid; const uint8_t* mask_valid;
+    const float* zmin_lin; const float* zmax_lin;
+    float* pfout; int* devflags;
+    uint16_t* binlist; int bincap;
+    int* wpix; int* wface; float* wz; int wcap;
+    int* counter;
+    int T, N, H, W;
+    float k00, k02, k11, k12;
+    float rx, ry;                 // NDC extent of the x / y axis (2 on the short side)
+    float blur_d, blur_s, r_d, sigma, eps;
+    float coef_depth, coef_sil;
+    float* dbg_zbuf; float* dbg_alpha; int dbg_body;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float wsum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// fractional pixel index of an NDC coordinate on an axis of S pixels and NDC extent r (inverse of the
+// pixel-centre formula; used only for conservative ranges)
+__device__ __forceinline__ float pix_of(float ndc, int S, float r) { return (float)(S - 1) - ((ndc + 0.5f * r) * (float)S - 0.5f * r) / r; }
+
+template <int MODE>      // 0: losses + gradients ; 1: dense zbuf / alpha planes of one body
+__global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sv = reinterpret_cast<float*>(smem_raw);                       // MH_LD3V  NDC vertices
+    float* sg = sv + MH_LD3V;                                             // MH_LD3V  NDC gradients
+    int* tcount = reinterpret_cast<int*>(sg + MH_LD3V);                   // R_MAXBINS + 1 (exclusive offsets after the scan)
+    int* tcur = tcount + R_MAXBINS + 1;                                   // R_MAXBINS
+    MhFace* sface = reinterpret_cast<MhFace*>(tcur + R_MAXBINS + 3);      // R_CHUNK
+    int* sfid = reinterpret_cast<int*>(sface + R_CHUNK);                  // R_CHUNK
+    float* sred = reinterpret_cast<float*>(sfid + R_CHUNK);               // 64
+    int* sint = reinterpret_cast<int*>(sred + 64);                        // 16
+    __shared__ __align__(8) unsigned long long mbar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int TN = P.T * P.N;
+    uint16_t* binlist = P.binlist + (size_t)blockIdx.x * P.bincap;
+    int* wpix = P.wpix + (size_t)blockIdx.x * P.wcap;
+    int* wface = P.wface + (size_t)blockIdx.x * P.wcap;
+    float* wz = P.wz + (size_t)blockIdx.x * P.wcap;
+    uint32_t phase = 0;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    for (int iter = 0;; ++iter) {
+        // ---- next body (dynamic scheduling: bodies differ a lot in projected size) ----
+        if (MODE == 1 && iter > 0) break;
+        if (tid == 0) sint[0] = (MODE == 1) ? P.dbg_body : atomicAdd(P.counter, 1);
+        __syncthreads();
+        const int i = sint[0];
+        __syncthreads();
+        if (i >= TN) break;
+        const int t = i / P.N, n = i % P.N;
+        const size_t b = (size_t)i + P.N;                                // slot-major body (slot 0 is the halo)
+        // ---- P0: TMA bulk copy of the vertex row, then world -> NDC in place ----
+        if (tid == 0) {
+            const uint32_t bytes = MH_LD3V * sizeof(float);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sv)),
+                         "l"(P.verts + b * MH_LD3V), "r"(bytes), "r"(smem_u32(&mbar))
+                         : "memory");
+        }
+        for (int e = tid; e < MH_LD3V; e += R_THREADS) sg[e] = 0.f;
+        {
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+            }
+        }
+        phase ^= 1;
+        float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
+        for (int v = tid; v < MH_V; v += R_THREADS) {
+            const float Pw[3] = {sv[3 * v], sv[3 * v + 1], sv[3 * v + 2]};
+            float o[3];
+            mh_world_to_ndc(Pw, P.k00, P.k02, P.k11, P.k12, o);
+            sv[3 * v] = o[0]; sv[3 * v + 1] = o[1]; sv[3 * v + 2] = o[2];
+            if (o[2] > 0.f) { bx0 = fminf(bx0, o[0]); bx1 = fmaxf(bx1, o[0]); by0 = fminf(by0, o[1]); by1 = fmaxf(by1, o[1]); }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+            by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+        }
+        if (lane == 0) { sred[warp] = bx0; sred[8 + warp] = bx1; sred[16 + warp] = by0; sred[24 + warp] = by1; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 8; ++w) {
+                bx0 = fminf(bx0, sred[w]); bx1 = fmaxf(bx1, sred[8 + w]); by0 = fminf(by0, sred[16 + w]); by1 = fmaxf(by1, sred[24 + w]);
+            }
+            // pixel bbox of the body (NDC x / y decrease with the pixel index), inflated by the blur radius + 1 px
+            int c0 = (int)floorf(fminf(fmaxf(pix_of(bx1 + P.r_d, P.W, P.rx) - 1.f, 0.f), (float)(P.W - 1)));
+            int c1 = (int)ceilf(fminf(fmaxf(pix_of(bx0 - P.r_d, P.W, P.rx) + 1.f, 0.f), (float)(P.W - 1)));
+            int r0 = (int)floorf(fminf(fmaxf(pix_of(by1 + P.r_d, P.H, P.ry) - 1.f, 0.f), (float)(P.H - 1)));
+            int r1 = (int)ceilf(fminf(fmaxf(pix_of(by0 - P.r_d, P.H, P.ry) + 1.f, 0.f), (float)(P.H - 1)));
+            if (!(bx0 <= bx1)) { c0 = 1; c1 = 0; r0 = 1; r1 = 0; }          // nothing in front of the camera
+            const int tx0 = c0 / RT, tx1 = c1 / RT, ty0 = r0 / RT, ty1 = r1 / RT;
+            int ntx = max(tx1 - tx0 + 1, 0), nty = max(ty1 - ty0 + 1, 0);
+            int ks = 0;
+            while ((((ntx + (1 << ks) - 1) >> ks) * ((nty + (1 << ks) - 1) >> ks)) > R_MAXBINS) ++ks;
+            sint[1] = tx0; sint[2] = ty0; sint[3] = ntx; sint[4] = nty; sint[5] = ks;
+            sint[6] = 0;     // winner count
+            sint[7] = 0;     // overflow flag
+        }
+        __syncthreads();
+        const int tx0 = sint[1], ty0 = sint[2], ntx = sint[3], nty = sint[4], ks = sint[5];
+        const int nbx = (ntx + (1 << ks) - 1) >> ks, nby = (nty + (1 << ks) - 1) >> ks, nbins = nbx * nby;
+        // ---- P1: bin the faces ----
+        for (int e = tid; e <= nbins; e += R_THREADS) tcount[e] = 0;
+        __syncthreads();
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int f = tid; f < MH_F; f += R_THREADS) {
+                const int i0 = P.faces[3 * f], i1 = P.faces[3 * f + 1], i2 = P.faces[3 * f + 2];
+                const float x0 = sv[3 * i0], y0 = sv[3 * i0 + 1], z0 = sv[3 * i0 + 2];
+                const float x1 = sv[3 * i1], y1 = sv[3 * i1 + 1], z1 = sv[3 * i1 + 2];
+                const float x2 = sv[3 * i2], y2 = sv[3 * i2 + 1], z2 = sv[3 * i2 + 2];
+                const float zmax = fmaxf(z0, fmaxf(z1, z2));
+                const float area = mh_edge(x2, y2, x0, y0, x1, y1);
+                if (!(zmax >= 0.f) || ((area <= MH_KEPS) && (area >= -MH_KEPS)) || nbins == 0) continue;
+                const float fx0 = fminf(fminf(x0, x1), x2) - P.r_d, fx1 = fmaxf(fmaxf(x0, x1), x2) + P.r_d;
+                const float fy0 = fminf(fminf(y0, y1), y2) - P.r_d, fy1 = fmaxf(fmaxf(y0, y1), y2) + P.r_d;
+                const float pc0 = pix_of(fx1, P.W, P.rx) - 1.f, pc1 = pix_of(fx0, P.W, P.rx) + 1.f;
+                const float pr0 = pix_of(fy1, P.H, P.ry) - 1.f, pr1 = pix_of(fy0, P.H, P.ry) + 1.f;
+                if (!(pc1 >= 0.f) || !(pr1 >= 0.f) || !(pc0 <= (float)(P.W - 1)) || !(pr0 <= (float)(P.H - 1))) continue;
+                const int c0 = (int)fmaxf(pc0, 0.f), c1 = (int)fminf(pc1, (float)(P.W - 1));
+                const int r0 = (int)fmaxf(pr0, 0.f), r1 = (int)fminf(pr1, (float)(P.H - 1));
+                const int bx_lo = max((c0 / RT - tx0) >> ks, 0), bx_hi = min((c1 / RT - tx0) >> ks, nbx - 1);
+                const int by_lo = max((r0 / RT - ty0) >> ks, 0), by_hi = min((r1 / RT - ty0) >> ks, nby - 1);
+                for (int by = by_lo; by <= by_hi; ++by)
+                    for (int bx = bx_lo; bx <= bx_hi; ++bx) {
+                        const int bin = by * nbx + bx;
+                        if (pass == 0) atomicAdd(&tcount[bin], 1);
+                        else {
+                            const int pos = atomicAdd(&tcur[bin], 1);
+                            if (pos < P.bincap) binlist[pos] = (uint16_t)f;
+                        }
+                    }
+            }
+            __syncthreads();
+            if (pass == 0) {
+                // exclusive scan of tcount[0..nbins) -> offsets ; tcount[nbins] = total
+                const int per = (nbins + R_THREADS - 1) / R_THREADS;
+                int local = 0;
+                for (int k = 0; k < per; ++k) { const int e = tid * per + k; if (e < nbins) local += tcount[e]; }
+                int incl = local;
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                if (lane == 31) sint[8 + warp] = incl;
+                __syncthreads();
+                int wbase = 0;
+                for (int w = 0; w < warp; ++w) wbase += sint[8 + w];
+                int run = wbase + incl - local;
+                for (int k = 0; k < per; ++k) {
+                    const int e = tid * per + k;
+                    if (e < nbins) { const int cnt = tcount[e]; tcount[e] = run; tcur[e] = run; run += cnt; }
+                }
+                if (tid == R_THREADS - 1) { tcount[nbins] = run; if (run > P.bincap) sint[7] = 1; }
+                __syncthreads();
+            }
+        }
+        const bool overflow = sint[7] != 0;
+        if (overflow && tid == 0) atomicAdd(P.devflags + 1, 1);
+        // ---- per-body constants ----
+        int q = 0;                                                        // position of person n in the depth order
+        for (int k = 0; k < P.N; ++k) if (P.order[t * P.N + k] == n) q = k;
+        const uint32_t pre = P.premask[t * P.N + q];
+        int sumM = P.rankcnt[t * (P.N + 1) + P.N];
+        for (int k = q; k < P.N; ++k) sumM += P.rankcnt[t * (P.N + 1) + k];
+        const float Nn = (float)sumM + 1.0f;                              // sum(mask) + 1   (losses.py:36)
+        const bool gate = P.mask_valid[t * P.N + q] && P.pose2d_valid[t * P.N + q];      // indexed by POSITION (optimizer.py:472)
+        const bool pvalid = P.pose2d_valid[t * P.N + n] != 0;
+        const float minz = logf(1.0f + expf(P.zmin_lin[t]));
+        const float maxz = minz + 1.0f + logf(1.0f + expf(P.zmax_lin[t]));
+        const float izmin = 1.0f / minz, izmax = 1.0f / maxz;
+        const float tda = izmin - izmax;
+        const size_t plane = (size_t)t * P.H * P.W;
+        float aS = 0.f, aA = 0.f, aC = 0.f, aGmin = 0.f, aGmax = 0.f, aSil = 0.f, aCnt = 0.f;
+        // ---- P2 / P3: tiles ----
+        const int ntiles = overflow ? 0 : ntx * nty;
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int ttx = tile % ntx, tty = tile / ntx;
+            const int bin = (tty >> ks) * nbx + (ttx >> ks);
+            const int off = tcount[bin], cnt = tcount[bin + 1] - off;
+            if (cnt == 0) continue;
+            const int xi = (tx0 + ttx) * RT + (tid & (RT - 1)), yi = (ty0 + tty) * RT + (tid >> 4);
+            const bool inimg = xi < P.W && yi < P.H;
+            const float pxn = inimg ? P.pix_x[xi] : 0.f, pyn = inimg ? P.pix_y[yi] : 0.f;
+            float dz = INFINITY; int df = 0x7fffffff;                     // nearest depth fragment
+            float sz[4] = {INFINITY, INFINITY, INFINITY, INFINITY};       // 4 nearest silhouette fragments
+            float sd[4] = {0.f, 0.f, 0.f, 0.f};
+            int sf[4] = {-1, -1, -1, -1};
+            for (int base = 0; base < cnt; base += R_CHUNK) {
+                const int m = min(R_CHUNK, cnt - base);
+                __syncthreads();
+                if (tid < m) {
+                    const int f = binlist[off + base + tid];
+                    const int i0 = P.faces[3 * f], i1 = P.faces[3 * f + 1], i2 = P.faces[3 * f + 2];
+                    mh_face_setup(sv + 3 * i0, sv + 3 * i1, sv + 3 * i2, P.r_d, &sface[tid]);
+                    sfid[tid] = f;
+                }
+                __syncthreads();
+                if (inimg) {
+                    for (int k = 0; k < m; ++k) {
+                        MhFrag fr;
+                        if (!mh_face_eval(sface[k], pxn, pyn, &fr)) continue;
+                        const int f = sfid[k];
+                        if (fr.inside || fr.dist < P.blur_d) {
+                            if (fr.pz < dz || (fr.pz == dz && f < df)) { dz = fr.pz; df = f; }
+                        }
+                        if (fr.inside || fr.dist < P.blur_s) {
+                            float cz = fr.pz, cd = fr.inside ? -fr.dist : fr.dist; int cf = f;
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                if (cz < sz[s] || (cz == sz[s] && (unsigned)cf < (unsigned)sf[s])) {
+                                    const float tz = sz[s], tdd = sd[s]; const int tf = sf[s];
+                                    sz[s] = cz; sd[s] = cd; sf[s] = cf; cz = tz; cd = tdd; cf = tf;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (!inimg) continue;
+            const size_t pidx = plane + (size_t)yi * P.W + xi;
+            if (MODE == 1) {
+                P.dbg_zbuf[(size_t)yi * P.W + xi] = (df != 0x7fffffff) ? dz : -1.0f;
+                float prod = 1.0f;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const float pk = (sf[s] >= 0) ? 1.0f / (1.0f + expf(sd[s] / P.sigma)) : 0.f;
+                    prod = prod * (1.0f - pk);
+                }
+                P.dbg_alpha[(size_t)yi * P.W + xi] = 1.0f - prod;
+                continue;
+            }
+            const uint32_t cb = P.cbits[pidx];
+            // ---- depth term (optimizer.py:431-442) ----
+            if (df != 0x7fffffff && dz > 0.f && pvalid && ((P.ebits[pidx] >> n) & 1u)) {
+                const float zc = fmaxf(dz + 0.2f, P.eps);
+                const float zdisp = 1.0f / zc;
+                aS += 1.0f;
+                aA += logf(fmaxf(zdisp, P.eps));
+                const float dd = P.depth[pidx];
+                const float td = dd * tda + izmax;                        // target_disp (:425)
+                aC += logf(fmaxf(td, P.eps));
+                if (td >= P.eps) { aGmin += dd / td; aGmax += (1.0f - dd) / td; }
+                // d log(clamp(1 / clamp(z + .2, eps), eps)) / dz
+                const float gfac = (dz + 0.2f >= P.eps && zdisp >= P.eps) ? -1.0f / zc : 0.f;
+                if (gfac != 0.f) {
+                    const int wq = atomicAdd(&sint[6], 1);
+                    if (wq < P.wcap) { wpix[wq] = yi * P.W + xi; wface[wq] = df; wz[wq] = gfac; }
+                }
+            }
+            // ---- silhouette term (optimizer.py:459-475, losses.py:35-38) ----
+            if (gate && (cb & pre) == 0u) {
+                const float seg = (float)((cb >> n) & 1u);
+                float pk[4];
+                float prod = 1.0f;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    pk[s] = (sf[s] >= 0) ? 1.0f / (1.0f + expf(sd[s] / P.sigma)) : 0.f;
+                    prod = prod * (1.0f - pk[s]);
+                }
+                const float alpha = 1.0f - prod;
+                const float df_ = alpha - seg;
+                aSil += df_ * df_;
+                aCnt += seg;
+                const float ga = P.coef_sil * 2.0f * df_ / Nn;
+                if (ga != 0.f) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        if (sf[s] < 0) continue;
+                        float others = 1.0f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (j != s) others *= (1.0f - pk[j]);
+                        // d alpha / d signed = others * d p / d signed ; p = sigmoid(-signed / sigma)
+                        const float gsd = ga * others * (-pk[s] * (1.0f - pk[s]) / P.sigma);
+                        const float gdist = sd[s] < 0.f ? -gsd : gsd;     // signed = inside ? -dist : dist
+                        if (gdist == 0.f) continue;
+                        const int f = sf[s];
+                        const int iv[3] = {P.faces[3 * f], P.faces[3 * f + 1], P.faces[3 * f + 2]};
+                        MhFace fc;
+                        mh_face_setup(sv + 3 * iv[0], sv + 3 * iv[1], sv + 3 * iv[2], P.r_d, &fc);
+                        float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        mh_face_bwd(fc, pxn, pyn, 0.f, gdist, g);
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) {
+                            if (g[3 * e] != 0.f) atomicAdd(&sg[3 * iv[e]], g[3 * e]);
+                            if (g[3 * e + 1] != 0.f) atomicAdd(&sg[3 * iv[e] + 1], g[3 * e + 1]);
+                        }
+                    }
+                }
+            }
+        }
+        if (MODE == 1) continue;
+        // ---- P4: whole-image sums, then the depth backward over the winner list ----
+        aS = wsum(aS); aA = wsum(aA); aC = wsum(aC); aGmin = wsum(aGmin); aGmax = wsum(aGmax); aSil = wsum(aSil); aCnt = wsum(aCnt);
+        __syncthreads();
+        if (lane == 0) {
+            sred[warp] = aS; sred[8 + warp] = aA; sred[16 + warp] = aC; sred[24 + warp] = aGmin; sred[32 + warp] = aGmax;
+            sred[40 + warp] = aSil; sred[48 + warp] = aCnt;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float r[7];
+            for (int k = 0; k < 7; ++k) { r[k] = 0.f; for (int w = 0; w < 8; ++w) r[k] += sred[8 * k + w]; }
+            float* o = P.pfout + (size_t)i * PF_COUNT;
+            o[PF_S] = r[0]; o[PF_A] = r[1]; o[PF_C] = r[2]; o[PF_GIZMIN] = r[3]; o[PF_GIZMAX] = r[4];
+            // loss = (sum over the whole image of (M (alpha - seg))^2) / Nn ; outside the visited tiles alpha = 0
+            const float base = gate ? ((float)P.rankcnt[t * (P.N + 1) + q] - r[6]) : 0.f;
+            o[PF_SIL] = gate ? (base + r[5]) / Nn : 0.f;
+            o[PF_CNTIN] = r[6];
+            const float inv = 1.0f / (r[0] + 1.0f);
+            const float diff = r[1] * inv - r[2] * inv;
+            o[PF_DEPTHLOSS] = diff * diff;
+            sred[56] = P.coef_depth * 2.0f * diff * inv;                  // dL/dA_sum
+            if (sint[6] > P.wcap) atomicAdd(P.devflags + 1, 1);
+        }
+        __syncthreads();
+        const float kappa = sred[56];
+        const int nw = min(sint[6], P.wcap);
+        if (kappa != 0.f) {
+            for (int e = tid; e < nw; e += R_THREADS) {
+                const int pix = wpix[e], f = wface[e];
+                const int yi = pix / P.W, xi = pix - yi * P.W;
+                const int iv[3] = {P.faces[3 * f], P.faces[3 * f + 1], P.faces[3 * f + 2]};
+                MhFace fc;
+                mh_face_setup(sv + 3 * iv[0], sv + 3 * iv[1], sv + 3 * iv[2], P.r_d, &fc);
+                float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                mh_face_bwd(fc, P.pix_x[xi], P.pix_y[yi], kappa * wz[e], 0.f, g);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) if (g[k] != 0.f) atomicAdd(&sg[3 * iv[k / 3] + (k % 3)], g[k]);
+            }
+        }
+        __syncthreads();
+        // ---- P5: NDC -> camera-space chain rule, accumulate into dL/dV (this CTA owns the row) ----
+        const float* vw = P.verts + b * MH_LD3V;
+        float* dv = P.dverts + b * MH_LD3V;
+        for (int v = tid; v < MH_V; v += R_THREADS) {
+            const float gx = sg[3 * v], gy = sg[3 * v + 1], gz = sg[3 * v + 2];
+            if (gx == 0.f && gy == 0.f && gz == 0.f) continue;
+            const float X = vw[3 * v], Y = vw[3 * v + 1], Z = vw[3 * v + 2];
+            const float iz = 1.0f / Z;
+            // x_ndc = -k00 X / Z + k02 ; y_ndc = -k11 Y / Z + k12 ; z_view = Z
+            dv[3 * v] += -P.k00 * iz * gx;
+            dv[3 * v + 1] += -P.k11 * iz * gy;
+            dv[3 * v + 2] += (P.k00 * X * gx + P.k11 * Y * gy) * iz * iz + gz;
+        }
+        __syncthreads();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+int mh_render_alloc(mh_ctx* c) {
+    MhRenderScratch* rs = new MhRenderScratch();
+    memset(rs, 0, sizeof(*rs));
+    c->rs = rs;
+    rs->nctas = c->num_sms;
+    rs->bincap = 1 << 20;
+    rs->wcap = c->d.H * c->d.W;
+    const size_t n = (size_t)rs->nctas;
+    cudaError_t e = cudaMalloc((void**)&rs->binlist, n * rs->bincap * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wpix, n * rs->wcap * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wface, n * rs->wcap * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wz, n * rs->wcap * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
+    if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
+    rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (size_t)R_CHUNK * (sizeof(MhFace) + sizeof(int)) +
+               64 * sizeof(float) + 16 * sizeof(int) + 64;
+    e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
+    if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render: %zu bytes of shared memory: %s", rs->smem, cudaGetErrorString(e));
+    return MH_OK;
+}
+
+void mh_render_free(mh_ctx* c) {
+    if (!c->rs) return;
+    cudaFree(c->rs->binlist); cudaFree(c->rs->wpix); cudaFree(c->rs->wface); cudaFree(c->rs->wz); cudaFree(c->rs->counter);
+    delete c->rs;
+    c->rs = nullptr;
+}
+
+static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
+    RenderParams P;
+    memset(&P, 0, sizeof(P));
+    const mh_dims& d = c->d;
+    P.verts = c->verts; P.dverts = c->dverts; P.faces = c->faces; P.pix_x = c->pix_x; P.pix_y = c->pix_y;
+    P.depth = c->depth; P.cbits = c->cbits; P.ebits = c->ebits; P.order = c->order; P.premask = c->premask; P.rankcnt = c->rankcnt;
+    P.pose2d_valid = c->pose2d_valid; P.mask_valid = c->mask_valid;
+    P.zmin_lin = c->params + c->off[MH_P_ZMIN_LIN]; P.zmax_lin = c->params + c->off[MH_P_ZMAX_LIN];
+    P.pfout = c->pfout; P.devflags = c->devflags;
+    P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
+    P.counter = c->rs->counter;
+    P.T = d.T; P.N = d.N; P.H = d.H; P.W = d.W;
+    P.k00 = c->Kndc[0]; P.k02 = c->Kndc[2]; P.k11 = c->Kndc[5]; P.k12 = c->Kndc[6];
+    P.rx = d.W > d.H ? (float)(2.0 * d.W / d.H) : 2.0f;
+    P.ry = d.H > d.W ? (float)(2.0 * d.H / d.W) : 2.0f;
+    P.blur_d = blur_d; P.blur_s = blur_s; P.r_d = sqrtf(blur_d > blur_s ? blur_d : blur_s);
+    P.sigma = 1e-4f;                 // BlendParams default used by SoftSilhouetteShader
+    P.eps = c->c.eps;
+    P.coef_depth = c->c.depth; P.coef_sil = c->c.silhouette;
+    return P;
+}
+
+int mh_render_all(mh_ctx* c, cudaStream_t st) {
+    RenderParams P = render_params(c, 1e-4f, 2e-5f);          // optimizer.py:213, 223
+    MH_CUDA(c, cudaMemsetAsync(c->rs->counter, 0, sizeof(int), st));
+    const int grid = std::min(c->rs->nctas, c->d.T * c->d.N);
+    k_render<0><<<grid, R_THREADS, c->rs->smem, st>>>(P);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+__global__ void k_fill2(float* a, float va, float* b, float vb, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { a[i] = va; b[i] = vb; }
+}
+
+int mh_render_planes(mh_ctx* c, int t, int n, float* zbuf_dev, float* alpha_dev, float blur_d, float blur_s, cudaStream_t st) {
+    RenderParams P = render_params(c, blur_d, blur_s);
+    P.dbg_zbuf = zbuf_dev; P.dbg_alpha = alpha_dev; P.dbg_body = t * c->d.N + n;
+    const int64_t HW = (int64_t)c->d.H * c->d.W;
+    k_fill2<<<mh_cdiv(HW, 1024), 256, 0, st>>>(zbuf_dev, -1.0f, alpha_dev, 0.0f, HW);
+    MH_LAUNCHED(c);
+    k_render<1><<<1, R_THREADS, c->rs->smem, st>>>(P);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+int mh_render_debug(mh_ctx* c, int t, int n, float* zbuf_dev, float* alpha_dev, cudaStream_t st) {
+    MH_TRY(mh_forward_only(c, st));
+    return mh_render_planes(c, t, n, zbuf_dev, alpha_dev, 1e-4f, 2e-5f, st);
+}

@@ -15,7 +15,7 @@
 //   pose_bwd     chain / Rodrigues backward -> dL/dtheta ; dL/dJ -> dL/dbeta
 #include "mh_ctx.h"
 
-#define V_ 6890
+#define V_ MH_V
 
 // -------------------------------------------------------------------------------------------------
 __global__ void k_shape_prep(const float* __restrict__ betas, int rows, const float* __restrict__ vt,
@@ -200,24 +200,19 @@ __global__ void __launch_bounds__(256) k_skin_fwd(const float* __restrict__ vpos
     }
 }
 
-int mh_smpl_forward_all(mh_ctx* c, int first_body, int n_bodies, bool per_body_shape, const float* betas_dev,
-                        const float* theta_dev, const float* trans_dev, const float* xscale_dev, float* verts_out,
-                        float* j17_out, int* lowidx_out, cudaStream_t st) {
-    // theta_dev / trans_dev / outputs are indexed by ABSOLUTE body (first_body .. first_body + n_bodies)
-    const int rows = per_body_shape ? (first_body + n_bodies) : c->d.N;
-    if (rows > c->vshaped_rows) MH_FAIL(c, MH_E_ARG, "smpl forward: %d shape rows exceed capacity %lld", rows, (long long)c->vshaped_rows);
-    k_shape_prep<<<dim3(mh_cdiv(MH_LD3V, 256), rows), 256, 0, st>>>(betas_dev, rows, c->vtemplate, c->pext, c->vshaped);
+int mh_smpl_forward_run(mh_ctx* c, const MhSmplArgs& a, cudaStream_t st) {
+    if (a.nbodies <= 0) return MH_OK;
+    k_shape_prep<<<dim3(mh_cdiv(MH_LD3V, 256), a.shape_rows), 256, 0, st>>>(a.betas, a.shape_rows, c->vtemplate, c->pext, a.vshaped);
     MH_LAUNCHED(c);
-    k_joint_prep<<<mh_cdiv(rows * 72, 128), 128, 0, st>>>(betas_dev, rows, c->Jt, c->Js, c->Jrest);
+    k_joint_prep<<<mh_cdiv(a.shape_rows * 72, 128), 128, 0, st>>>(a.betas, a.shape_rows, c->Jt, c->Js, a.Jrest);
     MH_LAUNCHED(c);
-    const int nb = first_body + n_bodies;
-    k_pose_prep<<<mh_cdiv(nb, 64), 64, 0, st>>>(theta_dev, c->Jrest, nb, c->d.N, per_body_shape ? 1 : 0, c->A, c->pf);
+    k_pose_prep<<<mh_cdiv(a.nbodies, 64), 64, 0, st>>>(a.theta, a.Jrest, a.nbodies, a.N, a.per_body_shape, a.A, a.pf);
     MH_LAUNCHED(c);
-    k_gemm_fwd<<<dim3(MH_LD3V / GF_BN, mh_cdiv(nb, GF_BM)), 256, 0, st>>>(c->pf, c->pext, c->vshaped, c->vposed, nb, c->d.N,
-                                                                          per_body_shape ? 1 : 0);
+    k_gemm_fwd<<<dim3(MH_LD3V / GF_BN, mh_cdiv(a.nbodies, GF_BM)), 256, 0, st>>>(a.pf, c->pext, a.vshaped, a.vposed, a.nbodies,
+                                                                               a.N, a.per_body_shape);
     MH_LAUNCHED(c);
-    k_skin_fwd<<<n_bodies, 256, 0, st>>>(c->vposed, c->A, c->wj, c->ww, c->KW, trans_dev, xscale_dev, c->d.N, c->rptr,
-                                         c->rvert, c->rw, verts_out, j17_out, lowidx_out, first_body);
+    k_skin_fwd<<<a.nbodies, 256, 0, st>>>(a.vposed, a.A, c->wj, c->ww, c->KW, a.trans, a.xscale, a.N, c->rptr, c->rvert, c->rw,
+                                          a.verts, a.j17, a.lowidx, 0);
     MH_LAUNCHED(c);
     return MH_OK;
 }

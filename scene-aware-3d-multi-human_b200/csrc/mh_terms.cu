@@ -1,0 +1,446 @@
+// Non-raster loss terms of one fit() cycle and of the translation-init loop, forward + analytic backward.
+//
+// Reference code replaced (mhmocap/optimizer.py): 2D reprojection :404-420 (+ transforms.py:57-95), pose / shape
+// priors :523-526, scale priors :531-532, contact + foot sliding :483-518, velocity :560-561, filtered-vertex
+// velocity :563-574, depth-range activations :683-688, translation init :740-761.  Batch-partition quirks
+//  are kept: a "batch" is B consecutive GLOBAL frames.
+#include "mh_ctx.h"
+
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum for blockDim.x <= 1024; result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float* sm /*32 floats*/) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (w == 0) {
+        r = (lane < (blockDim.x + 31) / 32) ? sm[lane] : 0.f;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+__device__ __forceinline__ float signf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// -------------------------------------------------------------------------------------------------
+// slot-major parameter views incl. the halo frames
+__global__ void k_gather(const float* __restrict__ theta, const float* __restrict__ trans, const float* __restrict__ halo, int T, int N,
+                         int use_prev, int use_next, float* __restrict__ theta_all, float* __restrict__ trans_all) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)(T + 2) * N * MH_HALO;
+    if (i >= total) return;
+    const int e = (int)(i % MH_HALO);
+    const int n = (int)((i / MH_HALO) % N);
+    const int s = (int)(i / ((int64_t)MH_HALO * N));
+    float v;
+    if (s == 0 && use_prev) v = halo[(size_t)n * MH_HALO + e];
+    else if (s == T + 1 && use_next) v = halo[(size_t)(N + n) * MH_HALO + e];
+    else {
+        const int t = min(max(s - 1, 0), T - 1);      // unused halo slots mirror the boundary frame (never read by a term)
+        v = e < 72 ? theta[((size_t)t * N + n) * 72 + e] : trans[((size_t)t * N + n) * 3 + (e - 72)];
+    }
+    const size_t b = (size_t)s * N + n;
+    if (e < 72) theta_all[b * 72 + e] = v; else trans_all[b * 3 + (e - 72)] = v;
+}
+
+int mh_terms_gather(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) {
+    const mh_dims& d = c->d;
+    const int64_t total = (int64_t)c->Ts * d.N * MH_HALO;
+    k_gather<<<mh_cdiv(total, 256), 256, 0, st>>>(c->params + c->off[MH_P_POSES_SMPL], c->params + c->off[MH_P_POSES_T], c->halo_recv, d.T, d.N,
+                                                 use_prev, use_next, c->theta_all, c->trans_all);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// one warp per local person-frame: 2D reprojection term + pose prior
+struct CamParams { float K[9]; float Kd[5]; int has_kd; float w17[MH_NJR]; };
+
+__global__ void k_body_terms(const float* __restrict__ j17, const float* __restrict__ pose2d, const float* __restrict__ theta,
+                             const float* __restrict__ theta_ref, const float* __restrict__ valid, CamParams cam, int T, int N, float W,
+                             float H, float thr, float coef_proj, float coef_poses, float* __restrict__ gj17,
+                             float* __restrict__ g_theta, float* __restrict__ losses) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);       // local person-frame
+    const int lane = threadIdx.x & 31;
+    if (i >= T * N) return;
+    const size_t b = (size_t)i + N;                                          // slot-major body
+    float l2d = 0.f;
+    if (lane < MH_NJR) {
+        const float* P = j17 + (b * MH_NJR + lane) * 3;
+        const float* q = pose2d + ((size_t)i * MH_NJR + lane) * 3;
+        const float m = (q[2] >= thr ? 1.0f : 0.0f) * cam.w17[lane];         // optimizer.py:404, 420
+        float uv[2];
+        const float Pv[3] = {P[0], P[1], P[2]};
+        mh_project(Pv, cam.K, cam.has_kd ? cam.Kd : nullptr, uv);
+        const float du = m * uv[0] / W - m * q[0] / W, dv = m * uv[1] / H - m * q[1] / H;      // optimizer.py:367-368
+        l2d = du * du + dv * dv;
+        float gP[3];
+        mh_project_bwd(Pv, cam.K, cam.has_kd ? cam.Kd : nullptr, coef_proj * 2.0f * du * m / W, coef_proj * 2.0f * dv * m / H, gP);
+        float* g = gj17 + (b * MH_NJR + lane) * 3;
+        g[0] = gP[0]; g[1] = gP[1]; g[2] = gP[2];
+    }
+    // pose prior: sum |valid * theta_ref - valid * theta|  (optimizer.py:523-525)
+    const float vld = valid[i];
+    float lp = 0.f;
+    for (int e = lane; e < 72; e += 32) {
+        const float df = vld * theta_ref[(size_t)i * 72 + e] - vld * theta[(size_t)i * 72 + e];
+        lp += fabsf(df);
+        g_theta[(size_t)i * 72 + e] = -coef_poses * vld * signf(df);
+    }
+    l2d = warp_sum(l2d); lp = warp_sum(lp);
+    if (lane == 0) { atomicAdd(losses + MH_L_POSE2D, l2d); atomicAdd(losses + MH_L_REF_POSES, lp); }
+}
+
+// -------------------------------------------------------------------------------------------------
+// dL/dV initialiser for the local bodies: filtered-vertex velocity term (optimizer.py:563-574) + the
+// regressed-joint gradients spread through R17^T.  Writes every column of the padded row.
+__global__ void __launch_bounds__(256) k_dverts_init(const float* __restrict__ verts, const float* __restrict__ filt,
+                                                     const float* __restrict__ gj17, const int* __restrict__ cptr,
+                                                     const int* __restrict__ cjoint, const float* __restrict__ cw, int T, int N, int t0,
+                                                     int T_total, int use_prev, int use_next, int has_filters, float coef,
+                                                     float* __restrict__ dverts, float* __restrict__ losses) {
+    __shared__ float sm[32];
+    const int i = blockIdx.y;                    // local person-frame
+    const int s = i / N + 1;                     // slot
+    const size_t b = (size_t)i + N;
+    const int tg = t0 + s - 1;
+    const bool has_prev = has_filters && tg >= 1 && (s > 1 || use_prev);
+    const bool has_next = has_filters && (tg + 1 <= T_total - 1) && (s < T || use_next);
+    const size_t row = b * MH_LD3V, rp = row - (size_t)N * MH_LD3V, rn = row + (size_t)N * MH_LD3V;
+    float loss = 0.f;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < MH_LD3V; e += gridDim.x * blockDim.x) {
+        float g = 0.f;
+        if (e < 3 * MH_V) {
+            const float v = verts[row + e];
+            if (has_prev) {
+                const float D = (v - verts[rp + e]) - (filt[row + e] - filt[rp + e]);
+                loss += D * D;
+                g += 2.0f * coef * D;
+            }
+            if (has_next) {
+                const float D = (verts[rn + e] - v) - (filt[rn + e] - filt[row + e]);
+                g -= 2.0f * coef * D;
+            }
+            const int vtx = e / 3, k = e - 3 * vtx;
+            for (int q = cptr[vtx]; q < cptr[vtx + 1]; ++q) g = fmaf(cw[q], gj17[(b * MH_NJR + cjoint[q]) * 3 + k], g);
+        }
+        dverts[row + e] = g;
+    }
+    if (has_filters) {
+        loss = block_sum(loss, sm);
+        if (threadIdx.x == 0 && loss != 0.f) atomicAdd(losses + MH_L_FILTER_VERTS, loss);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// velocity term on the translations (optimizer.py:560-561; init: :758-760)
+__global__ void k_velocity(const float* __restrict__ trans_all, int T, int N, int t0, int T_total, int use_prev, int use_next, float coef,
+                           float* __restrict__ g_trans, float* __restrict__ losses) {
+    __shared__ float sm[32];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // (t, n, k)
+    float loss = 0.f;
+    if (idx < T * N * 3) {
+        const int s = idx / (N * 3) + 1;
+        const int tg = t0 + s - 1;
+        const size_t o = (size_t)idx + (size_t)N * 3;
+        const float v = trans_all[o];
+        float g = 0.f;
+        if (tg >= 1 && (s > 1 || use_prev)) {
+            const float D = v - trans_all[o - (size_t)N * 3];
+            loss = D * D;
+            g += 2.0f * coef * D;
+        }
+        if (tg + 1 <= T_total - 1 && (s < T || use_next)) g -= 2.0f * coef * (trans_all[o + (size_t)N * 3] - v);
+        g_trans[idx] += g;
+    }
+    loss = block_sum(loss, sm);
+    if (threadIdx.x == 0 && loss != 0.f) atomicAdd(losses + MH_L_VEL, loss);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Contact term: streaming exact top-32 nearest scene points of the lowest vertex (optimizer.py:487-506).
+// One CTA per local person-frame.  Pass A: per-thread minima -> the 32nd smallest of them bounds the 32nd
+// nearest distance; pass B collects every point under the bound; the 32 nearest are ranked exactly by
+// (distance, index).  No distance matrix, no sort over M.
+#define KNN_THREADS 256
+#define KNN_CAP 2048
+__device__ __forceinline__ float d2_point(const float* __restrict__ p, float x, float y, float z) {
+    // sum(pow(pcd - low, 2), -1): three squares added in coordinate order
+    const float a = p[0] - x, b = p[1] - y, c = p[2] - z;
+    return (a * a + b * b) + c * c;
+}
+
+__global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict__ verts, const int* __restrict__ lowidx,
+                                                         const float* __restrict__ scene, int64_t M, int N, float coef,
+                                                         float* __restrict__ contact, float* __restrict__ g_trans,
+                                                         float* __restrict__ losses) {
+    __shared__ float smin[KNN_THREADS];
+    __shared__ float cd[KNN_CAP];
+    __shared__ int ci[KNN_CAP];
+    __shared__ int sel[MH_KNN];
+    __shared__ int scount;
+    __shared__ float stau, slo, shi;
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const size_t b = (size_t)i + N;
+    const int li = lowidx[b];
+    const float x = verts[b * MH_LD3V + 3 * li], y = verts[b * MH_LD3V + 3 * li + 1], z = verts[b * MH_LD3V + 3 * li + 2];
+    float mn = INFINITY;
+    for (int64_t p = tid; p < M; p += KNN_THREADS) mn = fminf(mn, d2_point(scene + 3 * p, x, y, z));
+    smin[tid] = mn;
+    __syncthreads();
+    int rank = 0;
+    for (int j = 0; j < KNN_THREADS; ++j) rank += (smin[j] < mn) || (smin[j] == mn && j < tid);
+    if (rank == MH_KNN - 1) { stau = mn; slo = 0.f; shi = mn; }
+    if (tid == 0) scount = 0;
+    __syncthreads();
+    for (int iter = 0; iter < 64; ++iter) {
+        const float tau = stau;
+        for (int64_t p = tid; p < M; p += KNN_THREADS) {
+            const float dd = d2_point(scene + 3 * p, x, y, z);
+            if (dd <= tau) {
+                const int q = atomicAdd(&scount, 1);
+                if (q < KNN_CAP) { cd[q] = dd; ci[q] = (int)p; }
+            }
+        }
+        __syncthreads();
+        const int cnt = scount;
+        if (cnt >= MH_KNN && cnt <= KNN_CAP) break;
+        __syncthreads();
+        if (tid == 0) {          // bisection on the bound (only reached with > KNN_CAP near-ties)
+            if (cnt > KNN_CAP) shi = tau; else slo = tau;
+            stau = 0.5f * (slo + shi);
+            scount = 0;
+        }
+        __syncthreads();
+    }
+    const int cnt = min(scount, KNN_CAP);
+    for (int a = tid; a < cnt; a += KNN_THREADS) {
+        const float da = cd[a];
+        const int ia = ci[a];
+        int r = 0;
+        for (int j = 0; j < cnt; ++j) r += (cd[j] < da) || (cd[j] == da && ci[j] < ia);
+        if (r < MH_KNN) sel[r] = ia;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float my = 0.f;
+        for (int r = 0; r < MH_KNN; ++r) my += scene[3 * (size_t)sel[r] + 1];
+        my *= (1.0f / MH_KNN);
+        const float cdv = my - y;                               // contact_dist_vertical (:501)
+        const float r = cdv + 0.02f;                            // target.y = T.y + cdv + 0.02 (:502-503)
+        atomicAdd(losses + MH_L_CONTACT, fabsf(r));
+        g_trans[(size_t)i * 3 + 1] += coef * -signf(r);         // d|T - target|/dT.y with the target detached (:504-506)
+        contact[(size_t)i * 4] = cdv;
+        contact[(size_t)i * 4 + 1] = cdv > -0.20f ? 1.0f : 0.0f;   // in_thr_contact_region (:509-510)
+    }
+}
+
+// foot sliding (optimizer.py:512-518): one CTA per local batch segment; pairs are ADJACENT ENTRIES OF ONE BATCH
+__global__ void k_foot(const float* __restrict__ verts, const int* __restrict__ lowidx, const float* __restrict__ contact, int T, int N,
+                       int B, float coef, float* __restrict__ dverts, float* __restrict__ losses) {
+    __shared__ float sm[32];
+    __shared__ float sden;
+    const int k = blockIdx.x;
+    const int ta = k * B, tb = min(ta + B, T);
+    const int npairs = (tb - ta - 1) * N;
+    float cnt = 0.f;
+    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+        const int t = ta + 1 + p / N, n = p % N;
+        cnt += contact[((size_t)t * N + n) * 4 + 1];
+    }
+    cnt = block_sum(cnt, sm);
+    if (threadIdx.x == 0) sden = fmaxf(cnt, 1.0f);               // clamp(sum(in), 1)
+    __syncthreads();
+    const float den = sden;
+    float loss = 0.f;
+    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+        const int t = ta + 1 + p / N, n = p % N;
+        const float in = contact[((size_t)t * N + n) * 4 + 1];
+        const size_t bt = (size_t)(t + 1) * N + n, bp = bt - N;
+        const int li = lowidx[bt];
+        for (int q = 0; q < 3; ++q) {
+            const float df = in * verts[bt * MH_LD3V + 3 * li + q] - in * verts[bp * MH_LD3V + 3 * li + q];
+            loss += fabsf(df);
+            const float g = coef * in * signf(df) / den;
+            if (g != 0.f) {
+                atomicAdd(dverts + bt * MH_LD3V + 3 * li + q, g);
+                atomicAdd(dverts + bp * MH_LD3V + 3 * li + q, -g);
+            }
+        }
+    }
+    loss = block_sum(loss, sm);
+    if (threadIdx.x == 0) atomicAdd(losses + MH_L_FOOT, loss / den);
+}
+
+static CamParams cam_of(const mh_ctx* c) {
+    CamParams p;
+    memcpy(p.K, c->K, sizeof(p.K));
+    memcpy(p.Kd, c->Kd, sizeof(p.Kd));
+    p.has_kd = c->has_kd ? 1 : 0;
+    memcpy(p.w17, c->w17, sizeof(p.w17));
+    return p;
+}
+
+int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) {
+    const mh_dims& d = c->d;
+    const int TN = d.T * d.N;
+    float* losses = c->grads + c->n_params;
+    float* g_trans = c->grads + c->off[MH_P_POSES_T];
+    k_body_terms<<<mh_cdiv(TN, 4), 128, 0, st>>>(c->j17, c->pose2d, c->params + c->off[MH_P_POSES_SMPL], c->theta_ref, c->valid, cam_of(c),
+                                                 d.T, d.N, (float)d.W, (float)d.H, c->c.joint_confidence_thr, c->c.proj2d, c->c.reg_poses,
+                                                 c->gj17, c->grads + c->off[MH_P_POSES_SMPL], losses);
+    MH_LAUNCHED(c);
+    k_dverts_init<<<dim3(8, TN), 256, 0, st>>>(c->verts, c->filtered, c->gj17, c->cptr, c->cjoint, c->cw, d.T, d.N, d.t0, d.T_total,
+                                               use_prev, use_next, c->has_filters ? 1 : 0, c->c.reg_verts_filter, c->dverts, losses);
+    MH_LAUNCHED(c);
+    k_velocity<<<mh_cdiv(TN * 3, 256), 256, 0, st>>>(c->trans_all, d.T, d.N, d.t0, d.T_total, use_prev, use_next, c->c.reg_velocity,
+                                                     g_trans, losses);
+    MH_LAUNCHED(c);
+    if (c->M > 0) {
+        k_contact<<<TN, KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, c->c.reg_contact, c->contact, g_trans, losses);
+        MH_LAUNCHED(c);
+        k_foot<<<mh_cdiv(d.T, d.B), 128, 0, st>>>(c->verts, c->lowidx, c->contact, d.T, d.N, d.B, c->c.reg_foot_sliding, c->dverts, losses);
+        MH_LAUNCHED(c);
+    }
+    return MH_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// after the render stage: depth-range gradients and the depth / silhouette loss sums, one thread per frame
+__global__ void k_frame_finalize(const float* __restrict__ pfout, const float* __restrict__ zmin_lin, const float* __restrict__ zmax_lin,
+                                 int T, int N, float coef_depth, float* __restrict__ g_zmin, float* __restrict__ g_zmax,
+                                 float* __restrict__ losses) {
+    __shared__ float sm[32];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    float ld = 0.f, ls = 0.f;
+    if (t < T) {
+        float gmin = 0.f, gmax = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float* o = pfout + ((size_t)t * N + n) * PF_COUNT;
+            const float inv = 1.0f / (o[PF_S] + 1.0f);
+            const float a = o[PF_A] * inv, cc = o[PF_C] * inv;          // losses.py:24-27
+            const float diff = a - cc;
+            ld += diff * diff;
+            ls += o[PF_SIL];
+            const float k = -2.0f * diff * inv * coef_depth;              // dL/dc / (S + 1)
+            gmin += k * o[PF_GIZMIN];
+            gmax += k * o[PF_GIZMAX];
+        }
+        // min_z = log(1 + e^x) ; max_z = stopgrad(min_z) + 1 + log(1 + e^y)   (optimizer.py:683-688)
+        const float ex = expf(zmin_lin[t]), ey = expf(zmax_lin[t]);
+        const float minz = logf(1.0f + ex), maxz = minz + 1.0f + logf(1.0f + ey);
+        g_zmin[t] += gmin * -(ex / (1.0f + ex)) / (minz * minz);
+        g_zmax[t] += gmax * -(ey / (1.0f + ey)) / (maxz * maxz);
+    }
+    ld = block_sum(ld, sm);
+    ls = block_sum(ls, sm);
+    if (threadIdx.x == 0) { atomicAdd(losses + MH_L_DEPTH, ld); atomicAdd(losses + MH_L_SILHOUETTE, ls); }
+}
+
+// shape prior (weighted by the batch size per batch, :526) and the scale priors (once per batch, :531-542)
+__global__ void k_shared_priors(const float* __restrict__ betas, const float* __restrict__ betas_ref, const float* __restrict__ xscale, int N,
+                                int T_local, int nbatch_local, float coef_poses, float coef_scales, float* __restrict__ g_betas,
+                                float* __restrict__ g_xscale, float* __restrict__ losses) {
+    __shared__ float sm[32];
+    const int tid = threadIdx.x;
+    float lb = 0.f;
+    for (int e = tid; e < N * MH_NBETA; e += blockDim.x) {
+        const float df = betas[e] - betas_ref[e];
+        lb += fabsf(df);
+        g_betas[e] += coef_poses * (float)T_local * signf(df);
+    }
+    lb = block_sum(lb, sm);
+    float s1 = 0.f, s2 = 0.f;
+    for (int n = tid; n < N; n += blockDim.x) {
+        const float s = powf(1.1f, xscale[n]) - 1.0f;
+        s1 += s; s2 += s * s;
+    }
+    s1 = block_sum(s1, sm);
+    __shared__ float ssum;
+    if (tid == 0) ssum = s1;
+    s2 = block_sum(s2, sm);
+    __syncthreads();
+    const float tot = ssum;
+    for (int n = tid; n < N; n += blockDim.x) {
+        const float sc = powf(1.1f, xscale[n]);
+        const float g = coef_scales * 2.0f * (sc - 1.0f) / (float)N + (coef_scales > 0.f ? 1.0f : 0.0f) * 2.0f * tot;
+        g_xscale[n] += (float)nbatch_local * g * 0.09531017980432493f * sc;
+    }
+    if (tid == 0) {
+        atomicAdd(losses + MH_L_REF_POSES, (float)T_local * lb);
+        atomicAdd(losses + MH_L_SCALE, (float)nbatch_local * (tot * tot + s2 / (float)N));
+    }
+}
+
+int mh_terms_post(mh_ctx* c, cudaStream_t st) {
+    const mh_dims& d = c->d;
+    float* losses = c->grads + c->n_params;
+    if (c->c.depth != 0.f || c->c.silhouette != 0.f) {
+        k_frame_finalize<<<mh_cdiv(d.T, 128), 128, 0, st>>>(c->pfout, c->params + c->off[MH_P_ZMIN_LIN], c->params + c->off[MH_P_ZMAX_LIN],
+                                                            d.T, d.N, c->c.depth, c->grads + c->off[MH_P_ZMIN_LIN],
+                                                            c->grads + c->off[MH_P_ZMAX_LIN], losses);
+        MH_LAUNCHED(c);
+    }
+    k_shared_priors<<<1, 128, 0, st>>>(c->params + c->off[MH_P_BETAS], c->betas_ref, c->params + c->off[MH_P_XSCALE], d.N, d.T,
+                                       mh_cdiv(d.T, d.B), c->c.reg_poses, c->c.reg_scales, c->grads + c->off[MH_P_BETAS],
+                                       c->grads + c->off[MH_P_XSCALE], losses);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// hot loop A (optimizer.py:740-761): one warp per local person-frame.
+//   loss_2d = mean over (T_total, N, 17, 2) of (vis * proj - vis * gt)^2   [pixels]
+__global__ void k_init_2d(const float* __restrict__ j17, const float* __restrict__ vis, const float* __restrict__ pose2d,
+                          const float* __restrict__ trans, const float* __restrict__ xscale, CamParams cam, int T, int N, float inv_count,
+                          float coef_proj, float* __restrict__ g_trans, float* __restrict__ losses) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= T * N) return;
+    const float s = powf(1.1f, xscale[i % N]);
+    float l = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (lane < MH_NJR) {
+        const float* J = j17 + ((size_t)i * MH_NJR + lane) * 3;
+        const float P[3] = {s * J[0] + trans[(size_t)i * 3], s * J[1] + trans[(size_t)i * 3 + 1], s * J[2] + trans[(size_t)i * 3 + 2]};
+        float uv[2];
+        mh_project(P, cam.K, cam.has_kd ? cam.Kd : nullptr, uv);
+        const float v = vis[(size_t)i * MH_NJR + lane];
+        const float* q = pose2d + ((size_t)i * MH_NJR + lane) * 3;
+        const float du = v * uv[0] - v * q[0], dv = v * uv[1] - v * q[1];
+        l = du * du + dv * dv;
+        float gP[3];
+        mh_project_bwd(P, cam.K, cam.has_kd ? cam.Kd : nullptr, coef_proj * 2.0f * du * v * inv_count, coef_proj * 2.0f * dv * v * inv_count, gP);
+        g0 = gP[0]; g1 = gP[1]; g2 = gP[2];
+    }
+    l = warp_sum(l); g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
+    if (lane == 0) {
+        atomicAdd(losses + MH_L_INIT_2D, l);
+        g_trans[(size_t)i * 3] += g0; g_trans[(size_t)i * 3 + 1] += g1; g_trans[(size_t)i * 3 + 2] += g2;
+    }
+}
+
+int mh_init_iter_grads(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) {
+    const mh_dims& d = c->d;
+    const int TN = d.T * d.N;
+    if (d.t0 == 0) use_prev = 0;
+    if (d.t0 + d.T == d.T_total) use_next = 0;
+    float* losses = c->grads + c->n_params;
+    float* g_trans = c->grads + c->off[MH_P_POSES_T];
+    MH_CUDA(c, cudaMemsetAsync(g_trans, 0, sizeof(float) * TN * 3, st));
+    MH_CUDA(c, cudaMemsetAsync(losses, 0, sizeof(float) * MH_L_COUNT, st));
+    MH_TRY(mh_terms_gather(c, use_prev, use_next, st));
+    const float inv_count = 1.0f / ((float)d.T_total * d.N * MH_NJR * 2);
+    k_init_2d<<<mh_cdiv(TN, 4), 128, 0, st>>>(c->init_j17, c->init_vis, c->pose2d, c->params + c->off[MH_P_POSES_T],
+                                              c->params + c->off[MH_P_XSCALE], cam_of(c), d.T, d.N, inv_count, c->c.proj2d, g_trans, losses);
+    MH_LAUNCHED(c);
+    k_velocity<<<mh_cdiv(TN * 3, 256), 256, 0, st>>>(c->trans_all, d.T, d.N, d.t0, d.T_total, use_prev, use_next, c->c.reg_velocity, g_trans,
+                                                     losses);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}

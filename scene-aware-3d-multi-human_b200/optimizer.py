@@ -1,0 +1,417 @@
+"""Drop-in replacement of the reference's ``mhmocap.optimizer`` for the B200.
+
+Keeps the public interface of ``SMPLDepthSequenceOptimizer`` (``mhmocap/optimizer.py:146-770``) -- constructor
+keywords, ``init_optimized_variables``, ``fit``, ``get_optimized_variables``, ``update_scene_pointcloud``,
+``one_euro_filter`` -- so that the reference's ``Predictor`` (``mhmocap/predict.py:290-306, 332-344``) drives it
+unchanged, while every per-iteration computation runs in ``libmhopt.so`` (hand-written sm_100a kernels behind the C
+ABI of ``include/mhopt.h``).  There is no CPU path: constructing the optimiser without a CUDA device raises.
+
+Differences from the reference that a caller can observe (all documented in DESIGN.md):
+  * the dataloader is consumed ONCE (first cycle): the modalities stay resident in HBM, keyed by ``idxs``;
+    with ``shuffle=False`` the objective is identical, with ``shuffle=True`` the reference's foot-sliding term
+    pairs random frames (``optimizer.py:512-518``) whereas this implementation always pairs frame t with t-1
+    inside batches of ``batch_size`` consecutive frames;
+  * ``fit(num_iter <= 30)`` returns (scene outputs ``None``) instead of raising ``UnboundLocalError``
+    (``optimizer.py:595``);
+  * with ``torch.distributed`` initialised, frames are sharded over the ranks (``sharding.py``).
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import camera
+from . import scene as scene_ops
+from . import sharding
+from . import smpl_io
+
+L = _lib
+
+
+def _device_ordinal(device):
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError('scene-aware-3d-multi-human_b200 needs a CUDA device (sm_100a); there is no CPU path')
+        return torch.cuda.current_device()
+    dev = torch.device(device)
+    if dev.type != 'cuda':
+        raise RuntimeError(f'device {dev} requested: this implementation runs on CUDA devices only (no CPU path)')
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+class _DevView(object):
+    """Exposes a raw device pointer of the library as a ``__cuda_array_interface__`` object."""
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+
+
+class SMPLOptimizerBase(object):
+    """Model paths and joint weights of ``SMPLOptimizerBase.__init__`` (``optimizer.py:35-131``)."""
+
+    def __init__(self, device=None, smpl_model_parameters_path='model_data/parameters',
+                 smpl_J_reg_extra_path='J_regressor_extra.npy', smpl_J_reg_h37m_path='J_regressor_h36m.npy',
+                 smpl_J_reg_alphapose_path='SMPL_AlphaPose_Regressor_RMSprop_6.npy',
+                 smpl_sparse_joints_key='joints_alphapose', pose24j_weights=None, pose17j_weights=None,
+                 process_group=None, scene_update=True, max_scene_points=None):
+        self.device_ordinal = _device_ordinal(device)
+        self.device = torch.device('cuda', self.device_ordinal)
+        if smpl_sparse_joints_key != 'joints_alphapose':
+            raise NotImplementedError('only the AlphaPose 17-joint regressor is wired into the kernels '
+                                      '(the reference default, optimizer.py:40)')
+        self.smpl_model_parameters_path = os.path.abspath(smpl_model_parameters_path)
+        self.smpl_sparse_joints_key = smpl_sparse_joints_key
+        self.model = smpl_io.load_smpl_model(smpl_model_parameters_path, alphapose_regressor=smpl_J_reg_alphapose_path)
+        self.faces_smpl = self.model['faces']
+        w24 = np.ones(24, np.float32) if pose24j_weights is None else np.array(pose24j_weights, np.float32)
+        self.pose24j_weights = len(w24) * w24 / np.sum(w24)
+        w17 = np.ones(17, np.float32) if pose17j_weights is None else np.array(pose17j_weights, np.float32)
+        self.pose17j_weights = (len(w17) * w17 / np.sum(w17)).astype(np.float32)          # optimizer.py:127-130
+        self.group = process_group
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.rank = torch.distributed.get_rank(process_group)
+            self.world = torch.distributed.get_world_size(process_group)
+        else:
+            self.rank, self.world = 0, 1
+        self.scene_update = scene_update
+        self.max_scene_points = max_scene_points
+
+
+class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
+    """Space-time SMPL fit of a whole sequence (``optimizer.py:146-770``) on ``libmhopt.so``."""
+
+    def __init__(self, image_size, num_frames, fov=60, focal_length=None, znear=1.0, zfar=100.0, cam_K=None,
+                 cam_dist_coef=None, proj2d_loss_coef=1.0, depth_loss_coef=1.0, silhouette_loss_coef=1.0,
+                 reg_velocity_coef=1.0, reg_verts_filter_coef=1.0, reg_poses_coef=1.0, reg_scales_coef=1.0,
+                 reg_contact_coef=1.0, reg_foot_sliding_coef=1.0, joint_confidence_thr=0.5, eps=1e-3, **kargs):
+        """``image_size`` is (W, H) as the callers pass it (``predict.py:292``, ``datautils.py:601``)."""
+        super().__init__(**kargs)
+        if focal_length is None:
+            focal_length = camera.get_focal(min(image_size), fov)
+        if cam_K is None:
+            # the reference's fallback (optimizer.py:193-197), axes as written there
+            self.cam_K = np.array([[focal_length, 0, image_size[1] / 2.0], [0, focal_length, image_size[0] / 2.0],
+                                   [0, 0, 1]], dtype=np.float32)
+        else:
+            self.cam_K = np.asarray(cam_K).astype(np.float32)
+        self.cam_dist_coef = cam_dist_coef
+        self.znear, self.zfar = znear, zfar
+        self.K_ndc = camera.compute_calibration_matrix(znear, zfar, self.cam_K, image_size)       # optimizer.py:206
+        self.coefs = dict(proj2d=proj2d_loss_coef, depth=depth_loss_coef, silhouette=silhouette_loss_coef,
+                          reg_velocity=reg_velocity_coef, reg_verts_filter=reg_verts_filter_coef, reg_poses=reg_poses_coef,
+                          reg_scales=reg_scales_coef, reg_contact=reg_contact_coef, reg_foot_sliding=reg_foot_sliding_coef,
+                          joint_confidence_thr=joint_confidence_thr, eps=eps)
+        self.proj2d_loss_coef, self.depth_loss_coef, self.silhouette_loss_coef = proj2d_loss_coef, depth_loss_coef, silhouette_loss_coef
+        self.reg_velocity_coef, self.reg_verts_filter_coef, self.reg_poses_coef = reg_velocity_coef, reg_verts_filter_coef, reg_poses_coef
+        self.reg_scales_coef, self.reg_contact_coef, self.reg_foot_sliding_coef = reg_scales_coef, reg_contact_coef, reg_foot_sliding_coef
+        self.joint_confidence_thr, self.eps = joint_confidence_thr, eps
+        self.num_frames = num_frames
+        self.img_w, self.img_h = image_size
+        self.ctx = None
+        self.scene_depth = None
+        self.scene_pcd = None
+        self.scene_img = None
+        self.scene_mask = None
+        self.poses_T_filtered = None
+        self.verts_filtered = None
+        self._ingested = False
+        self._images = None
+        self._backmasks = None
+
+    # ------------------------------------------------------------------------------------------ context
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _make_context(self, T_total, N, B=None):
+        self.num_people = N
+        self.T_total = T_total
+        Bq = B if B else T_total
+        self.ranges = [sharding.frame_range(T_total, Bq, r, self.world) for r in range(self.world)]
+        self.t0, self.t1 = self.ranges[self.rank]
+        if self.t1 <= self.t0:
+            raise RuntimeError(f'rank {self.rank} owns no frames: {T_total} frames in batches of {Bq} over {self.world} ranks')
+        self.prev, self.next = sharding.neighbours(self.rank, self.world, self.ranges)
+        self.T_local = self.t1 - self.t0
+        torch.cuda.set_device(self.device)
+        self.ctx = L.Context(self.T_local, N, self.img_h, self.img_w, B=Bq, device=self.device_ordinal, rank=self.rank,
+                             world=self.world, t0=self.t0, T_total=T_total,
+                             M_max=self.max_scene_points if self.max_scene_points else self.img_h * self.img_w)
+        self.ctx.set_model(self.model)
+        self.ctx.set_camera(self.cam_K, self.K_ndc, self.cam_dist_coef)
+        self.ctx.set_coefs(**self.coefs)
+        w = np.ascontiguousarray(self.pose17j_weights, np.float32)
+        self.ctx.call('mh_set_joint_weights', w.ctypes.data_as(L.FP))
+        self._views = {}
+
+    def _view(self, which):
+        """torch tensor aliasing a device buffer of the library (for the NCCL plumbing)."""
+        if which not in self._views:
+            p, n = self.ctx.device_view(which)
+            self._views[which] = torch.as_tensor(_DevView(p, n), device=self.device)
+        return self._views[which]
+
+    def _set_batch(self, B):
+        ranges = [sharding.frame_range(self.T_total, B, r, self.world) for r in range(self.world)]
+        if ranges != self.ranges:
+            raise RuntimeError(f'the dataloader batch size {B} changes the frame sharding chosen at init; pass '
+                               f'batch_size={B} to init_optimized_variables')
+        self.ctx.call('mh_set_batch', B)
+        self.batch_size = B
+
+    def _exchange_halo(self):
+        if self.world == 1:
+            return 0, 0
+        self.ctx.call('mh_halo_pack', self._stream())
+        n = self.num_people * 75
+        send = self._view(L.BUF_HALO_SEND).view(2, n)
+        recv = self._view(L.BUF_HALO_RECV).view(2, n)
+        hp, hn = sharding.exchange_halo(send, recv, self.prev, self.next, self.group)
+        return int(hp), int(hn)
+
+    # ------------------------------------------------------------------------------------------ init
+    def init_optimized_variables(self, pose2d, poses_smpl, betas_smpl, valid_smpl, scale_factor=None, num_iter=100,
+                                 batch_size=None):
+        """``optimizer.py:262-321``; arrays cover the WHOLE sequence on every rank.  ``batch_size`` (extension) fixes
+        the frame sharding when it is known before ``fit``."""
+        assert (pose2d.shape[:2] == poses_smpl.shape[:2] == betas_smpl.shape[:2] == valid_smpl.shape[:2]), (
+            f'Error: invalid inputs {pose2d.shape}, {poses_smpl.shape}, {betas_smpl.shape}, {valid_smpl.shape}')
+        T, N = pose2d.shape[0:2]
+        if self.ctx is not None:
+            self.ctx.close()
+        self._make_context(T, N, batch_size)
+        ctx, st = self.ctx, self._stream()
+        sl = slice(self.t0, self.t1)
+        if scale_factor is not None:
+            xs = (np.log(scale_factor) / np.log(1.1)).astype(np.float32)
+            self.optim_scale_factor = False
+        else:
+            xs = np.zeros(N, np.float32)
+            self.optim_scale_factor = True
+        ctx.call('mh_set_optimize_scale', int(self.optim_scale_factor))
+        ctx.set_param(L.P_XSCALE, xs.reshape(N), st)
+        optim_log = self.__init_global_poses(pose2d[sl], poses_smpl[sl], betas_smpl[sl], num_iter)
+        # remaining leaves (optimizer.py:291-303)
+        poses_T_local = ctx.get_param(L.P_POSES_T, (self.T_local, N, 3))
+        max_z = np.clip(np.max(poses_T_local[..., 2], axis=1), 2, None)
+        ctx.set_param(L.P_POSES_SMPL, poses_smpl[sl], st)
+        avg_betas = np.mean(betas_smpl, axis=0, keepdims=True).astype(np.float32)              # (1, N, 10), mean over ALL frames
+        ctx.set_param(L.P_BETAS, avg_betas, st)
+        ctx.set_param(L.P_BETAS_REF, avg_betas, st)
+        self.valid_smpl = (valid_smpl > 0.7).astype(np.float32)
+        ctx.set_param(L.P_ZMIN_LIN, np.ones_like(max_z), st)
+        ctx.set_param(L.P_ZMAX_LIN, 2.0 * max_z, st)
+        self.scene_depth = self.scene_pcd = None
+        self.poses_T_filtered = self.verts_filtered = None
+        ctx.call('mh_clear_filters')
+        ctx.call('mh_set_scene', None, 0, st)
+        self._ingested = False
+        return optim_log
+
+    def __init_global_poses(self, pose2d, poses_smpl, betas_smpl, num_iter, joints_thr=0.15):
+        """Hot loop A (``optimizer.py:710-770``): Adam(lr .5, betas (.5,.5), eps 1e-6) + ExponentialLR(.95) on poses_T."""
+        ctx, st = self.ctx, self._stream()
+        p2d, th, be = L.f32(pose2d), L.f32(poses_smpl), L.f32(betas_smpl)
+        ctx.call('mh_init_begin', L.ptr(p2d), L.ptr(th), L.ptr(be), joints_thr, st)
+        lr = 0.5
+        log = []
+        count = float(self.T_total * self.num_people * 17 * 2)
+        for it in range(num_iter):
+            hp, hn = self._exchange_halo()
+            ctx.call('mh_init_grads', hp, hn, st)
+            if self.world > 1:
+                sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
+            ctx.call('mh_init_update', lr, it + 1, st)
+            lr *= 0.95
+            losses = ctx.read_losses(st)
+            log.append({'loss_2d': np.float32(losses[L.L_INIT_2D] / count)})
+        return log
+
+    # ------------------------------------------------------------------------------------------ ingest
+    def _ingest(self, dataloader):
+        """One pass over the dataloader (``optimizer.py:394-400``): every modality goes to the device once."""
+        ctx, st = self.ctx, self._stream()
+        H, W, N = self.img_h, self.img_w, self.num_people
+        seen = np.zeros(self.T_total, bool)
+        B = None
+        keep_scene = self.scene_update
+        if keep_scene:
+            self._images = np.zeros((self.T_local, H, W, 3), np.uint8)
+            self._backmasks = np.zeros((self.T_local, H, W), np.float32)
+        for data in dataloader:
+            idxs = np.asarray(data['idxs']).astype(np.int64).reshape(-1)
+            if B is None:
+                B = len(idxs)
+                self._set_batch(B)
+            arr = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in data.items()
+                   if k in ('depths', 'seg_mask', 'pose2d', 'poses_smpl', 'images', 'backmasks')}
+            for j, t in enumerate(idxs):
+                seen[t] = True
+                if not (self.t0 <= t < self.t1):
+                    continue
+                tl = int(t - self.t0)
+                dep = L.f32(arr['depths'][j]); seg = L.f32(arr['seg_mask'][j]); p2d = L.f32(arr['pose2d'][j])
+                th = L.f32(arr['poses_smpl'][j]); vl = L.f32(self.valid_smpl[t].reshape(N))
+                assert dep.shape == (H, W) and seg.shape == (N, H, W), (dep.shape, seg.shape)
+                ctx.call('mh_ingest_frames', tl, 1, L.ptr(dep), L.ptr(seg), L.ptr(p2d), L.ptr(th), L.ptr(vl), st)
+                torch.cuda.current_stream(self.device).synchronize()       # host buffers are temporaries
+                if keep_scene:
+                    self._images[tl] = arr['images'][j]
+                    self._backmasks[tl] = arr['backmasks'][j] / 1.0
+        if not seen.all():
+            raise RuntimeError(f'the dataloader did not deliver frames {np.nonzero(~seen)[0][:8]}...')
+        ctx.call('mh_finalize_ingest', st)
+        self._ingested = True
+
+    # ------------------------------------------------------------------------------------------ fit
+    def fit(self, dataloader, num_iter=250, min_cutoff1=0.01, min_cutoff2=0.001, beta1=0.02, beta2=0.5,
+            update_filters_every=25, verbose=False):
+        """Hot loop B (``optimizer.py:324-602``): RMSprop(lr .01, alpha .5, momentum .9) + ExponentialLR(.99), one
+        step per pass over the video.  Returns the reference's ``optim_log``."""
+        ctx, st = self.ctx, self._stream()
+        if not self._ingested:
+            self._ingest(dataloader)
+        if not self.optim_scale_factor:
+            print('WARNING!!! Not optimizing scale_factor!')
+        ctx.call('mh_reset_optimizer', st)
+        n_batches = (self.T_total + self.batch_size - 1) // self.batch_size
+        lr = 0.01
+        optim_log = []
+        cycles = range(num_iter)
+        if verbose:
+            from tqdm import tqdm
+            cycles = tqdm(cycles)
+        ma = None
+        for cycle in cycles:
+            if (cycle >= 30) and (cycle % update_filters_every == 0):
+                self._refresh_filters(min_cutoff1, beta1, min_cutoff2, beta2)
+            hp, hn = self._exchange_halo()
+            ctx.call('mh_fit_grads', hp, hn, st)
+            if self.world > 1:
+                sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
+            if cycle >= 30 and self.scene_update:
+                ma = self._update_scene_geometry()
+            ctx.call('mh_fit_update', lr, st)
+            lr *= 0.99
+            losses = ctx.read_losses(st)
+            optim_log.append(sharding.log_from_loss_block(losses, n_batches))
+        if ma is not None:
+            scene_img, scene_mask = ma[0].copy(), ma[2].copy()
+            while scene_mask.min() == 0:
+                scene_img, scene_mask = scene_ops.fillin_values(scene_img, scene_mask, filter_size=11)
+            self.scene_img, self.scene_mask = scene_img, scene_mask
+        return optim_log
+
+    def step_device_only(self, lr):
+        """One cycle without any host readback (bench inner loop): halo, gradients, all-reduce, update."""
+        hp, hn = self._exchange_halo()
+        st = self._stream()
+        self.ctx.call('mh_fit_grads', hp, hn, st)
+        if self.world > 1:
+            sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
+        self.ctx.call('mh_fit_update', lr, st)
+
+    def _refresh_filters(self, mc1, b1, mc2, b2, frame_rate=25):
+        """``optimizer.py:383-392``: the One-Euro scan is sequential in time, so the ranks run it one after the other,
+        handing the filter state over; then the filtered boundary frames are exchanged for the halo slots."""
+        ctx, st = self.ctx, self._stream()
+        if self.world > 1:
+            sharding.pass_carry(None, self._view(L.BUF_CARRY_IN), self.prev, self.next, self.group)
+        ctx.call('mh_refresh_filters', mc1, b1, mc2, b2, float(frame_rate), int(self.prev is None), st)
+        if self.world > 1:
+            sharding.send_carry(self._view(L.BUF_CARRY_OUT), self.next, self.group)
+            row = self.num_people * L.LD3V
+            F = self._view(L.BUF_FILTERED).view(self.T_local + 2, row)
+            send = torch.stack([F[1], F[self.T_local]])
+            recv = torch.empty_like(send)
+            hp, hn = sharding.exchange_halo(send, recv, self.prev, self.next, self.group)
+            if hp:
+                F[0].copy_(recv[0])
+            if hn:
+                F[self.T_local + 1].copy_(recv[1])
+        self.poses_T_filtered = True
+        self.verts_filtered = True
+
+    def _update_scene_geometry(self):
+        """``optimizer.py:578-584``: masked temporal median of the per-frame scene depths -> post-processing -> cloud."""
+        depths = np.empty((self.T_local, self.img_h, self.img_w), np.float32)
+        self.ctx.call('mh_scene_depths', 0, self.T_local, L.ptr(depths))
+        images, backmasks = self._images, self._backmasks
+        if self.world > 1:
+            gathered = [None] * self.world if self.rank == 0 else None
+            torch.distributed.gather_object((depths, images, backmasks), gathered, dst=0, group=self.group)
+            if self.rank == 0:
+                depths = np.concatenate([g[0] for g in gathered], 0)
+                images = np.concatenate([g[1] for g in gathered], 0)
+                backmasks = np.concatenate([g[2] for g in gathered], 0)
+        out = [None]
+        if self.rank == 0:
+            ma_image, ma_depth, ma_mask = scene_ops.aggregate_scene_geometry_median(depths, images, backmasks)
+            scene_depth = scene_ops.postprocess_depthmap(ma_depth, ma_mask, use_bilateral_filter=True)
+            out = [(ma_image, ma_depth, ma_mask, scene_depth)]
+        if self.world > 1:
+            torch.distributed.broadcast_object_list(out, src=0, group=self.group)
+        ma_image, ma_depth, ma_mask, scene_depth = out[0]
+        self.scene_depth = scene_depth
+        self.update_scene_pointcloud(scene_depth, ma_mask)
+        return ma_image, ma_depth, ma_mask
+
+    def update_scene_pointcloud(self, scene_depth, scene_mask):
+        """``optimizer.py:605-616``: inverse-project the pixel centres with the scene depth, keep ``mask > 0.5``."""
+        d = L.f32(scene_depth)
+        m = np.ascontiguousarray(np.asarray(scene_mask).astype(np.float32) > 0.5).astype(np.uint8)
+        self.ctx.call('mh_set_scene_from_depth', L.ptr(d), L.ptr(m), self._stream())
+        self.scene_depth = scene_depth
+        self.scene_pcd = True
+
+    def set_scene_pcd(self, pcd):
+        """Extension: hand the scene cloud (M, 3) over directly (frozen-scene runs)."""
+        p = L.f32(pcd).reshape(-1, 3)
+        self.ctx.call('mh_set_scene', L.ptr(p), p.shape[0], self._stream())
+        torch.cuda.current_stream(self.device).synchronize()
+        self.scene_pcd = True
+        self.scene_depth = True
+
+    # ------------------------------------------------------------------------------------------ outputs
+    def _gather_frames(self, local):
+        if self.world == 1:
+            return local
+        parts = [None] * self.world
+        torch.distributed.all_gather_object(parts, local, group=self.group)
+        return np.concatenate([p for p in parts if p is not None and len(p)], axis=0)
+
+    def get_optimized_variables(self):
+        """``optimizer.py:619-636`` (same keys and shapes)."""
+        ctx, N, T = self.ctx, self.num_people, self.T_local
+        xs = ctx.get_param(L.P_XSCALE, (1, N, 1, 1))
+        zmin_lin = ctx.get_param(L.P_ZMIN_LIN, (T, 1, 1))
+        zmax_lin = ctx.get_param(L.P_ZMAX_LIN, (T, 1, 1))
+        min_z = np.log(1.0 + np.exp(zmin_lin)).astype(np.float32)                                  # transforms.py:296
+        max_z = (min_z + 1.0 + np.log(1.0 + np.exp(zmax_lin))).astype(np.float32)
+        return {
+            'scale_factor': np.power(np.float32(1.1), xs).astype(np.float32),
+            'poses_T': self._gather_frames(ctx.get_param(L.P_POSES_T, (T, N, 1, 3))),
+            'poses_smpl': self._gather_frames(ctx.get_param(L.P_POSES_SMPL, (T, N, 72))),
+            'betas_smpl': ctx.get_param(L.P_BETAS, (1, N, 10)),
+            'valid_smpl': self.valid_smpl,
+            'min_z': self._gather_frames(min_z),
+            'max_z': self._gather_frames(max_z),
+            'scene_depth': self.scene_depth if isinstance(self.scene_depth, np.ndarray) else None,
+            'scene_img': self.scene_img,
+            'scene_mask': self.scene_mask,
+        }
+
+    def one_euro_filter(self, x, min_cutoff=0.1, beta=0.02, frame_rate=25):
+        """``optimizer.py:664-675`` on the device: x (T, ...) -> filtered float32 tensor on ``self.device``."""
+        y = L.f32(x.detach().cpu().numpy() if torch.is_tensor(x) else x)
+        out = np.empty_like(y)
+        T = y.shape[0]
+        self.ctx.call('mh_one_euro_filter', L.ptr(y), L.ptr(out), T, y.size // T, float(min_cutoff), float(beta), float(frame_rate))
+        return torch.from_numpy(out).to(self.device)
+
+    def smpl_forward(self, betas, poses):
+        """``SMPL.forward`` (``smpl.py:297-399``) through the kernels: (verts (nb,6890,3), joints_alphapose (nb,17,3))."""
+        b, p = L.f32(betas).reshape(-1, 10), L.f32(poses).reshape(-1, 72)
+        verts = np.empty((b.shape[0], L.V, 3), np.float32)
+        j17 = np.empty((b.shape[0], 17, 3), np.float32)
+        self.ctx.call('mh_smpl_forward', L.ptr(b), L.ptr(p), b.shape[0], L.ptr(verts), L.ptr(j17))
+        return verts, j17

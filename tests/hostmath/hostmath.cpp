@@ -12,12 +12,12 @@ void hm_project(const float* P, const float* K, const float* Kd, float* uv) { mh
 void hm_project_bwd(const float* P, const float* K, const float* Kd, float gu, float gv, float* gP) { mh_project_bwd(P, K, Kd, gu, gv, gP); }
 // verts: 9 floats (x0,y0,z0,x1,y1,z1,x2,y2,z2) NDC; out: pz, dist, inside, valid
 void hm_face_eval(const float* v, float px, float py, float* out) {
-    MhFace f; mh_face_setup(v, v + 3, v + 6, &f);
+    MhFace f; mh_face_setup(v, v + 3, v + 6, 1.0f, &f);
     MhFrag fr; bool ok = mh_face_eval(f, px, py, &fr);
-    out[0] = fr.pz; out[1] = fr.dist; out[2] = fr.inside ? 1.f : 0.f; out[3] = (ok && f.flags == 0.f) ? 1.f : 0.f;
+    out[0] = fr.pz; out[1] = fr.dist; out[2] = fr.inside ? 1.f : 0.f; out[3] = (ok && !f.skip) ? 1.f : 0.f;
 }
 void hm_face_bwd(const float* v, float px, float py, float gz, float gd, float* g) {
-    MhFace f; mh_face_setup(v, v + 3, v + 6, &f);
+    MhFace f; mh_face_setup(v, v + 3, v + 6, 1.0f, &f);
     for (int i = 0; i < 9; ++i) g[i] = 0.f;
     mh_face_bwd(f, px, py, gz, gd, g);
 }
