@@ -205,6 +205,11 @@ int mh_debug_render(mh_ctx* ctx, int32_t t_local, int32_t n, float* zbuf_host, f
 int mh_synth_planes(mh_ctx* ctx, float y_ground, float z_wall, void* stream);
 /* copies the context's planes of frames [t_local0, t_local0+count) back to HOST buffers (either may be NULL) */
 int mh_read_planes(mh_ctx* ctx, int32_t t_local0, int32_t count, float* depths_host, float* seg_host);
+/* CUDA-event timing of the stages of mh_fit_grads on the caller's stream, ring of the last 64 cycles.
+ * mh_read_timing: out (n_cycles, 6) ms [smpl forward | pre-raster terms | order prepass | render | smpl backward | post terms],
+ * oldest first; *n_cycles is the capacity in and the number of cycles written out.  Blocking. */
+int mh_set_timing(mh_ctx* ctx, int32_t on);
+int mh_read_timing(mh_ctx* ctx, float* out_ms, int32_t* n_cycles);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t mh_launch_count(const mh_ctx* ctx);
 

@@ -90,6 +90,8 @@ def _load():
         'mh_debug_render': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p]),
         'mh_synth_planes': (c_int32, [ctx, c_float, c_float, c_void_p]),
         'mh_read_planes': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p]),
+        'mh_set_timing': (c_int32, [ctx, c_int32]),
+        'mh_read_timing': (c_int32, [ctx, c_void_p, ctypes.POINTER(c_int32)]),
         'mh_launch_count': (c_int64, [ctx]),
     }
     for name, (res, args) in sig.items():
@@ -198,6 +200,12 @@ class Context(object):
         out = np.zeros(L_COUNT, np.float32)
         self.call('mh_read_losses', ptr(out), stream)
         return out
+
+    def read_timing(self, n=64):
+        out = np.zeros((n, 6), np.float32)
+        k = c_int32(n)
+        self.call('mh_read_timing', ptr(out), ctypes.byref(k))
+        return out[:k.value]
 
     def launches(self):
         return int(lib.mh_launch_count(self.h))

@@ -62,6 +62,7 @@ extern "C" int mh_create(mh_ctx** out, const mh_dims* dims) {
     c->optim_scale = true;
     c->rs = nullptr;
     c->M = 0;
+    c->events = nullptr; c->timing = false; c->timing_iter = 0;
     for (int k = 0; k < MH_NJR; ++k) c->w17[k] = 1.0f;
     *out = c;     // returned even on failure so that the caller can read the error text, then mh_destroy
     const mh_dims& d = c->d;
@@ -150,6 +151,7 @@ extern "C" void mh_destroy(mh_ctx* c) {
     cudaSetDevice(c->d.device);
     cudaDeviceSynchronize();
     mh_render_free(c);
+    if (c->events) { for (int i = 0; i < MH_TIMING_RING * MH_TIMING_EVENTS; ++i) cudaEventDestroy(c->events[i]); delete[] c->events; }
     for (void* p : c->allocs) cudaFree(p);
     if (c->stage) cudaFree(c->stage);
     delete c;
@@ -598,18 +600,62 @@ extern "C" int mh_fit_grads(mh_ctx* c, int32_t use_prev, int32_t use_next, void*
     const mh_dims& d = c->d;
     if (d.t0 == 0) use_prev = 0;
     if (d.t0 + d.T == d.T_total) use_next = 0;
+    cudaEvent_t* ev = nullptr;
+    if (c->timing) {
+        ev = c->events + (size_t)(c->timing_iter % MH_TIMING_RING) * MH_TIMING_EVENTS;
+        c->timing_iter++;
+    }
+#define MH_MARK(k) do { if (ev) MH_CUDA(c, cudaEventRecord(ev[k], st)); } while (0)
+    MH_MARK(0);
     MH_CUDA(c, cudaMemsetAsync(c->grads, 0, sizeof(float) * (c->n_params + MH_L_COUNT), st));
     MH_TRY(mh_terms_gather(c, use_prev, use_next, st));
     MhSmplArgs a = {c->params + c->off[MH_P_BETAS], d.N, 0, c->theta_all, c->trans_all, c->params + c->off[MH_P_XSCALE], c->nb, d.N,
                     c->vshaped, c->Jrest, c->A, c->pf, c->vposed, c->verts, c->j17, c->lowidx};
     MH_TRY(mh_smpl_forward_run(c, a, st));
+    MH_MARK(1);
     MH_TRY(mh_terms_pre_raster(c, use_prev, use_next, st));
+    MH_MARK(2);
     if (c->c.depth != 0.f || c->c.silhouette != 0.f) {
         MH_TRY(mh_render_prepass(c, st));
+        MH_MARK(3);
         MH_TRY(mh_render_all(c, st));
+    } else {
+        MH_MARK(3);
     }
+    MH_MARK(4);
     MH_TRY(mh_smpl_backward_all(c, st));
+    MH_MARK(5);
     MH_TRY(mh_terms_post(c, st));
+    MH_MARK(6);
+#undef MH_MARK
+    return MH_OK;
+}
+
+// Stage timing with CUDA events on the caller's stream (bench.py's roofline): a ring of the last MH_TIMING_RING cycles.
+extern "C" int mh_set_timing(mh_ctx* c, int32_t on) {
+    API_BEGIN(c);
+    if (on && !c->events) {
+        c->events = new cudaEvent_t[(size_t)MH_TIMING_RING * MH_TIMING_EVENTS];
+        for (int i = 0; i < MH_TIMING_RING * MH_TIMING_EVENTS; ++i) MH_CUDA(c, cudaEventCreate(&c->events[i]));
+    }
+    c->timing = on != 0;
+    c->timing_iter = 0;
+    return MH_OK;
+}
+
+// out: (n_cycles, MH_TIMING_STAGES) milliseconds of the most recent cycles, oldest first; *n_cycles in/out. Blocking.
+extern "C" int mh_read_timing(mh_ctx* c, float* out, int32_t* n_cycles) {
+    API_BEGIN(c);
+    if (!c->events || !out || !n_cycles) MH_FAIL(c, MH_E_STATE, "mh_read_timing: timing was not enabled");
+    MH_CUDA(c, cudaDeviceSynchronize());
+    const int64_t have = std::min<int64_t>(c->timing_iter, MH_TIMING_RING);
+    const int n = (int)std::min<int64_t>(have, *n_cycles);
+    for (int k = 0; k < n; ++k) {
+        const int64_t it = c->timing_iter - n + k;
+        cudaEvent_t* ev = c->events + (size_t)(it % MH_TIMING_RING) * MH_TIMING_EVENTS;
+        for (int sgi = 0; sgi < MH_TIMING_STAGES; ++sgi) MH_CUDA(c, cudaEventElapsedTime(out + (size_t)k * MH_TIMING_STAGES + sgi, ev[sgi], ev[sgi + 1]));
+    }
+    *n_cycles = n;
     return MH_OK;
 }
 

@@ -18,6 +18,9 @@
 #define MH_KSPLIT 19           // split-K factor of the backward contraction (20672 = 19 * 1088)
 #define MH_MAXN 32             // persons per frame (bit masks are 32-bit)
 #define MH_KNN 32              // scene points averaged by the contact term (optimizer.py:494)
+#define MH_TIMING_RING 64
+#define MH_TIMING_STAGES 6      // smpl forward | pre-raster terms | order prepass | render | smpl backward | post terms
+#define MH_TIMING_EVENTS 7
 #define MH_HALO 75             // floats per person in a halo frame: theta (72) + T (3)
 
 // per person-frame outputs of the render stage (floats)
@@ -108,6 +111,8 @@ struct mh_ctx {
     float* carry_in; float* carry_out; int64_t carry_floats;
     float* transfilt;          // (T*N*3) filtered translations (only a not-None flag upstream)
     MhRenderScratch* rs;
+    // stage timing (bench)
+    cudaEvent_t* events; bool timing; int64_t timing_iter;
 };
 
 #define MH_FAIL(ctx, code, ...) do { snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); return (code); } while (0)

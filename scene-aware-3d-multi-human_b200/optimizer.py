@@ -232,6 +232,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         ctx, st = self.ctx, self._stream()
         H, W, N = self.img_h, self.img_w, self.num_people
         seen = np.zeros(self.T_total, bool)
+        self.h2d_bytes = 0
         B = None
         keep_scene = self.scene_update
         if keep_scene:
@@ -244,20 +245,29 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
                 self._set_batch(B)
             arr = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in data.items()
                    if k in ('depths', 'seg_mask', 'pose2d', 'poses_smpl', 'images', 'backmasks')}
-            for j, t in enumerate(idxs):
-                seen[t] = True
+            seen[idxs] = True
+            # runs of consecutive frames owned by this rank go to the device in one call
+            j = 0
+            while j < len(idxs):
+                t = int(idxs[j])
                 if not (self.t0 <= t < self.t1):
+                    j += 1
                     continue
-                tl = int(t - self.t0)
-                dep = L.f32(arr['depths'][j]); seg = L.f32(arr['seg_mask'][j]); p2d = L.f32(arr['pose2d'][j])
-                th = L.f32(arr['poses_smpl'][j]); vl = L.f32(self.valid_smpl[t].reshape(N))
-                assert dep.shape == (H, W) and seg.shape == (N, H, W), (dep.shape, seg.shape)
-                ctx.call('mh_ingest_frames', tl, 1, L.ptr(dep), L.ptr(seg), L.ptr(p2d), L.ptr(th), L.ptr(vl), st)
-                torch.cuda.current_stream(self.device).synchronize()       # host buffers are temporaries
+                e = j + 1
+                while e < len(idxs) and int(idxs[e]) == int(idxs[e - 1]) + 1 and int(idxs[e]) < self.t1:
+                    e += 1
+                tl, cnt = t - self.t0, e - j
+                dep = L.f32(arr['depths'][j:e]); seg = L.f32(arr['seg_mask'][j:e]); p2d = L.f32(arr['pose2d'][j:e])
+                th = L.f32(arr['poses_smpl'][j:e]); vl = L.f32(self.valid_smpl[t:t + cnt].reshape(cnt, N))
+                assert dep.shape == (cnt, H, W) and seg.shape == (cnt, N, H, W), (dep.shape, seg.shape)
+                ctx.call('mh_ingest_frames', tl, cnt, L.ptr(dep), L.ptr(seg), L.ptr(p2d), L.ptr(th), L.ptr(vl), st)
+                torch.cuda.current_stream(self.device).synchronize()       # the host buffers may be temporaries
+                self.h2d_bytes += dep.nbytes + seg.nbytes + p2d.nbytes + th.nbytes + vl.nbytes
                 if keep_scene:
-                    self._images[tl] = arr['images'][j]
-                    self._backmasks[tl] = arr['backmasks'][j] / 1.0
-        if not seen.all():
+                    self._images[tl:tl + cnt] = arr['images'][j:e]
+                    self._backmasks[tl:tl + cnt] = arr['backmasks'][j:e] / 1.0
+                j = e
+        if not seen[self.t0:self.t1].all() or not (seen.all() or getattr(self, 'partial_loader_ok', False)):
             raise RuntimeError(f'the dataloader did not deliver frames {np.nonzero(~seen)[0][:8]}...')
         ctx.call('mh_finalize_ingest', st)
         self._ingested = True
@@ -408,10 +418,10 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         self.ctx.call('mh_one_euro_filter', L.ptr(y), L.ptr(out), T, y.size // T, float(min_cutoff), float(beta), float(frame_rate))
         return torch.from_numpy(out).to(self.device)
 
-    def smpl_forward(self, betas, poses):
-        """``SMPL.forward`` (``smpl.py:297-399``) through the kernels: (verts (nb,6890,3), joints_alphapose (nb,17,3))."""
+    def smpl_forward(self, betas, poses, want_verts=True):
+        """``SMPL.forward`` (``smpl.py:297-399``) through the kernels: (verts (nb,6890,3) | None, joints_alphapose (nb,17,3))."""
         b, p = L.f32(betas).reshape(-1, 10), L.f32(poses).reshape(-1, 72)
-        verts = np.empty((b.shape[0], L.V, 3), np.float32)
+        verts = np.empty((b.shape[0], L.V, 3), np.float32) if want_verts else None
         j17 = np.empty((b.shape[0], 17, 3), np.float32)
         self.ctx.call('mh_smpl_forward', L.ptr(b), L.ptr(p), b.shape[0], L.ptr(verts), L.ptr(j17))
         return verts, j17
