@@ -24,10 +24,12 @@
 // (mh_planes.cu) keeps per (frame, order position).
 #include "mh_ctx.h"
 
-#define RT 16
-#define R_THREADS 256
-#define R_MAXBINS 4096
-#define R_CHUNK 128
+#define TW 32                 // tile width  (pixels)
+#define TH 16                 // tile height (pixels)
+#define R_THREADS 512         // one thread per tile pixel in the per-pixel phases
+#define R_MAXBINS 1024
+#define R_CHUNK 256
+#define KEY_EMPTY 0xffffffffffffffffull
 
 struct MhRenderScratch {
     uint16_t* binlist; int bincap;
@@ -56,6 +58,16 @@ struct RenderParams {
     float* dbg_zbuf; float* dbg_alpha; int dbg_body;
 };
 
+// face record staged per tile: everything the (face, pixel) pair evaluation needs
+struct FaceRec {
+    float x0, y0, x1, y1, x2, y2, z0, z1, z2;
+    float den, inv_den;
+    float il01, il02, il12;           // 1 / |edge|^2, 0 when degenerate
+    float bxmin, bxmax, bymin, bymax; // exact bbox inflated by sqrt(blur) (oracle's test)
+    int pxy;                          // pixel rectangle inside the tile: col0 | row0 << 5 | w << 9 | magic(w) << 16
+    int fid;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ float wsum(float v) {
@@ -67,25 +79,56 @@ __device__ __forceinline__ float wsum(float v) {
 // pixel-centre formula; used only for conservative ranges)
 __device__ __forceinline__ float pix_of(float ndc, int S, float r) { return (float)(S - 1) - ((ndc + 0.5f * r) * (float)S - 0.5f * r) / r; }
 
+// approximate squared distance to a segment (reciprocal multiply instead of the oracle's division); only used
+// to decide far from the blur threshold -- near it the exact form is evaluated
+__device__ __forceinline__ float seg_dist_fast(float dx, float dy, float bax, float bay, float il, float dbx, float dby) {
+    if (il == 0.f) return dbx * dbx + dby * dby;
+    const float t = __saturatef((bax * dx + bay * dy) * il);
+    const float qx = dx - t * bax, qy = dy - t * bay;
+    return qx * qx + qy * qy;
+}
+
+__device__ __forceinline__ void load_face(const float* sv, const int32_t* __restrict__ faces, int f, float r, MhFace* fc, int iv[3]) {
+    iv[0] = faces[3 * f]; iv[1] = faces[3 * f + 1]; iv[2] = faces[3 * f + 2];
+    mh_face_setup(sv + 3 * iv[0], sv + 3 * iv[1], sv + 3 * iv[2], r, fc);
+}
+
+__device__ __forceinline__ void key_insert4(unsigned long long* slot /*stride R_THREADS*/, unsigned long long x) {
+    // concurrent sorted insertion: every slot keeps the minimum of what reaches it and passes the rest on
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const unsigned long long old = atomicMin(slot + s * R_THREADS, x);
+        x = old > x ? old : x;
+        if (x == KEY_EMPTY) break;
+    }
+}
+
 template <int MODE>      // 0: losses + gradients ; 1: dense zbuf / alpha planes of one body
 __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* sv = reinterpret_cast<float*>(smem_raw);                       // MH_LD3V  NDC vertices
-    float* sg = sv + MH_LD3V;                                             // MH_LD3V  NDC gradients
-    int* tcount = reinterpret_cast<int*>(sg + MH_LD3V);                   // R_MAXBINS + 1 (exclusive offsets after the scan)
-    int* tcur = tcount + R_MAXBINS + 1;                                   // R_MAXBINS
-    MhFace* sface = reinterpret_cast<MhFace*>(tcur + R_MAXBINS + 3);      // R_CHUNK
-    int* sfid = reinterpret_cast<int*>(sface + R_CHUNK);                  // R_CHUNK
-    float* sred = reinterpret_cast<float*>(sfid + R_CHUNK);               // 64
-    int* sint = reinterpret_cast<int*>(sred + 64);                        // 16
+    float* sv = reinterpret_cast<float*>(smem_raw);                                   // MH_LD3V  NDC vertices
+    float* sg = sv + MH_LD3V;                                                         // MH_LD3V  NDC gradients
+    unsigned long long* dkey = reinterpret_cast<unsigned long long*>(sg + MH_LD3V);   // R_THREADS     nearest depth fragment
+    unsigned long long* skey = dkey + R_THREADS;                                      // 4 x R_THREADS nearest silhouette fragments
+    FaceRec* srec = reinterpret_cast<FaceRec*>(skey + 4 * R_THREADS);                 // R_CHUNK
+    int* spre = reinterpret_cast<int*>(srec + R_CHUNK);                               // R_CHUNK + 1 (+ pad)
+    int* tcount = spre + R_CHUNK + 4;                                                 // R_MAXBINS + 1 (exclusive offsets after the scan)
+    int* tcur = tcount + R_MAXBINS + 1;                                               // R_MAXBINS
+    float* sred = reinterpret_cast<float*>(tcur + R_MAXBINS + 3);                     // 128
+    float* spx = sred + 128;                                                          // TW
+    float* spy = spx + TW;                                                            // TH
+    int* sint = reinterpret_cast<int*>(spy + TH);                                     // 32
     __shared__ __align__(8) unsigned long long mbar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = R_THREADS / 32;
     const int TN = P.T * P.N;
     uint16_t* binlist = P.binlist + (size_t)blockIdx.x * P.bincap;
     int* wpix = P.wpix + (size_t)blockIdx.x * P.wcap;
     int* wface = P.wface + (size_t)blockIdx.x * P.wcap;
     float* wz = P.wz + (size_t)blockIdx.x * P.wcap;
+    const float blur_d_lo = P.blur_d * (1.0f - 1e-5f), blur_d_hi = P.blur_d * (1.0f + 1e-5f);
+    const float blur_s_lo = P.blur_s * (1.0f - 1e-5f), blur_s_hi = P.blur_s * (1.0f + 1e-5f);
     uint32_t phase = 0;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
@@ -133,11 +176,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
             by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
         }
-        if (lane == 0) { sred[warp] = bx0; sred[8 + warp] = bx1; sred[16 + warp] = by0; sred[24 + warp] = by1; }
+        if (lane == 0) { sred[warp] = bx0; sred[NW + warp] = bx1; sred[2 * NW + warp] = by0; sred[3 * NW + warp] = by1; }
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < 8; ++w) {
-                bx0 = fminf(bx0, sred[w]); bx1 = fmaxf(bx1, sred[8 + w]); by0 = fminf(by0, sred[16 + w]); by1 = fmaxf(by1, sred[24 + w]);
+            for (int w = 1; w < NW; ++w) {
+                bx0 = fminf(bx0, sred[w]); bx1 = fmaxf(bx1, sred[NW + w]); by0 = fminf(by0, sred[2 * NW + w]); by1 = fmaxf(by1, sred[3 * NW + w]);
             }
             // pixel bbox of the body (NDC x / y decrease with the pixel index), inflated by the blur radius + 1 px
             int c0 = (int)floorf(fminf(fmaxf(pix_of(bx1 + P.r_d, P.W, P.rx) - 1.f, 0.f), (float)(P.W - 1)));
@@ -145,7 +188,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             int r0 = (int)floorf(fminf(fmaxf(pix_of(by1 + P.r_d, P.H, P.ry) - 1.f, 0.f), (float)(P.H - 1)));
             int r1 = (int)ceilf(fminf(fmaxf(pix_of(by0 - P.r_d, P.H, P.ry) + 1.f, 0.f), (float)(P.H - 1)));
             if (!(bx0 <= bx1)) { c0 = 1; c1 = 0; r0 = 1; r1 = 0; }          // nothing in front of the camera
-            const int tx0 = c0 / RT, tx1 = c1 / RT, ty0 = r0 / RT, ty1 = r1 / RT;
+            const int tx0 = c0 / TW, tx1 = c1 / TW, ty0 = r0 / TH, ty1 = r1 / TH;
             int ntx = max(tx1 - tx0 + 1, 0), nty = max(ty1 - ty0 + 1, 0);
             int ks = 0;
             while ((((ntx + (1 << ks) - 1) >> ks) * ((nty + (1 << ks) - 1) >> ks)) > R_MAXBINS) ++ks;
@@ -170,13 +213,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 if (!(zmax >= 0.f) || ((area <= MH_KEPS) && (area >= -MH_KEPS)) || nbins == 0) continue;
                 const float fx0 = fminf(fminf(x0, x1), x2) - P.r_d, fx1 = fmaxf(fmaxf(x0, x1), x2) + P.r_d;
                 const float fy0 = fminf(fminf(y0, y1), y2) - P.r_d, fy1 = fmaxf(fmaxf(y0, y1), y2) + P.r_d;
-                const float pc0 = pix_of(fx1, P.W, P.rx) - 1.f, pc1 = pix_of(fx0, P.W, P.rx) + 1.f;
-                const float pr0 = pix_of(fy1, P.H, P.ry) - 1.f, pr1 = pix_of(fy0, P.H, P.ry) + 1.f;
-                if (!(pc1 >= 0.f) || !(pr1 >= 0.f) || !(pc0 <= (float)(P.W - 1)) || !(pr0 <= (float)(P.H - 1))) continue;
+                const float pc0 = ceilf(pix_of(fx1, P.W, P.rx) - 0.01f), pc1 = floorf(pix_of(fx0, P.W, P.rx) + 0.01f);
+                const float pr0 = ceilf(pix_of(fy1, P.H, P.ry) - 0.01f), pr1 = floorf(pix_of(fy0, P.H, P.ry) + 0.01f);
+                if (!(pc1 >= 0.f) || !(pr1 >= 0.f) || !(pc0 <= (float)(P.W - 1)) || !(pr0 <= (float)(P.H - 1)) || !(pc0 <= pc1) || !(pr0 <= pr1)) continue;
                 const int c0 = (int)fmaxf(pc0, 0.f), c1 = (int)fminf(pc1, (float)(P.W - 1));
                 const int r0 = (int)fmaxf(pr0, 0.f), r1 = (int)fminf(pr1, (float)(P.H - 1));
-                const int bx_lo = max((c0 / RT - tx0) >> ks, 0), bx_hi = min((c1 / RT - tx0) >> ks, nbx - 1);
-                const int by_lo = max((r0 / RT - ty0) >> ks, 0), by_hi = min((r1 / RT - ty0) >> ks, nby - 1);
+                const int bx_lo = max((c0 / TW - tx0) >> ks, 0), bx_hi = min((c1 / TW - tx0) >> ks, nbx - 1);
+                const int by_lo = max((r0 / TH - ty0) >> ks, 0), by_hi = min((r1 / TH - ty0) >> ks, nby - 1);
                 for (int by = by_lo; by <= by_hi; ++by)
                     for (int bx = bx_lo; bx <= bx_hi; ++bx) {
                         const int bin = by * nbx + bx;
@@ -232,60 +275,154 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             const int bin = (tty >> ks) * nbx + (ttx >> ks);
             const int off = tcount[bin], cnt = tcount[bin + 1] - off;
             if (cnt == 0) continue;
-            const int xi = (tx0 + ttx) * RT + (tid & (RT - 1)), yi = (ty0 + tty) * RT + (tid >> 4);
-            const bool inimg = xi < P.W && yi < P.H;
-            const float pxn = inimg ? P.pix_x[xi] : 0.f, pyn = inimg ? P.pix_y[yi] : 0.f;
-            float dz = INFINITY; int df = 0x7fffffff;                     // nearest depth fragment
-            float sz[4] = {INFINITY, INFINITY, INFINITY, INFINITY};       // 4 nearest silhouette fragments
-            float sd[4] = {0.f, 0.f, 0.f, 0.f};
-            int sf[4] = {-1, -1, -1, -1};
+            const int ox = (tx0 + ttx) * TW, oy = (ty0 + tty) * TH;       // tile origin (pixels)
+            __syncthreads();
+            dkey[tid] = KEY_EMPTY;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) skey[s * R_THREADS + tid] = KEY_EMPTY;
+            if (tid < TW) spx[tid] = (ox + tid < P.W) ? P.pix_x[ox + tid] : 0.f;
+            if (tid >= 64 && tid < 64 + TH) spy[tid - 64] = (oy + tid - 64 < P.H) ? P.pix_y[oy + tid - 64] : 0.f;
+            const int txmax = min(TW, P.W - ox) - 1, tymax = min(TH, P.H - oy) - 1;     // last valid local column / row
+            // ---- P2: scatter -- one (face, pixel) pair per thread, pairs enumerated over the faces' pixel rectangles ----
             for (int base = 0; base < cnt; base += R_CHUNK) {
                 const int m = min(R_CHUNK, cnt - base);
                 __syncthreads();
+                int npix = 0;
                 if (tid < m) {
                     const int f = binlist[off + base + tid];
                     const int i0 = P.faces[3 * f], i1 = P.faces[3 * f + 1], i2 = P.faces[3 * f + 2];
-                    mh_face_setup(sv + 3 * i0, sv + 3 * i1, sv + 3 * i2, P.r_d, &sface[tid]);
-                    sfid[tid] = f;
+                    FaceRec r;
+                    r.x0 = sv[3 * i0]; r.y0 = sv[3 * i0 + 1]; r.z0 = sv[3 * i0 + 2];
+                    r.x1 = sv[3 * i1]; r.y1 = sv[3 * i1 + 1]; r.z1 = sv[3 * i1 + 2];
+                    r.x2 = sv[3 * i2]; r.y2 = sv[3 * i2 + 1]; r.z2 = sv[3 * i2 + 2];
+                    const float area = mh_edge(r.x2, r.y2, r.x0, r.y0, r.x1, r.y1);
+                    r.den = MH_ADD(area, MH_KEPS);
+                    r.inv_den = 1.0f / r.den;
+                    const float l01 = MH_ADD(MH_MUL(r.x1 - r.x0, r.x1 - r.x0), MH_MUL(r.y1 - r.y0, r.y1 - r.y0));
+                    const float l02 = MH_ADD(MH_MUL(r.x2 - r.x0, r.x2 - r.x0), MH_MUL(r.y2 - r.y0, r.y2 - r.y0));
+                    const float l12 = MH_ADD(MH_MUL(r.x2 - r.x1, r.x2 - r.x1), MH_MUL(r.y2 - r.y1, r.y2 - r.y1));
+                    r.il01 = l01 <= MH_KEPS ? 0.f : 1.0f / l01;
+                    r.il02 = l02 <= MH_KEPS ? 0.f : 1.0f / l02;
+                    r.il12 = l12 <= MH_KEPS ? 0.f : 1.0f / l12;
+                    r.bxmin = MH_SUB(fminf(fminf(r.x0, r.x1), r.x2), P.r_d); r.bxmax = MH_ADD(fmaxf(fmaxf(r.x0, r.x1), r.x2), P.r_d);
+                    r.bymin = MH_SUB(fminf(fminf(r.y0, r.y1), r.y2), P.r_d); r.bymax = MH_ADD(fmaxf(fmaxf(r.y0, r.y1), r.y2), P.r_d);
+                    // pixel rectangle of the inflated bbox, clipped to the tile (conservative by 0.01 px; the exact test is per pair)
+                    const int c0 = max((int)ceilf(pix_of(r.bxmax, P.W, P.rx) - 0.01f) - ox, 0);
+                    const int c1 = min((int)floorf(pix_of(r.bxmin, P.W, P.rx) + 0.01f) - ox, txmax);
+                    const int r0 = max((int)ceilf(pix_of(r.bymax, P.H, P.ry) - 0.01f) - oy, 0);
+                    const int r1 = min((int)floorf(pix_of(r.bymin, P.H, P.ry) + 0.01f) - oy, tymax);
+                    const int w = c1 - c0 + 1, h = r1 - r0 + 1;
+                    if (w > 0 && h > 0) {
+                        npix = w * h;
+                        r.pxy = c0 | (r0 << 5) | (w << 9) | (((65536 + w - 1) / w) << 15);
+                    } else {
+                        r.pxy = 0;
+                    }
+                    r.fid = f;
+                    srec[tid] = r;
+                }
+                // exclusive scan of npix over the first R_CHUNK threads
+                if (tid < R_CHUNK) {
+                    int incl = npix;
+                    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                    if (lane == 31) sint[8 + warp] = incl;
+                    spre[tid + 1] = incl;      // warp-local inclusive; fixed up below
                 }
                 __syncthreads();
-                if (inimg) {
-                    for (int k = 0; k < m; ++k) {
-                        MhFrag fr;
-                        if (!mh_face_eval(sface[k], pxn, pyn, &fr)) continue;
-                        const int f = sfid[k];
-                        if (fr.inside || fr.dist < P.blur_d) {
-                            if (fr.pz < dz || (fr.pz == dz && f < df)) { dz = fr.pz; df = f; }
-                        }
-                        if (fr.inside || fr.dist < P.blur_s) {
-                            float cz = fr.pz, cd = fr.inside ? -fr.dist : fr.dist; int cf = f;
-#pragma unroll
-                            for (int s = 0; s < 4; ++s) {
-                                if (cz < sz[s] || (cz == sz[s] && (unsigned)cf < (unsigned)sf[s])) {
-                                    const float tz = sz[s], tdd = sd[s]; const int tf = sf[s];
-                                    sz[s] = cz; sd[s] = cd; sf[s] = cf; cz = tz; cd = tdd; cf = tf;
-                                }
-                            }
+                if (tid < R_CHUNK && warp > 0) {
+                    int wbase = 0;
+                    for (int w = 0; w < warp; ++w) wbase += sint[8 + w];
+                    spre[tid + 1] += wbase;
+                }
+                if (tid == 0) spre[0] = 0;
+                __syncthreads();
+                const int npairs = spre[m];
+                for (int p = tid; p < npairs; p += R_THREADS) {
+                    int lo = 0, hi = m;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (spre[mid] <= p) lo = mid; else hi = mid; }
+                    const FaceRec& r = srec[lo];
+                    const int o = p - spre[lo];
+                    const int pxy = r.pxy;
+                    const int w = (pxy >> 9) & 63;
+                    const int row = (o * ((pxy >> 15) & 0x1ffff)) >> 16;
+                    const int col = o - row * w;
+                    const int lx = (pxy & 31) + col, ly = ((pxy >> 5) & 15) + row;
+                    const float px = spx[lx], py = spy[ly];
+                    if (px > r.bxmax || px < r.bxmin || py > r.bymax || py < r.bymin) continue;
+                    const float dx0 = MH_SUB(px, r.x0), dy0 = MH_SUB(py, r.y0);
+                    const float dx1 = MH_SUB(px, r.x1), dy1 = MH_SUB(py, r.y1);
+                    const float dx2 = MH_SUB(px, r.x2), dy2 = MH_SUB(py, r.y2);
+                    // edge functions exactly as the oracle rounds them (their signs decide `inside`)
+                    const float e0 = MH_SUB(MH_MUL(dx1, MH_SUB(r.y2, r.y1)), MH_MUL(dy1, MH_SUB(r.x2, r.x1)));
+                    const float e1 = MH_SUB(MH_MUL(dx2, MH_SUB(r.y0, r.y2)), MH_MUL(dy2, MH_SUB(r.x0, r.x2)));
+                    const float e2 = MH_SUB(MH_MUL(dx0, MH_SUB(r.y1, r.y0)), MH_MUL(dy0, MH_SUB(r.x1, r.x0)));
+                    const bool dpos = r.den > 0.f;
+                    const bool inside = (e0 != 0.f) && (e1 != 0.f) && (e2 != 0.f) && ((e0 > 0.f) == dpos) && ((e1 > 0.f) == dpos) && ((e2 > 0.f) == dpos);
+                    bool vd = inside, vs = inside;
+                    if (!inside) {
+                        const float d01 = seg_dist_fast(dx0, dy0, r.x1 - r.x0, r.y1 - r.y0, r.il01, dx1, dy1);
+                        const float d02 = seg_dist_fast(dx0, dy0, r.x2 - r.x0, r.y2 - r.y0, r.il02, dx2, dy2);
+                        const float d12 = seg_dist_fast(dx1, dy1, r.x2 - r.x1, r.y2 - r.y1, r.il12, dx2, dy2);
+                        const float d = fminf(fminf(d01, d02), d12);
+                        if (d >= blur_d_hi) continue;
+                        vd = d < blur_d_lo; vs = d < blur_s_lo;
+                        if ((!vd) || (!vs && d < blur_s_hi)) {              // within 1e-5 of a threshold: decide on the exact distance
+                            MhFace fc; int iv[3]; MhFrag fr;
+                            load_face(sv, P.faces, r.fid, P.r_d, &fc, iv);
+                            mh_face_eval(fc, px, py, &fr);
+                            vd = fr.dist < P.blur_d; vs = fr.dist < P.blur_s;
+                            if (!vd) continue;
                         }
                     }
+                    const float c0 = __saturatef(e0 * r.inv_den), c1 = __saturatef(e1 * r.inv_den), c2 = __saturatef(e2 * r.inv_den);
+                    const float pz = __fdividef(c0 * r.z0 + c1 * r.z1 + c2 * r.z2, fmaxf(c0 + c1 + c2, 1e-5f));
+                    if (!(pz >= 0.f)) continue;
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)r.fid;
+                    const int pix = ly * TW + lx;
+                    if (vd && key < dkey[pix]) atomicMin(&dkey[pix], key);
+                    if (vs && key < skey[3 * R_THREADS + pix]) key_insert4(skey + pix, key);
                 }
             }
-            if (!inimg) continue;
+            __syncthreads();
+            // ---- P3: one thread per pixel: exact fragments of the winners, losses, silhouette backward ----
+            const int lx = tid & (TW - 1), ly = tid >> 5;
+            const int xi = ox + lx, yi = oy + ly;
+            if (xi >= P.W || yi >= P.H) continue;
+            const float pxn = spx[lx], pyn = spy[ly];
             const size_t pidx = plane + (size_t)yi * P.W + xi;
-            if (MODE == 1) {
-                P.dbg_zbuf[(size_t)yi * P.W + xi] = (df != 0x7fffffff) ? dz : -1.0f;
-                float prod = 1.0f;
+            float dz = -1.0f; int df = -1;
+            if (dkey[tid] != KEY_EMPTY) {
+                df = (int)(dkey[tid] & 0xffffffffull);
+                MhFace fc; int iv[3]; MhFrag fr;
+                load_face(sv, P.faces, df, P.r_d, &fc, iv);
+                mh_face_eval(fc, pxn, pyn, &fr);
+                dz = fr.pz;
+            }
+            int sf[4]; float sd[4]; float pk[4];
+            float prod = 1.0f;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const float pk = (sf[s] >= 0) ? 1.0f / (1.0f + expf(sd[s] / P.sigma)) : 0.f;
-                    prod = prod * (1.0f - pk);
+            for (int s = 0; s < 4; ++s) {
+                const unsigned long long k = skey[s * R_THREADS + tid];
+                sf[s] = -1; sd[s] = 0.f; pk[s] = 0.f;
+                if (k != KEY_EMPTY) {
+                    sf[s] = (int)(k & 0xffffffffull);
+                    MhFace fc; int iv[3]; MhFrag fr;
+                    load_face(sv, P.faces, sf[s], P.r_d, &fc, iv);
+                    mh_face_eval(fc, pxn, pyn, &fr);
+                    sd[s] = fr.inside ? -fr.dist : fr.dist;
+                    pk[s] = 1.0f / (1.0f + expf(sd[s] / P.sigma));        // sigmoid(-signed / sigma)
                 }
-                P.dbg_alpha[(size_t)yi * P.W + xi] = 1.0f - prod;
+                prod = prod * (1.0f - pk[s]);
+            }
+            const float alpha = 1.0f - prod;
+            if (MODE == 1) {
+                P.dbg_zbuf[(size_t)yi * P.W + xi] = (df >= 0) ? dz : -1.0f;
+                P.dbg_alpha[(size_t)yi * P.W + xi] = alpha;
                 continue;
             }
             const uint32_t cb = P.cbits[pidx];
             // ---- depth term (optimizer.py:431-442) ----
-            if (df != 0x7fffffff && dz > 0.f && pvalid && ((P.ebits[pidx] >> n) & 1u)) {
+            if (df >= 0 && dz > 0.f && pvalid && ((P.ebits[pidx] >> n) & 1u)) {
                 const float zc = fmaxf(dz + 0.2f, P.eps);
                 const float zdisp = 1.0f / zc;
                 aS += 1.0f;
@@ -304,14 +441,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             // ---- silhouette term (optimizer.py:459-475, losses.py:35-38) ----
             if (gate && (cb & pre) == 0u) {
                 const float seg = (float)((cb >> n) & 1u);
-                float pk[4];
-                float prod = 1.0f;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    pk[s] = (sf[s] >= 0) ? 1.0f / (1.0f + expf(sd[s] / P.sigma)) : 0.f;
-                    prod = prod * (1.0f - pk[s]);
-                }
-                const float alpha = 1.0f - prod;
                 const float df_ = alpha - seg;
                 aSil += df_ * df_;
                 aCnt += seg;
@@ -327,10 +456,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         const float gsd = ga * others * (-pk[s] * (1.0f - pk[s]) / P.sigma);
                         const float gdist = sd[s] < 0.f ? -gsd : gsd;     // signed = inside ? -dist : dist
                         if (gdist == 0.f) continue;
-                        const int f = sf[s];
-                        const int iv[3] = {P.faces[3 * f], P.faces[3 * f + 1], P.faces[3 * f + 2]};
-                        MhFace fc;
-                        mh_face_setup(sv + 3 * iv[0], sv + 3 * iv[1], sv + 3 * iv[2], P.r_d, &fc);
+                        MhFace fc; int iv[3];
+                        load_face(sv, P.faces, sf[s], P.r_d, &fc, iv);
                         float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         mh_face_bwd(fc, pxn, pyn, 0.f, gdist, g);
 #pragma unroll
@@ -347,13 +474,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         aS = wsum(aS); aA = wsum(aA); aC = wsum(aC); aGmin = wsum(aGmin); aGmax = wsum(aGmax); aSil = wsum(aSil); aCnt = wsum(aCnt);
         __syncthreads();
         if (lane == 0) {
-            sred[warp] = aS; sred[8 + warp] = aA; sred[16 + warp] = aC; sred[24 + warp] = aGmin; sred[32 + warp] = aGmax;
-            sred[40 + warp] = aSil; sred[48 + warp] = aCnt;
+            sred[warp] = aS; sred[NW + warp] = aA; sred[2 * NW + warp] = aC; sred[3 * NW + warp] = aGmin; sred[4 * NW + warp] = aGmax;
+            sred[5 * NW + warp] = aSil; sred[6 * NW + warp] = aCnt;
         }
         __syncthreads();
         if (tid == 0) {
             float r[7];
-            for (int k = 0; k < 7; ++k) { r[k] = 0.f; for (int w = 0; w < 8; ++w) r[k] += sred[8 * k + w]; }
+            for (int k = 0; k < 7; ++k) { r[k] = 0.f; for (int w = 0; w < NW; ++w) r[k] += sred[NW * k + w]; }
             float* o = P.pfout + (size_t)i * PF_COUNT;
             o[PF_S] = r[0]; o[PF_A] = r[1]; o[PF_C] = r[2]; o[PF_GIZMIN] = r[3]; o[PF_GIZMAX] = r[4];
             // loss = (sum over the whole image of (M (alpha - seg))^2) / Nn ; outside the visited tiles alpha = 0
@@ -363,19 +490,18 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             const float inv = 1.0f / (r[0] + 1.0f);
             const float diff = r[1] * inv - r[2] * inv;
             o[PF_DEPTHLOSS] = diff * diff;
-            sred[56] = P.coef_depth * 2.0f * diff * inv;                  // dL/dA_sum
+            sred[7 * NW] = P.coef_depth * 2.0f * diff * inv;              // dL/dA_sum
             if (sint[6] > P.wcap) atomicAdd(P.devflags + 1, 1);
         }
         __syncthreads();
-        const float kappa = sred[56];
+        const float kappa = sred[7 * NW];
         const int nw = min(sint[6], P.wcap);
         if (kappa != 0.f) {
             for (int e = tid; e < nw; e += R_THREADS) {
                 const int pix = wpix[e], f = wface[e];
                 const int yi = pix / P.W, xi = pix - yi * P.W;
-                const int iv[3] = {P.faces[3 * f], P.faces[3 * f + 1], P.faces[3 * f + 2]};
-                MhFace fc;
-                mh_face_setup(sv + 3 * iv[0], sv + 3 * iv[1], sv + 3 * iv[2], P.r_d, &fc);
+                MhFace fc; int iv[3];
+                load_face(sv, P.faces, f, P.r_d, &fc, iv);
                 float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 mh_face_bwd(fc, P.pix_x[xi], P.pix_y[yi], kappa * wz[e], 0.f, g);
 #pragma unroll
@@ -415,8 +541,8 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wz, n * rs->wcap * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
-    rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (size_t)R_CHUNK * (sizeof(MhFace) + sizeof(int)) +
-               64 * sizeof(float) + 16 * sizeof(int) + 64;
+    rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) + (size_t)R_CHUNK * sizeof(FaceRec) +
+               (size_t)(R_CHUNK + 4) * sizeof(int) + (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (128 + TW + TH) * sizeof(float) + 32 * sizeof(int) + 64;
     e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render: %zu bytes of shared memory: %s", rs->smem, cudaGetErrorString(e));
