@@ -30,6 +30,7 @@ WORKLOADS = {
     'c3': dict(name='8 persons x 512 frames x 1280x720, 200k-pt scene cloud, batch 8', N=8, T=512, W=1280, H=720, M=200000, B=8),
     'c2': dict(name='3 persons x 200 frames x 512x512, batch 10', N=3, T=200, W=512, H=512, M=200000, B=10),
     'c4': dict(name='4 persons x 1000 frames x 1920x1080, batch 8', N=4, T=1000, W=1920, H=1080, M=200000, B=8),
+    'c3s': dict(name='profiling slice of c3: 8 persons x 64 frames x 1280x720, batch 8', N=8, T=64, W=1280, H=720, M=200000, B=8),
     'small': dict(name='2 persons x 16 frames x 320x240 (plumbing)', N=2, T=16, W=320, H=240, M=20000, B=4),
 }
 COEFS = dict(proj2d_loss_coef=1.0, depth_loss_coef=0.05, silhouette_loss_coef=0.1, reg_velocity_coef=0.05,

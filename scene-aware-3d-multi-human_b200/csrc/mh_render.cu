@@ -29,6 +29,7 @@
 #define R_THREADS 512         // one thread per tile pixel in the per-pixel phases
 #define R_MAXBINS 1024
 #define R_CHUNK 256
+#define R_ITEMS (R_CHUNK * (TW * TH / 32))   // 32-pixel groups of one staged chunk (a face covers at most the whole tile)
 #define KEY_EMPTY 0xffffffffffffffffull
 
 struct MhRenderScratch {
@@ -64,8 +65,10 @@ struct FaceRec {
     float den, inv_den;
     float il01, il02, il12;           // 1 / |edge|^2, 0 when degenerate
     float bxmin, bxmax, bymin, bymax; // exact bbox inflated by sqrt(blur) (oracle's test)
-    int pxy;                          // pixel rectangle inside the tile: col0 | row0 << 5 | w << 9 | magic(w) << 16
+    int pxy;                          // pixel rectangle inside the tile: col0 | row0 << 5 | w << 9 | magic(w) << 15
     int fid;
+    int npix;                         // pixels of the rectangle
+    unsigned zbits;                   // bits of a lower bound of every fragment depth of the face (its nearest vertex)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,7 +115,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     unsigned long long* skey = dkey + R_THREADS;                                      // 4 x R_THREADS nearest silhouette fragments
     FaceRec* srec = reinterpret_cast<FaceRec*>(skey + 4 * R_THREADS);                 // R_CHUNK
     int* spre = reinterpret_cast<int*>(srec + R_CHUNK);                               // R_CHUNK + 1 (+ pad)
-    int* tcount = spre + R_CHUNK + 4;                                                 // R_MAXBINS + 1 (exclusive offsets after the scan)
+    unsigned short* sitem = reinterpret_cast<unsigned short*>(spre + R_CHUNK + 4);    // R_ITEMS: face (8 bits) | 32-pixel group (8 bits)
+    int* tcount = reinterpret_cast<int*>(sitem + R_ITEMS);                            // R_MAXBINS + 1 (exclusive offsets after the scan)
     int* tcur = tcount + R_MAXBINS + 1;                                               // R_MAXBINS
     float* sred = reinterpret_cast<float*>(tcur + R_MAXBINS + 3);                     // 128
     float* spx = sred + 128;                                                          // TW
@@ -312,14 +316,18 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const int r0 = max((int)ceilf(pix_of(r.bymax, P.H, P.ry) - 0.01f) - oy, 0);
                     const int r1 = min((int)floorf(pix_of(r.bymin, P.H, P.ry) + 0.01f) - oy, tymax);
                     const int w = c1 - c0 + 1, h = r1 - r0 + 1;
+                    int np = 0;
                     if (w > 0 && h > 0) {
-                        npix = w * h;
+                        np = w * h;
                         r.pxy = c0 | (r0 << 5) | (w << 9) | (((65536 + w - 1) / w) << 15);
                     } else {
                         r.pxy = 0;
                     }
                     r.fid = f;
+                    r.npix = np;
+                    r.zbits = __float_as_uint(fmaxf(fminf(fminf(r.z0, r.z1), r.z2) * (1.0f - 1e-6f), 0.f));
                     srec[tid] = r;
+                    npix = (np + 31) >> 5;      // 32-pixel groups: one warp pass each
                 }
                 // exclusive scan of npix over the first R_CHUNK threads
                 if (tid < R_CHUNK) {
@@ -336,12 +344,17 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 }
                 if (tid == 0) spre[0] = 0;
                 __syncthreads();
-                const int npairs = spre[m];
-                for (int p = tid; p < npairs; p += R_THREADS) {
-                    int lo = 0, hi = m;
-                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (spre[mid] <= p) lo = mid; else hi = mid; }
-                    const FaceRec& r = srec[lo];
-                    const int o = p - spre[lo];
+                const int nitems = spre[m];
+                if (tid < m) {
+                    const int first = spre[tid], ng = spre[tid + 1] - first;
+                    for (int g = 0; g < ng; ++g) sitem[first + g] = (unsigned short)(tid | (g << 8));
+                }
+                __syncthreads();
+                for (int k = warp; k < nitems; k += NW) {
+                    const unsigned it = sitem[k];
+                    const FaceRec& r = srec[it & 255u];
+                    const int o = (int)(it >> 8) * 32 + lane;
+                    if (o >= r.npix) continue;
                     const int pxy = r.pxy;
                     const int w = (pxy >> 9) & 63;
                     const int row = (o * ((pxy >> 15) & 0x1ffff)) >> 16;
@@ -349,6 +362,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const int lx = (pxy & 31) + col, ly = ((pxy >> 5) & 15) + row;
                     const float px = spx[lx], py = spy[ly];
                     if (px > r.bxmax || px < r.bxmin || py > r.bymax || py < r.bymin) continue;
+                    const int pix = ly * TW + lx;
+                    const unsigned long long dk = dkey[pix], sk = skey[3 * R_THREADS + pix];
+                    const unsigned long long zkey = (unsigned long long)r.zbits << 32;
+                    if (zkey > dk && zkey > sk) continue;      // no fragment of this face can be nearer than its nearest vertex
                     const float dx0 = MH_SUB(px, r.x0), dy0 = MH_SUB(py, r.y0);
                     const float dx1 = MH_SUB(px, r.x1), dy1 = MH_SUB(py, r.y1);
                     const float dx2 = MH_SUB(px, r.x2), dy2 = MH_SUB(py, r.y2);
@@ -378,9 +395,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const float pz = __fdividef(c0 * r.z0 + c1 * r.z1 + c2 * r.z2, fmaxf(c0 + c1 + c2, 1e-5f));
                     if (!(pz >= 0.f)) continue;
                     const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)r.fid;
-                    const int pix = ly * TW + lx;
-                    if (vd && key < dkey[pix]) atomicMin(&dkey[pix], key);
-                    if (vs && key < skey[3 * R_THREADS + pix]) key_insert4(skey + pix, key);
+                    if (vd && key < dk) atomicMin(&dkey[pix], key);
+                    if (vs && key < sk) key_insert4(skey + pix, key);
                 }
             }
             __syncthreads();
@@ -542,7 +558,7 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
     rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) + (size_t)R_CHUNK * sizeof(FaceRec) +
-               (size_t)(R_CHUNK + 4) * sizeof(int) + (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (128 + TW + TH) * sizeof(float) + 32 * sizeof(int) + 64;
+               (size_t)(R_CHUNK + 4) * sizeof(int) + (size_t)R_ITEMS * sizeof(unsigned short) + (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (128 + TW + TH) * sizeof(float) + 32 * sizeof(int) + 64;
     e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render: %zu bytes of shared memory: %s", rs->smem, cudaGetErrorString(e));
