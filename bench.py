@@ -318,6 +318,7 @@ def main():
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--render-profile', action='store_true', help='development: per-phase cycle counters of the render kernel')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))
@@ -348,6 +349,8 @@ def main():
         opt.step_device_only(lr); lr *= 0.99
     losses0 = ctx.read_losses(opt._stream())
     ctx.call('mh_set_timing', 1)
+    if args.render_profile:
+        ctx.call('mh_render_profile', 1, None)
     torch.cuda.synchronize(device)
     if world > 1:
         dist.barrier()
@@ -370,6 +373,11 @@ def main():
         tt = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+    if args.render_profile:
+        prof = np.zeros(8, np.int64)
+        ctx.call('mh_render_profile', 0, L.ptr(prof))
+        names = ['load+ndc', 'binning', 'staging', 'pairs', 'per-pixel', 'sums+depth-bwd', 'chain', '-']
+        print('render phases (% of CTA cycles):', {n_: round(100.0 * float(v) / max(float(prof.sum()), 1.0), 1) for n_, v in zip(names, prof)}, file=sys.stderr)
     stage = ctx.read_timing(min(args.steps, 64))
     ctx.call('mh_set_timing', 0)
     losses1 = ctx.read_losses(opt._stream())

@@ -210,6 +210,10 @@ int mh_read_planes(mh_ctx* ctx, int32_t t_local0, int32_t count, float* depths_h
  * oldest first; *n_cycles is the capacity in and the number of cycles written out.  Blocking. */
 int mh_set_timing(mh_ctx* ctx, int32_t on);
 int mh_read_timing(mh_ctx* ctx, float* out_ms, int32_t* n_cycles);
+/* development aid: per-phase cycle counters of the render kernel summed over its CTAs (8 int64: load+NDC | binning |
+ * tile staging | pair scatter | per-pixel + silhouette backward | sums + depth backward | chain rule | unused);
+ * `on` (re)starts / stops counting, out8_host (may be NULL) receives the counters accumulated so far. */
+int mh_render_profile(mh_ctx* ctx, int32_t on, long long* out8_host);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t mh_launch_count(const mh_ctx* ctx);
 

@@ -33,11 +33,12 @@
 #define KEY_EMPTY 0xffffffffffffffffull
 
 struct MhRenderScratch {
-    uint16_t* binlist; int bincap;
+    ushort4* binlist; int bincap;
     int* wpix; int* wface; float* wz; int wcap;
     int nctas;
     size_t smem;
     int* counter;
+    long long* prof;
 };
 
 struct RenderParams {
@@ -48,7 +49,7 @@ struct RenderParams {
     const uint8_t* pose2d_valid; const uint8_t* mask_valid;
     const float* zmin_lin; const float* zmax_lin;
     float* pfout; int* devflags;
-    uint16_t* binlist; int bincap;
+    ushort4* binlist; int bincap;
     int* wpix; int* wface; float* wz; int wcap;
     int* counter;
     int T, N, H, W;
@@ -57,6 +58,7 @@ struct RenderParams {
     float blur_d, blur_s, r_d, sigma, eps;
     float coef_depth, coef_sil;
     float* dbg_zbuf; float* dbg_alpha; int dbg_body;
+    long long* prof;              // optional: per-phase cycle counters (8 per CTA)
 };
 
 // face record staged per tile: everything the (face, pixel) pair evaluation needs
@@ -70,6 +72,8 @@ struct FaceRec {
     int npix;                         // pixels of the rectangle
     unsigned zbits;                   // bits of a lower bound of every fragment depth of the face (its nearest vertex)
 };
+
+__constant__ int c_magic[TW + 1];      // ceil(65536 / w): row = (o * magic) >> 16 for o < 512
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,6 +110,8 @@ __device__ __forceinline__ void key_insert4(unsigned long long* slot /*stride R_
     }
 }
 
+#define PROF(k) do { if (P.prof && tid == 0) { const long long now_ = clock64(); P.prof[blockIdx.x * 8 + (k)] += now_ - tprof; tprof = now_; } } while (0)
+
 template <int MODE>      // 0: losses + gradients ; 1: dense zbuf / alpha planes of one body
 __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -113,10 +119,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     float* sg = sv + MH_LD3V;                                                         // MH_LD3V  NDC gradients
     unsigned long long* dkey = reinterpret_cast<unsigned long long*>(sg + MH_LD3V);   // R_THREADS     nearest depth fragment
     unsigned long long* skey = dkey + R_THREADS;                                      // 4 x R_THREADS nearest silhouette fragments
-    FaceRec* srec = reinterpret_cast<FaceRec*>(skey + 4 * R_THREADS);                 // R_CHUNK
-    int* spre = reinterpret_cast<int*>(srec + R_CHUNK);                               // R_CHUNK + 1 (+ pad)
-    unsigned short* sitem = reinterpret_cast<unsigned short*>(spre + R_CHUNK + 4);    // R_ITEMS: face (8 bits) | 32-pixel group (8 bits)
-    int* tcount = reinterpret_cast<int*>(sitem + R_ITEMS);                            // R_MAXBINS + 1 (exclusive offsets after the scan)
+    int* tcount = reinterpret_cast<int*>(skey + 4 * R_THREADS);                            // R_MAXBINS + 1 (exclusive offsets after the scan)
     int* tcur = tcount + R_MAXBINS + 1;                                               // R_MAXBINS
     float* sred = reinterpret_cast<float*>(tcur + R_MAXBINS + 3);                     // 128
     float* spx = sred + 128;                                                          // TW
@@ -127,13 +130,14 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = R_THREADS / 32;
     const int TN = P.T * P.N;
-    uint16_t* binlist = P.binlist + (size_t)blockIdx.x * P.bincap;
+    ushort4* binlist = P.binlist + (size_t)blockIdx.x * P.bincap;
     int* wpix = P.wpix + (size_t)blockIdx.x * P.wcap;
     int* wface = P.wface + (size_t)blockIdx.x * P.wcap;
     float* wz = P.wz + (size_t)blockIdx.x * P.wcap;
     const float blur_d_lo = P.blur_d * (1.0f - 1e-5f), blur_d_hi = P.blur_d * (1.0f + 1e-5f);
     const float blur_s_lo = P.blur_s * (1.0f - 1e-5f), blur_s_hi = P.blur_s * (1.0f + 1e-5f);
     uint32_t phase = 0;
+    long long tprof = clock64();
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             sint[7] = 0;     // overflow flag
         }
         __syncthreads();
+        PROF(0);
         const int tx0 = sint[1], ty0 = sint[2], ntx = sint[3], nty = sint[4], ks = sint[5];
         const int nbx = (ntx + (1 << ks) - 1) >> ks, nby = (nty + (1 << ks) - 1) >> ks, nbins = nbx * nby;
         // ---- P1: bin the faces ----
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         if (pass == 0) atomicAdd(&tcount[bin], 1);
                         else {
                             const int pos = atomicAdd(&tcur[bin], 1);
-                            if (pos < P.bincap) binlist[pos] = (uint16_t)f;
+                            if (pos < P.bincap) binlist[pos] = make_ushort4((unsigned short)f, (unsigned short)i0, (unsigned short)i1, (unsigned short)i2);
                         }
                     }
             }
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 __syncthreads();
             }
         }
+        PROF(1);
         const bool overflow = sint[7] != 0;
         if (overflow && tid == 0) atomicAdd(P.devflags + 1, 1);
         // ---- per-body constants ----
@@ -281,125 +287,91 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             if (cnt == 0) continue;
             const int ox = (tx0 + ttx) * TW, oy = (ty0 + tty) * TH;       // tile origin (pixels)
             __syncthreads();
+            PROF(4);
             dkey[tid] = KEY_EMPTY;
 #pragma unroll
             for (int s = 0; s < 4; ++s) skey[s * R_THREADS + tid] = KEY_EMPTY;
             if (tid < TW) spx[tid] = (ox + tid < P.W) ? P.pix_x[ox + tid] : 0.f;
             if (tid >= 64 && tid < 64 + TH) spy[tid - 64] = (oy + tid - 64 < P.H) ? P.pix_y[oy + tid - 64] : 0.f;
             const int txmax = min(TW, P.W - ox) - 1, tymax = min(TH, P.H - oy) - 1;     // last valid local column / row
-            // ---- P2: scatter -- one (face, pixel) pair per thread, pairs enumerated over the faces' pixel rectangles ----
-            for (int base = 0; base < cnt; base += R_CHUNK) {
-                const int m = min(R_CHUNK, cnt - base);
-                __syncthreads();
-                int npix = 0;
-                if (tid < m) {
-                    const int f = binlist[off + base + tid];
-                    const int i0 = P.faces[3 * f], i1 = P.faces[3 * f + 1], i2 = P.faces[3 * f + 2];
-                    FaceRec r;
-                    r.x0 = sv[3 * i0]; r.y0 = sv[3 * i0 + 1]; r.z0 = sv[3 * i0 + 2];
-                    r.x1 = sv[3 * i1]; r.y1 = sv[3 * i1 + 1]; r.z1 = sv[3 * i1 + 2];
-                    r.x2 = sv[3 * i2]; r.y2 = sv[3 * i2 + 1]; r.z2 = sv[3 * i2 + 2];
-                    const float area = mh_edge(r.x2, r.y2, r.x0, r.y0, r.x1, r.y1);
-                    r.den = MH_ADD(area, MH_KEPS);
-                    r.inv_den = 1.0f / r.den;
-                    const float l01 = MH_ADD(MH_MUL(r.x1 - r.x0, r.x1 - r.x0), MH_MUL(r.y1 - r.y0, r.y1 - r.y0));
-                    const float l02 = MH_ADD(MH_MUL(r.x2 - r.x0, r.x2 - r.x0), MH_MUL(r.y2 - r.y0, r.y2 - r.y0));
-                    const float l12 = MH_ADD(MH_MUL(r.x2 - r.x1, r.x2 - r.x1), MH_MUL(r.y2 - r.y1, r.y2 - r.y1));
-                    r.il01 = l01 <= MH_KEPS ? 0.f : 1.0f / l01;
-                    r.il02 = l02 <= MH_KEPS ? 0.f : 1.0f / l02;
-                    r.il12 = l12 <= MH_KEPS ? 0.f : 1.0f / l12;
-                    r.bxmin = MH_SUB(fminf(fminf(r.x0, r.x1), r.x2), P.r_d); r.bxmax = MH_ADD(fmaxf(fmaxf(r.x0, r.x1), r.x2), P.r_d);
-                    r.bymin = MH_SUB(fminf(fminf(r.y0, r.y1), r.y2), P.r_d); r.bymax = MH_ADD(fmaxf(fmaxf(r.y0, r.y1), r.y2), P.r_d);
-                    // pixel rectangle of the inflated bbox, clipped to the tile (conservative by 0.01 px; the exact test is per pair)
-                    const int c0 = max((int)ceilf(pix_of(r.bxmax, P.W, P.rx) - 0.01f) - ox, 0);
-                    const int c1 = min((int)floorf(pix_of(r.bxmin, P.W, P.rx) + 0.01f) - ox, txmax);
-                    const int r0 = max((int)ceilf(pix_of(r.bymax, P.H, P.ry) - 0.01f) - oy, 0);
-                    const int r1 = min((int)floorf(pix_of(r.bymin, P.H, P.ry) + 0.01f) - oy, tymax);
-                    const int w = c1 - c0 + 1, h = r1 - r0 + 1;
-                    int np = 0;
-                    if (w > 0 && h > 0) {
-                        np = w * h;
-                        r.pxy = c0 | (r0 << 5) | (w << 9) | (((65536 + w - 1) / w) << 15);
-                    } else {
-                        r.pxy = 0;
-                    }
-                    r.fid = f;
-                    r.npix = np;
-                    r.zbits = __float_as_uint(fmaxf(fminf(fminf(r.z0, r.z1), r.z2) * (1.0f - 1e-6f), 0.f));
-                    srec[tid] = r;
-                    npix = (np + 31) >> 5;      // 32-pixel groups: one warp pass each
-                }
-                // exclusive scan of npix over the first R_CHUNK threads
-                if (tid < R_CHUNK) {
-                    int incl = npix;
-                    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                    if (lane == 31) sint[8 + warp] = incl;
-                    spre[tid + 1] = incl;      // warp-local inclusive; fixed up below
-                }
-                __syncthreads();
-                if (tid < R_CHUNK && warp > 0) {
-                    int wbase = 0;
-                    for (int w = 0; w < warp; ++w) wbase += sint[8 + w];
-                    spre[tid + 1] += wbase;
-                }
-                if (tid == 0) spre[0] = 0;
-                __syncthreads();
-                const int nitems = spre[m];
-                if (tid < m) {
-                    const int first = spre[tid], ng = spre[tid + 1] - first;
-                    for (int g = 0; g < ng; ++g) sitem[first + g] = (unsigned short)(tid | (g << 8));
-                }
-                __syncthreads();
-                for (int k = warp; k < nitems; k += NW) {
-                    const unsigned it = sitem[k];
-                    const FaceRec& r = srec[it & 255u];
-                    const int o = (int)(it >> 8) * 32 + lane;
-                    if (o >= r.npix) continue;
-                    const int pxy = r.pxy;
-                    const int w = (pxy >> 9) & 63;
-                    const int row = (o * ((pxy >> 15) & 0x1ffff)) >> 16;
+            // ---- P2: scatter -- each warp takes one face of the tile at a time (set-up evaluated redundantly by the lanes, no
+            //      staging barrier) and spreads the face's pixel rectangle over its lanes, 32 pixels per pass ----
+            __syncthreads();
+            PROF(2);
+            ushort4 ent = (warp < cnt) ? binlist[off + warp] : make_ushort4(0, 0, 0, 0);
+            for (int k = warp; k < cnt; k += NW) {
+                const ushort4 cur = ent;
+                if (k + NW < cnt) ent = binlist[off + k + NW];            // prefetch the next face of this warp
+                const int f = cur.x, i0 = cur.y, i1 = cur.z, i2 = cur.w;
+                const float x0 = sv[3 * i0], y0 = sv[3 * i0 + 1], z0 = sv[3 * i0 + 2];
+                const float x1 = sv[3 * i1], y1 = sv[3 * i1 + 1], z1 = sv[3 * i1 + 2];
+                const float x2 = sv[3 * i2], y2 = sv[3 * i2 + 1], z2 = sv[3 * i2 + 2];
+                const float bxmin = MH_SUB(fminf(fminf(x0, x1), x2), P.r_d), bxmax = MH_ADD(fmaxf(fmaxf(x0, x1), x2), P.r_d);
+                const float bymin = MH_SUB(fminf(fminf(y0, y1), y2), P.r_d), bymax = MH_ADD(fmaxf(fmaxf(y0, y1), y2), P.r_d);
+                // pixel rectangle of the inflated bbox, clipped to the tile (conservative by 0.01 px; the exact test is per pixel)
+                const int c0 = max((int)ceilf(pix_of(bxmax, P.W, P.rx) - 0.01f) - ox, 0);
+                const int c1 = min((int)floorf(pix_of(bxmin, P.W, P.rx) + 0.01f) - ox, txmax);
+                const int r0 = max((int)ceilf(pix_of(bymax, P.H, P.ry) - 0.01f) - oy, 0);
+                const int r1 = min((int)floorf(pix_of(bymin, P.H, P.ry) + 0.01f) - oy, tymax);
+                const int w = c1 - c0 + 1, h = r1 - r0 + 1;
+                if (w <= 0 || h <= 0) continue;
+                const int npix = w * h;
+                const int magic = c_magic[w];
+                const float den = MH_ADD(mh_edge(x2, y2, x0, y0, x1, y1), MH_KEPS);
+                const float inv_den = __frcp_rn(den);
+                const bool dpos = den > 0.f;
+                // edge vectors exactly as the oracle rounds them
+                const float ex12 = MH_SUB(x2, x1), ey12 = MH_SUB(y2, y1);
+                const float ex20 = MH_SUB(x0, x2), ey20 = MH_SUB(y0, y2);
+                const float ex01 = MH_SUB(x1, x0), ey01 = MH_SUB(y1, y0);
+                const float l01 = ex01 * ex01 + ey01 * ey01, l02 = ex20 * ex20 + ey20 * ey20, l12 = ex12 * ex12 + ey12 * ey12;
+                const float il01 = l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), il02 = l02 <= MH_KEPS ? 0.f : __frcp_rn(l02),
+                            il12 = l12 <= MH_KEPS ? 0.f : __frcp_rn(l12);
+                // no fragment of this face can be nearer than its nearest vertex
+                const unsigned long long zkey = (unsigned long long)__float_as_uint(fmaxf(fminf(fminf(z0, z1), z2) * (1.0f - 1e-6f), 0.f)) << 32;
+                for (int o = lane; o < npix; o += 32) {
+                    const int row = (o * magic) >> 16;
                     const int col = o - row * w;
-                    const int lx = (pxy & 31) + col, ly = ((pxy >> 5) & 15) + row;
+                    const int lx = c0 + col, ly = r0 + row;
                     const float px = spx[lx], py = spy[ly];
-                    if (px > r.bxmax || px < r.bxmin || py > r.bymax || py < r.bymin) continue;
+                    if (px > bxmax || px < bxmin || py > bymax || py < bymin) continue;
                     const int pix = ly * TW + lx;
                     const unsigned long long dk = dkey[pix], sk = skey[3 * R_THREADS + pix];
-                    const unsigned long long zkey = (unsigned long long)r.zbits << 32;
-                    if (zkey > dk && zkey > sk) continue;      // no fragment of this face can be nearer than its nearest vertex
-                    const float dx0 = MH_SUB(px, r.x0), dy0 = MH_SUB(py, r.y0);
-                    const float dx1 = MH_SUB(px, r.x1), dy1 = MH_SUB(py, r.y1);
-                    const float dx2 = MH_SUB(px, r.x2), dy2 = MH_SUB(py, r.y2);
+                    if (zkey > dk && zkey > sk) continue;
+                    const float dx0 = MH_SUB(px, x0), dy0 = MH_SUB(py, y0);
+                    const float dx1 = MH_SUB(px, x1), dy1 = MH_SUB(py, y1);
+                    const float dx2 = MH_SUB(px, x2), dy2 = MH_SUB(py, y2);
                     // edge functions exactly as the oracle rounds them (their signs decide `inside`)
-                    const float e0 = MH_SUB(MH_MUL(dx1, MH_SUB(r.y2, r.y1)), MH_MUL(dy1, MH_SUB(r.x2, r.x1)));
-                    const float e1 = MH_SUB(MH_MUL(dx2, MH_SUB(r.y0, r.y2)), MH_MUL(dy2, MH_SUB(r.x0, r.x2)));
-                    const float e2 = MH_SUB(MH_MUL(dx0, MH_SUB(r.y1, r.y0)), MH_MUL(dy0, MH_SUB(r.x1, r.x0)));
-                    const bool dpos = r.den > 0.f;
+                    const float e0 = MH_SUB(MH_MUL(dx1, ey12), MH_MUL(dy1, ex12));
+                    const float e1 = MH_SUB(MH_MUL(dx2, ey20), MH_MUL(dy2, ex20));
+                    const float e2 = MH_SUB(MH_MUL(dx0, ey01), MH_MUL(dy0, ex01));
                     const bool inside = (e0 != 0.f) && (e1 != 0.f) && (e2 != 0.f) && ((e0 > 0.f) == dpos) && ((e1 > 0.f) == dpos) && ((e2 > 0.f) == dpos);
                     bool vd = inside, vs = inside;
                     if (!inside) {
-                        const float d01 = seg_dist_fast(dx0, dy0, r.x1 - r.x0, r.y1 - r.y0, r.il01, dx1, dy1);
-                        const float d02 = seg_dist_fast(dx0, dy0, r.x2 - r.x0, r.y2 - r.y0, r.il02, dx2, dy2);
-                        const float d12 = seg_dist_fast(dx1, dy1, r.x2 - r.x1, r.y2 - r.y1, r.il12, dx2, dy2);
+                        const float d01 = seg_dist_fast(dx0, dy0, ex01, ey01, il01, dx1, dy1);
+                        const float d02 = seg_dist_fast(dx0, dy0, -ex20, -ey20, il02, dx2, dy2);
+                        const float d12 = seg_dist_fast(dx1, dy1, ex12, ey12, il12, dx2, dy2);
                         const float d = fminf(fminf(d01, d02), d12);
                         if (d >= blur_d_hi) continue;
                         vd = d < blur_d_lo; vs = d < blur_s_lo;
                         if ((!vd) || (!vs && d < blur_s_hi)) {              // within 1e-5 of a threshold: decide on the exact distance
-                            MhFace fc; int iv[3]; MhFrag fr;
-                            load_face(sv, P.faces, r.fid, P.r_d, &fc, iv);
+                            MhFace fc; MhFrag fr;
+                            mh_face_setup(sv + 3 * i0, sv + 3 * i1, sv + 3 * i2, P.r_d, &fc);
                             mh_face_eval(fc, px, py, &fr);
                             vd = fr.dist < P.blur_d; vs = fr.dist < P.blur_s;
                             if (!vd) continue;
                         }
                     }
-                    const float c0 = __saturatef(e0 * r.inv_den), c1 = __saturatef(e1 * r.inv_den), c2 = __saturatef(e2 * r.inv_den);
-                    const float pz = __fdividef(c0 * r.z0 + c1 * r.z1 + c2 * r.z2, fmaxf(c0 + c1 + c2, 1e-5f));
+                    const float c0w = __saturatef(e0 * inv_den), c1w = __saturatef(e1 * inv_den), c2w = __saturatef(e2 * inv_den);
+                    const float pz = __fdividef(c0w * z0 + c1w * z1 + c2w * z2, fmaxf(c0w + c1w + c2w, 1e-5f));
                     if (!(pz >= 0.f)) continue;
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)r.fid;
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)f;
                     if (vd && key < dk) atomicMin(&dkey[pix], key);
                     if (vs && key < sk) key_insert4(skey + pix, key);
                 }
             }
             __syncthreads();
+            PROF(3);
             // ---- P3: one thread per pixel: exact fragments of the winners, losses, silhouette backward ----
             const int lx = tid & (TW - 1), ly = tid >> 5;
             const int xi = ox + lx, yi = oy + ly;
@@ -485,6 +457,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 }
             }
         }
+        __syncthreads();
+        PROF(4);
         if (MODE == 1) continue;
         // ---- P4: whole-image sums, then the depth backward over the winner list ----
         aS = wsum(aS); aA = wsum(aA); aC = wsum(aC); aGmin = wsum(aGmin); aGmax = wsum(aGmax); aSil = wsum(aSil); aCnt = wsum(aCnt);
@@ -525,6 +499,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             }
         }
         __syncthreads();
+        PROF(5);
         // ---- P5: NDC -> camera-space chain rule, accumulate into dL/dV (this CTA owns the row) ----
         const float* vw = P.verts + b * MH_LD3V;
         float* dv = P.dverts + b * MH_LD3V;
@@ -539,6 +514,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             dv[3 * v + 2] += (P.k00 * X * gx + P.k11 * Y * gy) * iz * iz + gz;
         }
         __syncthreads();
+        PROF(6);
     }
 }
 
@@ -551,14 +527,21 @@ int mh_render_alloc(mh_ctx* c) {
     rs->bincap = 1 << 20;
     rs->wcap = c->d.H * c->d.W;
     const size_t n = (size_t)rs->nctas;
-    cudaError_t e = cudaMalloc((void**)&rs->binlist, n * rs->bincap * sizeof(uint16_t));
+    cudaError_t e = cudaMalloc((void**)&rs->binlist, n * rs->bincap * sizeof(ushort4));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wpix, n * rs->wcap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wface, n * rs->wcap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wz, n * rs->wcap * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
+    rs->prof = nullptr;
+    {
+        int magic[TW + 1];
+        magic[0] = 0;
+        for (int w = 1; w <= TW; ++w) magic[w] = (65536 + w - 1) / w;
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_magic, magic, sizeof(magic));
+    }
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
-    rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) + (size_t)R_CHUNK * sizeof(FaceRec) +
-               (size_t)(R_CHUNK + 4) * sizeof(int) + (size_t)R_ITEMS * sizeof(unsigned short) + (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (128 + TW + TH) * sizeof(float) + 32 * sizeof(int) + 64;
+    rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) +
+               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (128 + TW + TH) * sizeof(float) + 32 * sizeof(int) + 64;
     e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render: %zu bytes of shared memory: %s", rs->smem, cudaGetErrorString(e));
@@ -567,6 +550,7 @@ int mh_render_alloc(mh_ctx* c) {
 
 void mh_render_free(mh_ctx* c) {
     if (!c->rs) return;
+    if (c->rs->prof) cudaFree(c->rs->prof);
     cudaFree(c->rs->binlist); cudaFree(c->rs->wpix); cudaFree(c->rs->wface); cudaFree(c->rs->wz); cudaFree(c->rs->counter);
     delete c->rs;
     c->rs = nullptr;
@@ -583,6 +567,7 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.pfout = c->pfout; P.devflags = c->devflags;
     P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
     P.counter = c->rs->counter;
+    P.prof = c->rs->prof;
     P.T = d.T; P.N = d.N; P.H = d.H; P.W = d.W;
     P.k00 = c->Kndc[0]; P.k02 = c->Kndc[2]; P.k11 = c->Kndc[5]; P.k12 = c->Kndc[6];
     P.rx = d.W > d.H ? (float)(2.0 * d.W / d.H) : 2.0f;
@@ -621,4 +606,23 @@ int mh_render_planes(mh_ctx* c, int t, int n, float* zbuf_dev, float* alpha_dev,
 int mh_render_debug(mh_ctx* c, int t, int n, float* zbuf_dev, float* alpha_dev, cudaStream_t st) {
     MH_TRY(mh_forward_only(c, st));
     return mh_render_planes(c, t, n, zbuf_dev, alpha_dev, 1e-4f, 2e-5f, st);
+}
+
+// Development aid: per-phase cycle counters of the render kernel, summed over the CTAs (8 slots:
+// load+ndc | binning | tile staging | pair scatter | per-pixel + silhouette backward | sums + depth backward | chain rule | -).
+extern "C" int mh_render_profile(mh_ctx* c, int32_t on, long long* out8_host) {
+    if (!c || !c->rs) return MH_E_ARG;
+    cudaSetDevice(c->d.device);
+    MhRenderScratch* rs = c->rs;
+    const size_t n = (size_t)rs->nctas * 8;
+    if (out8_host && rs->prof) {
+        std::vector<long long> h(n);
+        MH_CUDA(c, cudaDeviceSynchronize());
+        MH_CUDA(c, cudaMemcpy(h.data(), rs->prof, n * sizeof(long long), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 8; ++k) { out8_host[k] = 0; for (int b = 0; b < rs->nctas; ++b) out8_host[k] += h[(size_t)b * 8 + k]; }
+    }
+    if (on && !rs->prof) MH_CUDA(c, cudaMalloc((void**)&rs->prof, n * sizeof(long long)));
+    if (on) MH_CUDA(c, cudaMemset(rs->prof, 0, n * sizeof(long long)));
+    if (!on && rs->prof) { cudaFree(rs->prof); rs->prof = nullptr; }
+    return MH_OK;
 }
