@@ -29,11 +29,13 @@
 #define R_THREADS 512         // one thread per tile pixel in the per-pixel phases
 #define R_MAXBINS 1024
 #define R_CHUNK 256
+#define R_NSLAB 8             // depth slabs: the tile lists are ordered near -> far so that later faces are pruned early
 #define R_ITEMS (R_CHUNK * (TW * TH / 32))   // 32-pixel groups of one staged chunk (a face covers at most the whole tile)
 #define KEY_EMPTY 0xffffffffffffffffull
 
 struct MhRenderScratch {
-    ushort4* binlist; int bincap;
+    uint16_t* binlist; int bincap;
+    float4* frec; uint2* fbin;
     int* wpix; int* wface; float* wz; int wcap;
     int nctas;
     size_t smem;
@@ -49,7 +51,8 @@ struct RenderParams {
     const uint8_t* pose2d_valid; const uint8_t* mask_valid;
     const float* zmin_lin; const float* zmax_lin;
     float* pfout; int* devflags;
-    ushort4* binlist; int bincap;
+    uint16_t* binlist; int bincap;
+    float4* frec; uint2* fbin;    // per-CTA scratch: 5 float4 per face (set-up record), packed bin range + depth slab per face
     int* wpix; int* wface; float* wz; int wcap;
     int* counter;
     int T, N, H, W;
@@ -130,7 +133,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = R_THREADS / 32;
     const int TN = P.T * P.N;
-    ushort4* binlist = P.binlist + (size_t)blockIdx.x * P.bincap;
+    uint16_t* binlist = P.binlist + (size_t)blockIdx.x * P.bincap;
+    float4* frec = P.frec + (size_t)blockIdx.x * MH_F * 5;
+    uint2* fbin = P.fbin + (size_t)blockIdx.x * MH_F;
     int* wpix = P.wpix + (size_t)blockIdx.x * P.wcap;
     int* wface = P.wface + (size_t)blockIdx.x * P.wcap;
     float* wz = P.wz + (size_t)blockIdx.x * P.wcap;
@@ -172,24 +177,27 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             }
         }
         phase ^= 1;
-        float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
+        float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY, bz0 = INFINITY, bz1 = -INFINITY;
         for (int v = tid; v < MH_V; v += R_THREADS) {
             const float Pw[3] = {sv[3 * v], sv[3 * v + 1], sv[3 * v + 2]};
             float o[3];
             mh_world_to_ndc(Pw, P.k00, P.k02, P.k11, P.k12, o);
             sv[3 * v] = o[0]; sv[3 * v + 1] = o[1]; sv[3 * v + 2] = o[2];
-            if (o[2] > 0.f) { bx0 = fminf(bx0, o[0]); bx1 = fmaxf(bx1, o[0]); by0 = fminf(by0, o[1]); by1 = fmaxf(by1, o[1]); }
+            if (o[2] > 0.f) { bx0 = fminf(bx0, o[0]); bx1 = fmaxf(bx1, o[0]); by0 = fminf(by0, o[1]); by1 = fmaxf(by1, o[1]); bz0 = fminf(bz0, o[2]); bz1 = fmaxf(bz1, o[2]); }
         }
         for (int o = 16; o > 0; o >>= 1) {
             bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
             by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+            bz0 = fminf(bz0, __shfl_xor_sync(0xffffffffu, bz0, o)); bz1 = fmaxf(bz1, __shfl_xor_sync(0xffffffffu, bz1, o));
         }
-        if (lane == 0) { sred[warp] = bx0; sred[NW + warp] = bx1; sred[2 * NW + warp] = by0; sred[3 * NW + warp] = by1; }
+        if (lane == 0) { sred[warp] = bx0; sred[NW + warp] = bx1; sred[2 * NW + warp] = by0; sred[3 * NW + warp] = by1; sred[4 * NW + warp] = bz0; sred[5 * NW + warp] = bz1; }
         __syncthreads();
         if (tid == 0) {
             for (int w = 1; w < NW; ++w) {
                 bx0 = fminf(bx0, sred[w]); bx1 = fmaxf(bx1, sred[NW + w]); by0 = fminf(by0, sred[2 * NW + w]); by1 = fmaxf(by1, sred[3 * NW + w]);
+                bz0 = fminf(bz0, sred[4 * NW + w]); bz1 = fmaxf(bz1, sred[5 * NW + w]);
             }
+            sred[6 * NW] = bz0; sred[6 * NW + 1] = (bz1 > bz0) ? (float)R_NSLAB / (bz1 - bz0) : 0.f;
             // pixel bbox of the body (NDC x / y decrease with the pixel index), inflated by the blur radius + 1 px
             int c0 = (int)floorf(fminf(fmaxf(pix_of(bx1 + P.r_d, P.W, P.rx) - 1.f, 0.f), (float)(P.W - 1)));
             int c1 = (int)ceilf(fminf(fmaxf(pix_of(bx0 - P.r_d, P.W, P.rx) + 1.f, 0.f), (float)(P.W - 1)));
@@ -211,54 +219,81 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         // ---- P1: bin the faces ----
         for (int e = tid; e <= nbins; e += R_THREADS) tcount[e] = 0;
         __syncthreads();
-        for (int pass = 0; pass < 2; ++pass) {
+        const float zlo = sred[6 * NW], zscale = sred[6 * NW + 1];
+        // pass 0: per-face set-up record (once per body), bin range + depth slab, per-bin counts
+        for (int f = tid; f < MH_F; f += R_THREADS) {
+            const int i0 = P.faces[3 * f], i1 = P.faces[3 * f + 1], i2 = P.faces[3 * f + 2];
+            const float x0 = sv[3 * i0], y0 = sv[3 * i0 + 1], z0 = sv[3 * i0 + 2];
+            const float x1 = sv[3 * i1], y1 = sv[3 * i1 + 1], z1 = sv[3 * i1 + 2];
+            const float x2 = sv[3 * i2], y2 = sv[3 * i2 + 1], z2 = sv[3 * i2 + 2];
+            const float zmax = fmaxf(z0, fmaxf(z1, z2)), zmin = fminf(z0, fminf(z1, z2));
+            const float area = mh_edge(x2, y2, x0, y0, x1, y1);
+            uint2 fb = make_uint2(0u, 0u);
+            if ((zmax >= 0.f) && !((area <= MH_KEPS) && (area >= -MH_KEPS)) && nbins > 0) {
+                const float bxmin = MH_SUB(fminf(fminf(x0, x1), x2), P.r_d), bxmax = MH_ADD(fmaxf(fmaxf(x0, x1), x2), P.r_d);
+                const float bymin = MH_SUB(fminf(fminf(y0, y1), y2), P.r_d), bymax = MH_ADD(fmaxf(fmaxf(y0, y1), y2), P.r_d);
+                // pixel rectangle of the inflated bbox (conservative by 0.01 px; the exact test is per pixel)
+                const float pc0 = ceilf(pix_of(bxmax, P.W, P.rx) - 0.01f), pc1 = floorf(pix_of(bxmin, P.W, P.rx) + 0.01f);
+                const float pr0 = ceilf(pix_of(bymax, P.H, P.ry) - 0.01f), pr1 = floorf(pix_of(bymin, P.H, P.ry) + 0.01f);
+                if ((pc1 >= 0.f) && (pr1 >= 0.f) && (pc0 <= (float)(P.W - 1)) && (pr0 <= (float)(P.H - 1)) && (pc0 <= pc1) && (pr0 <= pr1)) {
+                    const int c0 = (int)fmaxf(pc0, 0.f), c1 = (int)fminf(pc1, (float)(P.W - 1));
+                    const int r0 = (int)fmaxf(pr0, 0.f), r1 = (int)fminf(pr1, (float)(P.H - 1));
+                    const int bx_lo = max((c0 / TW - tx0) >> ks, 0), bx_hi = min((c1 / TW - tx0) >> ks, nbx - 1);
+                    const int by_lo = max((r0 / TH - ty0) >> ks, 0), by_hi = min((r1 / TH - ty0) >> ks, nby - 1);
+                    if (bx_lo <= bx_hi && by_lo <= by_hi) {
+                        const int slab = min(max((int)((zmin - zlo) * zscale), 0), R_NSLAB - 1);
+                        fb = make_uint2((unsigned)bx_lo | ((unsigned)bx_hi << 16), (unsigned)by_lo | ((unsigned)by_hi << 10) | ((unsigned)slab << 20) | 0x80000000u);
+                        for (int by = by_lo; by <= by_hi; ++by)
+                            for (int bx = bx_lo; bx <= bx_hi; ++bx) atomicAdd(&tcount[by * nbx + bx], 1);
+                        const float den = MH_ADD(area, MH_KEPS);
+                        const float ex12 = x2 - x1, ey12 = y2 - y1, ex20 = x0 - x2, ey20 = y0 - y2, ex01 = x1 - x0, ey01 = y1 - y0;
+                        const float l01 = ex01 * ex01 + ey01 * ey01, l02 = ex20 * ex20 + ey20 * ey20, l12 = ex12 * ex12 + ey12 * ey12;
+                        float4* rec = frec + (size_t)f * 5;
+                        rec[0] = make_float4(x0, y0, x1, y1);
+                        rec[1] = make_float4(x2, y2, z0, z1);
+                        rec[2] = make_float4(z2, __frcp_rn(den), l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), l02 <= MH_KEPS ? 0.f : __frcp_rn(l02));
+                        rec[3] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), bxmin, bxmax, bymin);
+                        // no fragment of a face can be nearer than its nearest vertex
+                        rec[4] = make_float4(bymax, __int_as_float(c0 | (c1 << 16)), __int_as_float(r0 | (r1 << 16)),
+                                             __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))));
+                    }
+                }
+            }
+            fbin[f] = fb;
+        }
+        __syncthreads();
+        {
+            // exclusive scan of tcount[0..nbins) -> offsets ; tcount[nbins] = total
+            const int per = (nbins + R_THREADS - 1) / R_THREADS;
+            int local = 0;
+            for (int k = 0; k < per; ++k) { const int e = tid * per + k; if (e < nbins) local += tcount[e]; }
+            int incl = local;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            if (lane == 31) sint[8 + warp] = incl;
+            __syncthreads();
+            int wbase = 0;
+            for (int w = 0; w < warp; ++w) wbase += sint[8 + w];
+            int run = wbase + incl - local;
+            for (int k = 0; k < per; ++k) {
+                const int e = tid * per + k;
+                if (e < nbins) { const int cnt = tcount[e]; tcount[e] = run; tcur[e] = run; run += cnt; }
+            }
+            if (tid == R_THREADS - 1) { tcount[nbins] = run; if (run > P.bincap) sint[7] = 1; }
+            __syncthreads();
+        }
+        // pass 1: fill the tile lists slab by slab (near -> far)
+        for (int slab = 0; slab < R_NSLAB; ++slab) {
             for (int f = tid; f < MH_F; f += R_THREADS) {
-                const int i0 = P.faces[3 * f], i1 = P.faces[3 * f + 1], i2 = P.faces[3 * f + 2];
-                const float x0 = sv[3 * i0], y0 = sv[3 * i0 + 1], z0 = sv[3 * i0 + 2];
-                const float x1 = sv[3 * i1], y1 = sv[3 * i1 + 1], z1 = sv[3 * i1 + 2];
-                const float x2 = sv[3 * i2], y2 = sv[3 * i2 + 1], z2 = sv[3 * i2 + 2];
-                const float zmax = fmaxf(z0, fmaxf(z1, z2));
-                const float area = mh_edge(x2, y2, x0, y0, x1, y1);
-                if (!(zmax >= 0.f) || ((area <= MH_KEPS) && (area >= -MH_KEPS)) || nbins == 0) continue;
-                const float fx0 = fminf(fminf(x0, x1), x2) - P.r_d, fx1 = fmaxf(fmaxf(x0, x1), x2) + P.r_d;
-                const float fy0 = fminf(fminf(y0, y1), y2) - P.r_d, fy1 = fmaxf(fmaxf(y0, y1), y2) + P.r_d;
-                const float pc0 = ceilf(pix_of(fx1, P.W, P.rx) - 0.01f), pc1 = floorf(pix_of(fx0, P.W, P.rx) + 0.01f);
-                const float pr0 = ceilf(pix_of(fy1, P.H, P.ry) - 0.01f), pr1 = floorf(pix_of(fy0, P.H, P.ry) + 0.01f);
-                if (!(pc1 >= 0.f) || !(pr1 >= 0.f) || !(pc0 <= (float)(P.W - 1)) || !(pr0 <= (float)(P.H - 1)) || !(pc0 <= pc1) || !(pr0 <= pr1)) continue;
-                const int c0 = (int)fmaxf(pc0, 0.f), c1 = (int)fminf(pc1, (float)(P.W - 1));
-                const int r0 = (int)fmaxf(pr0, 0.f), r1 = (int)fminf(pr1, (float)(P.H - 1));
-                const int bx_lo = max((c0 / TW - tx0) >> ks, 0), bx_hi = min((c1 / TW - tx0) >> ks, nbx - 1);
-                const int by_lo = max((r0 / TH - ty0) >> ks, 0), by_hi = min((r1 / TH - ty0) >> ks, nby - 1);
+                const uint2 fb = fbin[f];
+                if (!(fb.y & 0x80000000u) || (int)((fb.y >> 20) & 15u) != slab) continue;
+                const int bx_lo = fb.x & 0xffff, bx_hi = fb.x >> 16, by_lo = fb.y & 1023, by_hi = (fb.y >> 10) & 1023;
                 for (int by = by_lo; by <= by_hi; ++by)
                     for (int bx = bx_lo; bx <= bx_hi; ++bx) {
-                        const int bin = by * nbx + bx;
-                        if (pass == 0) atomicAdd(&tcount[bin], 1);
-                        else {
-                            const int pos = atomicAdd(&tcur[bin], 1);
-                            if (pos < P.bincap) binlist[pos] = make_ushort4((unsigned short)f, (unsigned short)i0, (unsigned short)i1, (unsigned short)i2);
-                        }
+                        const int pos = atomicAdd(&tcur[by * nbx + bx], 1);
+                        if (pos < P.bincap) binlist[pos] = (uint16_t)f;
                     }
             }
             __syncthreads();
-            if (pass == 0) {
-                // exclusive scan of tcount[0..nbins) -> offsets ; tcount[nbins] = total
-                const int per = (nbins + R_THREADS - 1) / R_THREADS;
-                int local = 0;
-                for (int k = 0; k < per; ++k) { const int e = tid * per + k; if (e < nbins) local += tcount[e]; }
-                int incl = local;
-                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                if (lane == 31) sint[8 + warp] = incl;
-                __syncthreads();
-                int wbase = 0;
-                for (int w = 0; w < warp; ++w) wbase += sint[8 + w];
-                int run = wbase + incl - local;
-                for (int k = 0; k < per; ++k) {
-                    const int e = tid * per + k;
-                    if (e < nbins) { const int cnt = tcount[e]; tcount[e] = run; tcur[e] = run; run += cnt; }
-                }
-                if (tid == R_THREADS - 1) { tcount[nbins] = run; if (run > P.bincap) sint[7] = 1; }
-                __syncthreads();
-            }
         }
         PROF(1);
         const bool overflow = sint[7] != 0;
@@ -298,37 +333,29 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             //      staging barrier) and spreads the face's pixel rectangle over its lanes, 32 pixels per pass ----
             __syncthreads();
             PROF(2);
-            ushort4 ent = (warp < cnt) ? binlist[off + warp] : make_ushort4(0, 0, 0, 0);
+            int fnext = (warp < cnt) ? binlist[off + warp] : 0;
             for (int k = warp; k < cnt; k += NW) {
-                const ushort4 cur = ent;
-                if (k + NW < cnt) ent = binlist[off + k + NW];            // prefetch the next face of this warp
-                const int f = cur.x, i0 = cur.y, i1 = cur.z, i2 = cur.w;
-                const float x0 = sv[3 * i0], y0 = sv[3 * i0 + 1], z0 = sv[3 * i0 + 2];
-                const float x1 = sv[3 * i1], y1 = sv[3 * i1 + 1], z1 = sv[3 * i1 + 2];
-                const float x2 = sv[3 * i2], y2 = sv[3 * i2 + 1], z2 = sv[3 * i2 + 2];
-                const float bxmin = MH_SUB(fminf(fminf(x0, x1), x2), P.r_d), bxmax = MH_ADD(fmaxf(fmaxf(x0, x1), x2), P.r_d);
-                const float bymin = MH_SUB(fminf(fminf(y0, y1), y2), P.r_d), bymax = MH_ADD(fmaxf(fmaxf(y0, y1), y2), P.r_d);
-                // pixel rectangle of the inflated bbox, clipped to the tile (conservative by 0.01 px; the exact test is per pixel)
-                const int c0 = max((int)ceilf(pix_of(bxmax, P.W, P.rx) - 0.01f) - ox, 0);
-                const int c1 = min((int)floorf(pix_of(bxmin, P.W, P.rx) + 0.01f) - ox, txmax);
-                const int r0 = max((int)ceilf(pix_of(bymax, P.H, P.ry) - 0.01f) - oy, 0);
-                const int r1 = min((int)floorf(pix_of(bymin, P.H, P.ry) + 0.01f) - oy, tymax);
+                const int f = fnext;
+                if (k + NW < cnt) fnext = binlist[off + k + NW];          // prefetch the next face of this warp
+                const float4* rec = frec + (size_t)f * 5;
+                const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4];
+                const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y, z0 = q1.z, z1 = q1.w, z2 = q2.x;
+                const float inv_den = q2.y, il01 = q2.z, il02 = q2.w, il12 = q3.x;
+                const float bxmin = q3.y, bxmax = q3.z, bymin = q3.w, bymax = q4.x;
+                const int cc = __float_as_int(q4.y), rr = __float_as_int(q4.z);
+                // the face's pixel rectangle clipped to the tile
+                const int c0 = max((cc & 0xffff) - ox, 0), c1 = min((cc >> 16) - ox, txmax);
+                const int r0 = max((rr & 0xffff) - oy, 0), r1 = min((rr >> 16) - oy, tymax);
                 const int w = c1 - c0 + 1, h = r1 - r0 + 1;
                 if (w <= 0 || h <= 0) continue;
                 const int npix = w * h;
                 const int magic = c_magic[w];
-                const float den = MH_ADD(mh_edge(x2, y2, x0, y0, x1, y1), MH_KEPS);
-                const float inv_den = __frcp_rn(den);
-                const bool dpos = den > 0.f;
+                const bool dpos = inv_den > 0.f;
                 // edge vectors exactly as the oracle rounds them
                 const float ex12 = MH_SUB(x2, x1), ey12 = MH_SUB(y2, y1);
                 const float ex20 = MH_SUB(x0, x2), ey20 = MH_SUB(y0, y2);
                 const float ex01 = MH_SUB(x1, x0), ey01 = MH_SUB(y1, y0);
-                const float l01 = ex01 * ex01 + ey01 * ey01, l02 = ex20 * ex20 + ey20 * ey20, l12 = ex12 * ex12 + ey12 * ey12;
-                const float il01 = l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), il02 = l02 <= MH_KEPS ? 0.f : __frcp_rn(l02),
-                            il12 = l12 <= MH_KEPS ? 0.f : __frcp_rn(l12);
-                // no fragment of this face can be nearer than its nearest vertex
-                const unsigned long long zkey = (unsigned long long)__float_as_uint(fmaxf(fminf(fminf(z0, z1), z2) * (1.0f - 1e-6f), 0.f)) << 32;
+                const unsigned long long zkey = (unsigned long long)__float_as_uint(q4.w) << 32;
                 for (int o = lane; o < npix; o += 32) {
                     const int row = (o * magic) >> 16;
                     const int col = o - row * w;
@@ -356,7 +383,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         vd = d < blur_d_lo; vs = d < blur_s_lo;
                         if ((!vd) || (!vs && d < blur_s_hi)) {              // within 1e-5 of a threshold: decide on the exact distance
                             MhFace fc; MhFrag fr;
-                            mh_face_setup(sv + 3 * i0, sv + 3 * i1, sv + 3 * i2, P.r_d, &fc);
+                            int iv[3];
+                            load_face(sv, P.faces, f, P.r_d, &fc, iv);
                             mh_face_eval(fc, px, py, &fr);
                             vd = fr.dist < P.blur_d; vs = fr.dist < P.blur_s;
                             if (!vd) continue;
@@ -527,7 +555,9 @@ int mh_render_alloc(mh_ctx* c) {
     rs->bincap = 1 << 20;
     rs->wcap = c->d.H * c->d.W;
     const size_t n = (size_t)rs->nctas;
-    cudaError_t e = cudaMalloc((void**)&rs->binlist, n * rs->bincap * sizeof(ushort4));
+    cudaError_t e = cudaMalloc((void**)&rs->binlist, n * rs->bincap * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->frec, n * MH_F * 5 * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->fbin, n * MH_F * sizeof(uint2));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wpix, n * rs->wcap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wface, n * rs->wcap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wz, n * rs->wcap * sizeof(float));
@@ -551,6 +581,7 @@ int mh_render_alloc(mh_ctx* c) {
 void mh_render_free(mh_ctx* c) {
     if (!c->rs) return;
     if (c->rs->prof) cudaFree(c->rs->prof);
+    cudaFree(c->rs->frec); cudaFree(c->rs->fbin);
     cudaFree(c->rs->binlist); cudaFree(c->rs->wpix); cudaFree(c->rs->wface); cudaFree(c->rs->wz); cudaFree(c->rs->counter);
     delete c->rs;
     c->rs = nullptr;
@@ -565,7 +596,7 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.pose2d_valid = c->pose2d_valid; P.mask_valid = c->mask_valid;
     P.zmin_lin = c->params + c->off[MH_P_ZMIN_LIN]; P.zmax_lin = c->params + c->off[MH_P_ZMAX_LIN];
     P.pfout = c->pfout; P.devflags = c->devflags;
-    P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
+    P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.frec = c->rs->frec; P.fbin = c->rs->fbin; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
     P.counter = c->rs->counter;
     P.prof = c->rs->prof;
     P.T = d.T; P.N = d.N; P.H = d.H; P.W = d.W;
