@@ -1,0 +1,350 @@
+"""Parity of the CUDA path (through the package / C ABI of libmhopt.so) with the golden vectors of the UNMODIFIED
+reference (tests/golden, produced by tests/golden/make_golden.py) and with the CPU oracle, plus size-independent
+properties at larger sizes.  Needs a B200: run with `-m gpu`.
+
+Tolerances (float32, stated per test): SMPL vertices / joints 1e-5 m absolute; every loss 1e-4 relative; every gradient
+1e-3 of its largest reference entry; optimiser updates 1e-6 relative."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import gpu_harness as gh
+
+pytestmark = pytest.mark.gpu
+
+CYCLES = [0, 1, 30, 31, 50, 51]
+
+
+@pytest.fixture(scope='module')
+def pkg():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import __graft_entry__ as ge
+    return ge.load_package()
+
+
+@pytest.fixture(scope='module')
+def L(pkg):
+    return sys.modules[pkg.__name__ + '._lib']
+
+
+@pytest.fixture(scope='module')
+def kat():
+    return np.load(os.path.join(gh.GOLDEN, 'kat_functions.npz'))
+
+
+@pytest.fixture(scope='module')
+def c1(pkg):
+    g, data, meta = gh.load_fit('fit_c1.npz')
+    opt = gh.make_optimizer(pkg, g, data, meta)
+    gh.prepare(opt, g, data, meta)
+    return opt, g, data, meta
+
+
+@pytest.fixture(scope='module')
+def n2(pkg):
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    opt = gh.make_optimizer(pkg, g, data, meta)
+    gh.prepare(opt, g, data, meta)
+    return opt, g, data, meta
+
+
+def test_smpl_forward_kat(c1, kat):
+    opt = c1[0]
+    v, j = opt.smpl_forward(kat['smpl_betas'], kat['smpl_poses'])
+    assert np.abs(v - kat['smpl_verts']).max() < 1e-5                        # metres
+    assert np.abs(j - kat['smpl_joints_alphapose']).max() < 1e-5
+    # ragged batch sizes go through the same chunked path
+    v1, j1 = opt.smpl_forward(kat['smpl_betas'][:1], kat['smpl_poses'][:1])
+    assert np.array_equal(v1, v[:1]) and np.array_equal(j1, j[:1])
+
+
+def test_one_euro_kat(c1, kat):
+    opt = c1[0]
+    assert np.array_equal(opt.one_euro_filter(kat['oef_in'], 0.01, 0.02).cpu().numpy(), kat['oef_out'])
+    assert np.abs(opt.one_euro_filter(kat['oef2_in'], 0.001, 0.5).cpu().numpy() - kat['oef2_out']).max() <= 1e-6
+    one = opt.one_euro_filter(kat['oef2_in'][:1], 0.001, 0.5).cpu().numpy()     # a single frame passes through
+    assert np.array_equal(one, kat['oef2_in'][:1])
+
+
+@pytest.mark.parametrize('which', ['c1', 'n2'])
+def test_render_planes_vs_oracle(which, c1, n2, L):
+    """zbuf[...,0] of the depth raster and the soft-silhouette alpha of every person-frame vs oracle.raster."""
+    import torch
+    from oracle import raster, refmath as rm, synth
+    opt, g, data, meta = c1 if which == 'c1' else n2
+    N, T, W, H = meta[:4]
+    c = 31
+    ctx, st = opt.ctx, opt._stream()
+    ctx.set_param(L.P_POSES_T, g[f'c{c}_p_poses_T'], st); ctx.set_param(L.P_POSES_SMPL, g[f'c{c}_p_poses_smpl'], st)
+    ctx.set_param(L.P_BETAS, g[f'c{c}_p_betas'], st); ctx.set_param(L.P_XSCALE, g[f'c{c}_p_xscale'], st)
+    model = synth.load_model_tensors(gh.model_dir())
+    mt = {a: (torch.from_numpy(v) if isinstance(v, np.ndarray) and v.dtype == np.float32 else v) for a, v in model.items()}
+    mt['parents'] = [int(p) for p in model['parents']]
+    faces = torch.from_numpy(model['faces'].astype(np.int64))
+    Kndc = torch.from_numpy(rm.compute_calibration_matrix(1.0, 100.0, g['cam_K'], (W, H)))
+    for t in range(T):
+        for n in range(N):
+            zb = np.zeros((H, W), np.float32); al = np.zeros((H, W), np.float32)
+            ctx.call('mh_debug_render', t, n, L.ptr(zb), L.ptr(al))
+            with torch.no_grad():
+                out = rm.smpl_forward(mt, torch.from_numpy(g[f'c{c}_p_betas'][0, n:n + 1]), torch.from_numpy(g[f'c{c}_p_poses_smpl'][t, n:n + 1]))
+                s = np.float32(1.1) ** g[f'c{c}_p_xscale'].reshape(-1)[n]
+                va = float(s) * out['verts'][0] + torch.from_numpy(g[f'c{c}_p_poses_T'][t, n])
+                z0, a0 = raster.render_person(va, faces, Kndc, H, W)
+            z0, a0 = z0.numpy(), a0.numpy()
+            assert (z0 > 0).sum() > 100
+            assert np.array_equal(z0 > 0, zb > 0), (t, n)                     # identical coverage
+            assert np.abs(zb - z0).max() < 1e-5                               # metres
+            assert np.abs(al - a0).max() < 1e-4
+
+
+@pytest.mark.parametrize('cycle', CYCLES)
+@pytest.mark.parametrize('which', ['c1', 'n2'])
+def test_teacher_forced_cycle_vs_reference(which, cycle, c1, n2):
+    """Same parameters / scene cloud / filtered vertices in -> the reference's 9 logged losses and 6 gradient tensors out."""
+    opt, g, data, meta = c1 if which == 'c1' else n2
+    log, grads = gh.teacher_forced_cycle(opt, g, data, meta, cycle)
+    for k, v in log.items():
+        ref = float(g[f'c{cycle}_log_{k}'])
+        assert abs(v - ref) <= 1e-4 * abs(ref) + 1e-9, (k, v, ref)
+    for nm, gr in grads.items():
+        ref = g[f'c{cycle}_g_{nm}'].reshape(gr.shape)
+        assert np.abs(gr - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, nm
+    if cycle >= 1:
+        assert np.all(grads['poses_smpl'][..., 66:] == -0.002 * np.sign(g[f'c{cycle}_p_poses_smpl'] - data['poses_smpl'])[..., 66:])  # hands: prior only
+
+
+def test_teacher_forced_cycle_vs_oracle(n2):
+    opt, g, data, meta = n2
+    log, grads = gh.teacher_forced_cycle(opt, g, data, meta, 51)
+    olog, ograds = gh.oracle_cycle(g, data, meta, 51)
+    for k, v in log.items():
+        assert abs(v - olog[k]) <= 1e-4 * abs(olog[k]) + 1e-9, (k, v, olog[k])
+    for nm, gr in grads.items():
+        ref = ograds[nm].reshape(gr.shape)
+        assert np.abs(gr - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, nm
+
+
+def test_cycle_is_repeatable(n2):
+    opt, g, data, meta = n2
+    a = gh.teacher_forced_cycle(opt, g, data, meta, 51)
+    b = gh.teacher_forced_cycle(opt, g, data, meta, 51)
+    for k in a[0]:
+        assert abs(a[0][k] - b[0][k]) <= 1e-6 * abs(a[0][k])                  # float atomics: order-dependent rounding only
+    for nm in a[1]:
+        assert np.abs(a[1][nm] - b[1][nm]).max() <= 1e-5 * np.abs(a[1][nm]).max() + 1e-9
+
+
+@pytest.mark.parametrize('name', ['fit_c1.npz', 'fit_n2.npz'])
+def test_init_stage(pkg, L, name):
+    """Hot loop A (Adam on the translations) vs the reference's result and loss curve."""
+    g, data, meta = gh.load_fit(name)
+    N, T, W, H, batch, num_iter, init_iter = meta
+    opt = gh.make_optimizer(pkg, g, data, meta)
+    log = opt.init_optimized_variables(data['pose2d'], data['poses_smpl'], data['betas_smpl'], data['valid_smpl'], num_iter=init_iter,
+                                       batch_size=batch)
+    pT = opt.ctx.get_param(L.P_POSES_T, (T, N, 1, 3))
+    assert np.abs(pT - g['init_poses_T']).max() < 1e-4                        # metres
+    l2d = np.array([float(l['loss_2d']) for l in log])
+    assert np.abs(l2d - g['init_loss_2d']).max() <= 1e-4 * g['init_loss_2d'].max()
+    assert np.allclose(opt.ctx.get_param(L.P_ZMAX_LIN, (T, 1, 1)), g['init_zmax_lin'], atol=1e-4)
+    assert np.allclose(opt.ctx.get_param(L.P_BETAS, (1, N, 10)), g['init_betas'], atol=1e-7)
+
+
+def test_optimizer_updates_match_torch(c1, L):
+    """Fused RMSprop / Adam steps vs torch.optim with identical gradients."""
+    import torch
+    opt, g, data, meta = c1
+    N, T = meta[0], meta[1]
+    ctx, st = opt.ctx, opt._stream()
+    rng = np.random.default_rng(5)
+    p0 = rng.normal(0, 1, (T, N, 72)).astype(np.float32)
+    ctx.set_param(L.P_POSES_SMPL, p0, st)
+    ctx.call('mh_reset_optimizer', st)
+    tp = torch.tensor(p0.copy(), requires_grad=True)
+    ropt = torch.optim.RMSprop([tp], lr=0.01, alpha=0.5, momentum=0.9)
+    view = opt._view(L.BUF_GRADS)
+    off = T * N * 3
+    lr = 0.01
+    for it in range(5):
+        gr = (rng.normal(0, 1, p0.shape) * 10.0 ** rng.integers(-4, 1)).astype(np.float32)
+        view.zero_()
+        view[off:off + gr.size].copy_(torch.from_numpy(gr.reshape(-1)).to(view.device))
+        ctx.call('mh_fit_update', lr, st)
+        tp.grad = torch.from_numpy(gr.copy())
+        for grp in ropt.param_groups:
+            grp['lr'] = lr
+        ropt.step()
+        lr *= 0.99
+        ours = ctx.get_param(L.P_POSES_SMPL, p0.shape)
+        assert np.abs(ours - tp.detach().numpy()).max() <= 1e-6 * np.abs(tp.detach().numpy()).max()
+    # Adam(lr .5, betas (.5, .5), eps 1e-6) on the translations
+    t0 = rng.normal(0, 1, (T, N, 3)).astype(np.float32)
+    ctx.set_param(L.P_POSES_T, t0, st)
+    ctx.call('mh_init_begin', L.ptr(L.f32(data['pose2d'])), L.ptr(L.f32(data['poses_smpl'])), L.ptr(L.f32(data['betas_smpl'])), 0.15, st)
+    ctx.set_param(L.P_POSES_T, t0, st)
+    tt = torch.tensor(t0.copy(), requires_grad=True)
+    aopt = torch.optim.Adam([tt], lr=0.5, betas=(0.5, 0.5), eps=1e-6)
+    lr = 0.5
+    for it in range(5):
+        gr = rng.normal(0, 1e-2, t0.shape).astype(np.float32)
+        view.zero_()
+        view[:gr.size].copy_(torch.from_numpy(gr.reshape(-1)).to(view.device))
+        ctx.call('mh_init_update', lr, it + 1, st)
+        tt.grad = torch.from_numpy(gr.copy())
+        for grp in aopt.param_groups:
+            grp['lr'] = lr
+        aopt.step()
+        lr *= 0.95
+        ours = ctx.get_param(L.P_POSES_T, t0.shape)
+        assert np.abs(ours - tt.detach().numpy()).max() <= 2e-6 * np.abs(tt.detach().numpy()).max()
+
+
+def test_contact_knn_against_brute_force(pkg, L):
+    """Streaming exact top-32 (no distance matrix) vs numpy on a 50k-point cloud with duplicated points (ties)."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch = meta[:5]
+    opt = gh.make_optimizer(pkg, g, data, meta, coefs=dict(gh.COEFS, depth=0.0, silhouette=0.0), max_scene_points=60000)
+    gh.prepare(opt, g, data, meta)
+    rng = np.random.default_rng(3)
+    cloud = np.stack([rng.uniform(-3, 3, 50000), rng.uniform(0.8, 1.2, 50000), rng.uniform(1, 8, 50000)], -1).astype(np.float32)
+    cloud[1000:1040] = cloud[1000]                                             # 40 identical points
+    c = 31
+    ctx, st = opt.ctx, opt._stream()
+    for which, key in ((L.P_POSES_T, 'poses_T'), (L.P_POSES_SMPL, 'poses_smpl'), (L.P_BETAS, 'betas'), (L.P_XSCALE, 'xscale')):
+        ctx.set_param(which, g[f'c{c}_p_{key}'], st)
+    ctx.set_param(L.P_ZMIN_LIN, g[f'c{c}_p_zmin_lin'], st); ctx.set_param(L.P_ZMAX_LIN, g[f'c{c}_p_zmax_lin'], st)
+    opt.set_scene_pcd(cloud)
+    ctx.call('mh_fit_grads', 0, 0, st)
+    losses = ctx.read_losses(st)
+    verts = opt._view(L.BUF_VERTS).view(T + 2, N, L.LD3V)[1:T + 1, :, :3 * L.V].cpu().numpy().reshape(T, N, L.V, 3)
+    low = verts[np.arange(T)[:, None], np.arange(N)[None], np.argmax(verts[..., 1], axis=2)]           # (T, N, 3)
+    ref = 0.0
+    for t in range(T):
+        for n in range(N):
+            d2 = ((cloud - low[t, n]) ** 2).sum(1)
+            nn = np.argsort(d2, kind='stable')[:32]
+            cdv = cloud[nn, 1].mean() - low[t, n, 1]
+            ref += abs(cdv + 0.02)
+    assert abs(float(losses[L.L_CONTACT]) - ref) <= 1e-5 * ref
+
+
+def _two_shard_cycle(pkg, L, g, data, meta, cycle):
+    """World-size-2 frame sharding emulated on ONE GPU: two contexts (rank 0 / 1), halo frames and the shared gradient block
+    exchanged through the host exactly as sharding.exchange_halo / allreduce_shared do over NCCL."""
+    import torch
+    N, T, W, H, batch = meta[:5]
+    sh = sys.modules[pkg.__name__ + '.sharding']
+    opts = []
+    for r in range(2):
+        o = gh.make_optimizer(pkg, g, data, meta)
+        o.rank, o.world = r, 2
+        gh.prepare(o, g, data, meta)
+        opts.append(o)
+    assert opts[0].t1 == opts[1].t0 and opts[0].t1 % batch == 0
+    halos = []
+    for o in opts:
+        ctx, st, c = o.ctx, o._stream(), cycle
+        sl = slice(o.t0, o.t1)
+        ctx.set_param(L.P_POSES_T, g[f'c{c}_p_poses_T'][sl], st); ctx.set_param(L.P_POSES_SMPL, g[f'c{c}_p_poses_smpl'][sl], st)
+        ctx.set_param(L.P_BETAS, g[f'c{c}_p_betas'], st); ctx.set_param(L.P_BETAS_REF, g['init_betas'], st)
+        ctx.set_param(L.P_ZMIN_LIN, g[f'c{c}_p_zmin_lin'][sl], st); ctx.set_param(L.P_ZMAX_LIN, g[f'c{c}_p_zmax_lin'][sl], st)
+        ctx.set_param(L.P_XSCALE, g[f'c{c}_p_xscale'], st)
+        if len(g[f'c{c}_scene_pcd']):
+            o.set_scene_pcd(g[f'c{c}_scene_pcd'])
+        if c >= 50:
+            gh.set_filtered(o, g['verts_filtered'])
+        ctx.call('mh_halo_pack', st)
+        halos.append(o._view(L.BUF_HALO_SEND).view(2, -1).clone())
+    opts[0]._view(L.BUF_HALO_RECV).view(2, -1)[1].copy_(halos[1][0])           # rank 0 <- rank 1's first frame
+    opts[1]._view(L.BUF_HALO_RECV).view(2, -1)[0].copy_(halos[0][1])           # rank 1 <- rank 0's last frame
+    opts[0].ctx.call('mh_fit_grads', 0, 1, opts[0]._stream())
+    opts[1].ctx.call('mh_fit_grads', 1, 0, opts[1]._stream())
+    torch.cuda.synchronize()
+    shared = opts[0]._view(L.BUF_SHARED) + opts[1]._view(L.BUF_SHARED)
+    for o in opts:
+        o._view(L.BUF_SHARED).copy_(shared)
+    losses = opts[0].ctx.read_losses(opts[0]._stream())
+    log = sh.log_from_loss_block(losses, (T + batch - 1) // batch)
+    cat = lambda which, shape_fn: np.concatenate([o.ctx.get_grad(which, shape_fn(o.T_local)) for o in opts], 0)
+    grads = {'poses_T': cat(L.P_POSES_T, lambda t: (t, N, 1, 3)), 'poses_smpl': cat(L.P_POSES_SMPL, lambda t: (t, N, 72)),
+             'zmin_lin': cat(L.P_ZMIN_LIN, lambda t: (t, 1, 1)), 'zmax_lin': cat(L.P_ZMAX_LIN, lambda t: (t, 1, 1)),
+             'betas': opts[0].ctx.get_grad(L.P_BETAS, (1, N, 10)), 'xscale': opts[0].ctx.get_grad(L.P_XSCALE, (1, N, 1, 1))}
+    for o in opts:
+        o.ctx.close()
+    return log, grads
+
+
+@pytest.mark.parametrize('cycle', [31, 51])
+def test_two_shards_equal_one(pkg, L, cycle):
+    """Frame sharding + 1-frame halo + shared-gradient sum reproduces the unsharded reference cycle."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    log, grads = _two_shard_cycle(pkg, L, g, data, meta, cycle)
+    for k, v in log.items():
+        ref = float(g[f'c{cycle}_log_{k}'])
+        assert abs(v - ref) <= 1e-4 * abs(ref) + 1e-9, (k, v, ref)
+    for nm, gr in grads.items():
+        ref = g[f'c{cycle}_g_{nm}'].reshape(gr.shape)
+        assert np.abs(gr - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, nm
+
+
+def test_error_paths(pkg, L):
+    g, data, meta = gh.load_fit('fit_c1.npz')
+    N, T, W, H, batch = meta[:5]
+    with pytest.raises(L.MhError):
+        L.Context(T, 40, H, W)                                                 # more than 32 persons
+    with pytest.raises(L.MhError):
+        L.Context(3, N, H, W, B=2, t0=1, T_total=4)                            # shard start not on a batch edge
+    opt = gh.make_optimizer(pkg, g, data, meta)
+    gh.prepare(opt, g, data, meta, ingest=False)
+    with pytest.raises(L.MhError):
+        opt.ctx.call('mh_fit_grads', 0, 0, opt._stream())                      # fit before ingest
+    bad = dict(data)
+    bad['seg_mask'] = data['seg_mask'] * 0.5                                   # non-binary instance masks
+    with pytest.raises(L.MhError):
+        opt._ingest(gh.ListLoader(bad, batch))
+    with pytest.raises(L.MhError):
+        opt.set_scene_pcd(np.zeros((5, 3), np.float32))                        # fewer than 32 scene points
+    with pytest.raises(L.MhError):
+        opt.set_scene_pcd(np.zeros((W * H + 1, 3), np.float32))                # beyond M_max
+    with pytest.raises(L.MhError):
+        opt.ctx.get_param(L.P_BETAS, (N, 11))                                  # wrong size
+
+
+def test_empty_and_degenerate_frames(pkg, L):
+    """Persons without a mask / without confident joints / outside the image contribute exactly what the reference's
+    validity gates say (optimizer.py:404-409, 436-438, 472)."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch = meta[:5]
+    d2 = {k: v.copy() for k, v in data.items()}
+    d2['seg_mask'][:, 1] = 0                                                   # person 1 has no mask at all
+    d2['pose2d'][0, 0, :, 2] = 0.1                                             # person 0 has no confident joint in frame 0
+    opt = gh.make_optimizer(pkg, g, d2, meta)
+    log, grads = gh.teacher_forced_cycle(opt, g, d2, meta, 31)
+    import torch
+    from oracle import fit_ref, synth
+    model = synth.load_model_tensors(gh.model_dir())
+    fr = fit_ref.FitRef(model, (W, H), T, g['cam_K'], gh.COEFS)
+    c = 31
+    fr.set_variables(g[f'c{c}_p_poses_T'], g[f'c{c}_p_poses_smpl'], g[f'c{c}_p_betas'], d2['valid_smpl'], g[f'c{c}_p_zmin_lin'],
+                     g[f'c{c}_p_zmax_lin'], g[f'c{c}_p_xscale'])
+    fr.betas_ref = torch.from_numpy(g['init_betas'])
+    fr.set_scene_pcd(g[f'c{c}_scene_pcd'])
+    olog, _ = fr.cycle_grads(d2, [np.arange(s, min(s + batch, T)) for s in range(0, T, batch)])
+    ograds = {nm: p.grad.numpy() for nm, p in zip(gh.NAMES, fr.leaves())}
+    for k, v in log.items():
+        assert abs(v - olog[k]) <= 1e-4 * abs(olog[k]) + 1e-9, (k, v, olog[k])
+    for nm, gr in grads.items():
+        ref = ograds[nm].reshape(gr.shape)
+        assert np.abs(gr - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, nm
+    # a body far outside the frustum renders nothing and must not fault
+    ctx, st = opt.ctx, opt._stream()
+    far = g[f'c{c}_p_poses_T'].copy()
+    far[:, 0, :, 0] += 50.0
+    ctx.set_param(L.P_POSES_T, far, st)
+    ctx.call('mh_fit_grads', 0, 0, st)
+    assert np.all(np.isfinite(ctx.read_losses(st)))

@@ -1,0 +1,100 @@
+"""Host-side pieces of the package against the oracle / the reference's golden vectors.  CPU only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as ge
+from conftest import GOLDEN
+from oracle import scene_ref, synth
+
+
+@pytest.fixture(scope='module')
+def pkg():
+    return ge.load_package()
+
+
+def _mod(pkg, name):
+    return sys.modules[pkg.__name__ + '.' + name]
+
+
+def test_calibration_and_focal(pkg):
+    cam = _mod(pkg, 'camera')
+    kat = np.load(os.path.join(GOLDEN, 'kat_functions.npz'))
+    assert np.array_equal(cam.compute_calibration_matrix(1, 100, kat['proj_K'], (1280, 720)), kat['calib_land'])
+    assert np.array_equal(cam.compute_calibration_matrix(1, 100, kat['calib_K2'], (512, 512)), kat['calib_square'])
+    assert np.array_equal(cam.compute_calibration_matrix(1, 100, kat['calib_K2'], (480, 640)), kat['calib_port'])
+    assert abs(cam.get_focal(720, 60) - float(kat['focal_720_60'])) < 1e-9
+
+
+def test_model_loader_matches_the_oracle_loader(pkg, model_dir):
+    io = _mod(pkg, 'smpl_io')
+    a = io.load_smpl_model(model_dir)
+    b = synth.load_model_tensors(model_dir)
+    for k in ('v_template', 'faces', 'shapedirs', 'posedirs', 'J_regressor', 'lbs_weights', 'parents', 'J_regressor_alphapose'):
+        assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+    with pytest.raises(FileNotFoundError):
+        io.load_smpl_model('/nonexistent/dir')
+
+
+def test_fillin_matches_the_reference_loop(pkg):
+    sc = _mod(pkg, 'scene')
+    rng = np.random.default_rng(0)
+    for shape, ks in (((23, 31), 7), ((17, 12), 3), ((20, 20, 3), 11)):
+        x = rng.random(shape).astype(np.float32)
+        if len(shape) == 3:
+            x = (x * 255).astype(np.uint8)
+        mask = (rng.random(shape[:2]) > 0.6).astype(np.float32)
+        mask[5:12, 4:9] = 0
+        ax, am = sc.fillin_values(x, mask, ks)
+        bx, bm = scene_ref.fillin_values(x, mask, ks)
+        assert np.array_equal(am, bm)
+        assert np.array_equal(ax, bx) if x.dtype == np.uint8 else np.allclose(ax, bx, rtol=0, atol=1e-7)
+    # a fully valid mask is a no-op, an empty one stays empty
+    x = rng.random((8, 9)).astype(np.float32)
+    assert np.array_equal(sc.fillin_values(x, np.ones((8, 9), np.float32), 5)[0], x)
+    assert sc.fillin_values(x, np.zeros((8, 9), np.float32), 5)[1].max() == 0
+
+
+def test_scene_aggregation_and_postprocess(pkg):
+    pytest.importorskip('cv2')
+    sc = _mod(pkg, 'scene')
+    rng = np.random.default_rng(1)
+    T, H, W = 7, 24, 32
+    depths = (2 + rng.random((T, H, W)) * 3).astype(np.float32)
+    images = rng.integers(0, 255, (T, H, W, 3), dtype=np.uint8)
+    back = (rng.random((T, H, W)) > 0.3).astype(np.float32)
+    back[:, 3:6, 3:6] = 0                                    # never seen as background
+    ai, ad, am = sc.aggregate_scene_geometry_median(depths, images, back)
+    bi, bd, bm = scene_ref.aggregate_scene_median(depths, images, back)
+    assert np.array_equal(am, bm) and np.array_equal(ad[am], bd[bm]) and np.array_equal(ai[am], bi[bm])
+    pa = sc.postprocess_depthmap(ad, am, use_bilateral_filter=True)
+    pb = scene_ref.postprocess_depthmap(bd, bm, use_bilateral_filter=True)
+    assert np.allclose(pa, pb, atol=1e-6)
+
+
+def test_log_from_loss_block(pkg):
+    sh = _mod(pkg, 'sharding')
+    L = np.arange(16, dtype=np.float32) + 1
+    log = sh.log_from_loss_block(L, 4)
+    assert log['loss_pose24j'] == 0.25 and log['reg_foot_sliding'] == 7 / 4 and log['reg_vel'] == 8 and log['reg_filter_verts'] == 9
+    assert list(log) == ['loss_pose24j', 'loss_depth', 'loss_silhouette', 'reg_ref_poses', 'reg_scale', 'reg_contact',
+                         'reg_foot_sliding', 'reg_vel', 'reg_filter_verts']
+
+
+def test_frame_ranges(pkg):
+    sh = _mod(pkg, 'sharding')
+    for T, B, world in ((512, 8, 8), (200, 10, 3), (7, 2, 2), (5, 8, 2), (1000, 8, 8), (33, 4, 4)):
+        ranges = [sh.frame_range(T, B, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == T
+        for (a0, a1), (b0, b1) in zip(ranges[:-1], ranges[1:]):
+            assert a1 == b0 and a0 <= a1
+        for (a0, a1) in ranges[:-1]:
+            assert a0 % B == 0 and (a1 % B == 0 or a1 == T)       # inner edges are batch edges
+        sizes = [(a1 - a0 + B - 1) // B for a0, a1 in ranges]
+        assert max(sizes) - min(sizes) <= 1
+    ranges = [sh.frame_range(5, 8, r, 2) for r in range(2)]
+    assert sh.neighbours(0, 2, ranges) == (None, None)              # rank 1 owns nothing -> no neighbour
+    ranges = [sh.frame_range(512, 8, r, 8) for r in range(8)]
+    assert sh.neighbours(3, 8, ranges) == (2, 4) and sh.neighbours(0, 8, ranges) == (None, 1) and sh.neighbours(7, 8, ranges) == (6, None)
