@@ -25,8 +25,8 @@
 #include "mh_ctx.h"
 
 #define TW 32                 // tile width  (pixels)
-#define TH 16                 // tile height (pixels)
-#define R_THREADS 512         // one thread per tile pixel in the per-pixel phases
+#define TH 32                 // tile height (pixels)
+#define R_THREADS 1024        // one thread per tile pixel in the per-pixel phases
 #define R_MAXBINS 1024
 #define R_CHUNK 256
 #define R_NSLAB 8             // depth slabs: the tile lists are ordered near -> far so that later faces are pruned early
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     int* tcount = reinterpret_cast<int*>(skey + 4 * R_THREADS);                            // R_MAXBINS + 1 (exclusive offsets after the scan)
     int* tcur = tcount + R_MAXBINS + 1;                                               // R_MAXBINS
     float* sred = reinterpret_cast<float*>(tcur + R_MAXBINS + 3);                     // 128
-    float* spx = sred + 128;                                                          // TW
+    float* spx = sred + 256;                                                          // TW
     float* spy = spx + TW;                                                            // TH
     int* sint = reinterpret_cast<int*>(spy + TH);                                     // 32
     __shared__ __align__(8) unsigned long long mbar;
@@ -571,7 +571,7 @@ int mh_render_alloc(mh_ctx* c) {
     }
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
     rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) +
-               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (128 + TW + TH) * sizeof(float) + 32 * sizeof(int) + 64;
+               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (256 + TW + TH) * sizeof(float) + 64 * sizeof(int) + 64;
     e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render: %zu bytes of shared memory: %s", rs->smem, cudaGetErrorString(e));
