@@ -80,6 +80,10 @@ __constant__ int c_magic[TW + 1];      // ceil(65536 / w): row = (o * magic) >> 
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 __device__ __forceinline__ float wsum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;
@@ -115,6 +119,32 @@ __device__ __forceinline__ void key_insert4(unsigned long long* slot /*stride R_
 
 #define PROF(k) do { if (P.prof && tid == 0) { const long long now_ = clock64(); P.prof[blockIdx.x * 8 + (k)] += now_ - tprof; tprof = now_; } } while (0)
 
+// depth and signed squared edge distance of one (face, pixel) fragment with reciprocal multiplies (values only: every
+// DECISION was taken in P2 with the oracle's exact arithmetic)
+__device__ __forceinline__ void frag_values(const float* sv, const int32_t* __restrict__ faces, int f, float px, float py, float* pz, float* sd) {
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    const float x0 = sv[3 * i0], y0 = sv[3 * i0 + 1], z0 = sv[3 * i0 + 2];
+    const float x1 = sv[3 * i1], y1 = sv[3 * i1 + 1], z1 = sv[3 * i1 + 2];
+    const float x2 = sv[3 * i2], y2 = sv[3 * i2 + 1], z2 = sv[3 * i2 + 2];
+    const float den = MH_ADD(mh_edge(x2, y2, x0, y0, x1, y1), MH_KEPS);
+    const float inv_den = __frcp_rn(den);
+    const float dx0 = px - x0, dy0 = py - y0, dx1 = px - x1, dy1 = py - y1, dx2 = px - x2, dy2 = py - y2;
+    const float ex12 = x2 - x1, ey12 = y2 - y1, ex20 = x0 - x2, ey20 = y0 - y2, ex01 = x1 - x0, ey01 = y1 - y0;
+    const float e0 = MH_SUB(MH_MUL(dx1, ey12), MH_MUL(dy1, ex12));
+    const float e1 = MH_SUB(MH_MUL(dx2, ey20), MH_MUL(dy2, ex20));
+    const float e2 = MH_SUB(MH_MUL(dx0, ey01), MH_MUL(dy0, ex01));
+    const bool dpos = den > 0.f;
+    const bool inside = (e0 != 0.f) && (e1 != 0.f) && (e2 != 0.f) && ((e0 > 0.f) == dpos) && ((e1 > 0.f) == dpos) && ((e2 > 0.f) == dpos);
+    const float c0 = __saturatef(e0 * inv_den), c1 = __saturatef(e1 * inv_den), c2 = __saturatef(e2 * inv_den);
+    *pz = (c0 * z0 + c1 * z1 + c2 * z2) / fmaxf(c0 + c1 + c2, 1e-5f);
+    const float l01 = ex01 * ex01 + ey01 * ey01, l02 = ex20 * ex20 + ey20 * ey20, l12 = ex12 * ex12 + ey12 * ey12;
+    const float d01 = seg_dist_fast(dx0, dy0, ex01, ey01, l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), dx1, dy1);
+    const float d02 = seg_dist_fast(dx0, dy0, -ex20, -ey20, l02 <= MH_KEPS ? 0.f : __frcp_rn(l02), dx2, dy2);
+    const float d12 = seg_dist_fast(dx1, dy1, ex12, ey12, l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), dx2, dy2);
+    const float d = fminf(fminf(d01, d02), d12);
+    *sd = inside ? -d : d;
+}
+
 template <int MODE>      // 0: losses + gradients ; 1: dense zbuf / alpha planes of one body
 __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -127,7 +157,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     float* sred = reinterpret_cast<float*>(tcur + R_MAXBINS + 3);                     // 128
     float* spx = sred + 256;                                                          // TW
     float* spy = spx + TW;                                                            // TH
-    int* sint = reinterpret_cast<int*>(spy + TH);                                     // 32
+    int* sint = reinterpret_cast<int*>(spy + TH);                                     // 64
+    float4* swrec = reinterpret_cast<float4*>(smem_raw + ((reinterpret_cast<size_t>(sint + 64) - reinterpret_cast<size_t>(smem_raw) + 15) & ~size_t(15)));   // NW x 2 x 5                                     // 32
     __shared__ __align__(8) unsigned long long mbar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -333,12 +364,24 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             //      staging barrier) and spreads the face's pixel rectangle over its lanes, 32 pixels per pass ----
             __syncthreads();
             PROF(2);
-            int fnext = (warp < cnt) ? binlist[off + warp] : 0;
-            for (int k = warp; k < cnt; k += NW) {
-                const int f = fnext;
-                if (k + NW < cnt) fnext = binlist[off + k + NW];          // prefetch the next face of this warp
-                const float4* rec = frec + (size_t)f * 5;
+            float4* wrec = swrec + warp * 10;
+            int f = 0, fn1 = 0, fn2 = 0;
+            if (warp < cnt) f = binlist[off + warp];
+            if (warp + NW < cnt) fn1 = binlist[off + warp + NW];
+            if (warp < cnt && lane < 5) cp_async16(wrec + lane, frec + (size_t)f * 5 + lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            int slot = 0;
+            for (int k = warp; k < cnt; k += NW, slot ^= 1) {
+                if (k + 2 * NW < cnt) fn2 = binlist[off + k + 2 * NW];    // face ids run two items ahead, records one item ahead
+                if (k + NW < cnt && lane < 5) cp_async16(wrec + (slot ^ 1) * 5 + lane, frec + (size_t)fn1 * 5 + lane);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
+                const float4* rec = wrec + slot * 5;
                 const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4];
+                __syncwarp();
+                const int fcur = f;
+                f = fn1; fn1 = fn2;
                 const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y, z0 = q1.z, z1 = q1.w, z2 = q2.x;
                 const float inv_den = q2.y, il01 = q2.z, il02 = q2.w, il12 = q3.x;
                 const float bxmin = q3.y, bxmax = q3.z, bymin = q3.w, bymax = q4.x;
@@ -384,7 +427,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         if ((!vd) || (!vs && d < blur_s_hi)) {              // within 1e-5 of a threshold: decide on the exact distance
                             MhFace fc; MhFrag fr;
                             int iv[3];
-                            load_face(sv, P.faces, f, P.r_d, &fc, iv);
+                            load_face(sv, P.faces, fcur, P.r_d, &fc, iv);
                             mh_face_eval(fc, px, py, &fr);
                             vd = fr.dist < P.blur_d; vs = fr.dist < P.blur_s;
                             if (!vd) continue;
@@ -393,7 +436,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const float c0w = __saturatef(e0 * inv_den), c1w = __saturatef(e1 * inv_den), c2w = __saturatef(e2 * inv_den);
                     const float pz = __fdividef(c0w * z0 + c1w * z1 + c2w * z2, fmaxf(c0w + c1w + c2w, 1e-5f));
                     if (!(pz >= 0.f)) continue;
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)f;
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)fcur;
                     if (vd && key < dk) atomicMin(&dkey[pix], key);
                     if (vs && key < sk) key_insert4(skey + pix, key);
                 }
@@ -409,10 +452,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             float dz = -1.0f; int df = -1;
             if (dkey[tid] != KEY_EMPTY) {
                 df = (int)(dkey[tid] & 0xffffffffull);
-                MhFace fc; int iv[3]; MhFrag fr;
-                load_face(sv, P.faces, df, P.r_d, &fc, iv);
-                mh_face_eval(fc, pxn, pyn, &fr);
-                dz = fr.pz;
+                float sdu;
+                frag_values(sv, P.faces, df, pxn, pyn, &dz, &sdu);
             }
             int sf[4]; float sd[4]; float pk[4];
             float prod = 1.0f;
@@ -422,10 +463,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 sf[s] = -1; sd[s] = 0.f; pk[s] = 0.f;
                 if (k != KEY_EMPTY) {
                     sf[s] = (int)(k & 0xffffffffull);
-                    MhFace fc; int iv[3]; MhFrag fr;
-                    load_face(sv, P.faces, sf[s], P.r_d, &fc, iv);
-                    mh_face_eval(fc, pxn, pyn, &fr);
-                    sd[s] = fr.inside ? -fr.dist : fr.dist;
+                    float pzu;
+                    frag_values(sv, P.faces, sf[s], pxn, pyn, &pzu, &sd[s]);
                     pk[s] = 1.0f / (1.0f + expf(sd[s] / P.sigma));        // sigmoid(-signed / sigma)
                 }
                 prod = prod * (1.0f - pk[s]);
@@ -571,7 +610,7 @@ int mh_render_alloc(mh_ctx* c) {
     }
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
     rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) +
-               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (256 + TW + TH) * sizeof(float) + 64 * sizeof(int) + 64;
+               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (256 + TW + TH) * sizeof(float) + 64 * sizeof(int) + (size_t)(R_THREADS / 32) * 10 * sizeof(float4) + 128;
     e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render: %zu bytes of shared memory: %s", rs->smem, cudaGetErrorString(e));
