@@ -100,7 +100,9 @@ enum {
     MH_BUF_GRADS = 5,      /* the whole flat gradient buffer (tests) */
     MH_BUF_VERTS = 6,      /* (T+2, N, 20672) posed vertices of the last forward incl. halo slots; rows padded to 20672 floats */
     MH_BUF_FILTERED = 7,   /* (T+2, N, 20672) filtered vertices (optimizer.py:390-392) incl. halo slots; rows padded to 20672 floats */
-    MH_BUF_PARAMS = 8      /* flat parameter buffer [poses_T | poses_smpl | zmin_lin | zmax_lin | betas | xscale] */
+    MH_BUF_PARAMS = 8,     /* flat parameter buffer [poses_T | poses_smpl | zmin_lin | zmax_lin | betas | xscale] */
+    MH_BUF_MEDIAN_HIST = 9, /* (48, H*W) per-pass digit histograms of the scene median: all-reduce(SUM) between passes */
+    MH_BUF_MEDIAN_AUX = 10  /* (6, H*W) last pass: planes 0-2 all-reduce(SUM), planes 3-5 all-reduce(MIN) */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -194,6 +196,17 @@ int mh_scene_depths(mh_ctx* ctx, int32_t t_local0, int32_t count, float* out_hos
 
 /* SMPL forward of every local person-frame with the current parameters into MH_BUF_VERTS (no losses) */
 int mh_forward_only(mh_ctx* ctx, void* stream);
+
+/* ---- scene geometry: masked temporal median on the device (fhsog.py:180-202, optimizer.py:578-582) -------------------- */
+/* background masks (count,H,W) u8 and, optionally, RGB frames (count,H,W,3) u8 of local frames [t_local0, t_local0+count) */
+int mh_scene_set_back(mh_ctx* ctx, int32_t t_local0, int32_t count, const uint8_t* backmask_host, const uint8_t* images_host_or_null,
+                      void* stream);
+/* one pass of the exact radix selection; which: 0 = depth 1/target_disp of the CURRENT parameters (10 passes), 1 = image
+ * (4 passes).  Between passes the caller all-reduces MH_BUF_MEDIAN_HIST (SUM) when the frames are sharded; after the last pass
+ * MH_BUF_MEDIAN_AUX (planes 0-2 SUM, planes 3-5 MIN). */
+int mh_scene_median_pass(mh_ctx* ctx, int32_t which, int32_t pass, void* stream);
+/* results to HOST: depth (H,W) f32 + mask (H,W) u8 (which = 0) or image (H,W,3) u8 (which = 1); blocking */
+int mh_scene_median_finish(mh_ctx* ctx, int32_t which, float* depth_host, uint8_t* mask_host, uint8_t* img_host, void* stream);
 
 /* ---- debugging / input synthesis ---------------------------------------------------------------- */
 /* renders person n of local frame t with the current parameters: zbuf[...,0] (depth raster, optimizer.py:429-431)

@@ -21,7 +21,7 @@ IP = ctypes.POINTER(ctypes.c_int32)
 (L_POSE2D, L_DEPTH, L_SILHOUETTE, L_REF_POSES, L_SCALE, L_CONTACT, L_FOOT, L_VEL, L_FILTER_VERTS, L_INIT_2D) = range(10)
 L_COUNT = 16
 (BUF_SHARED, BUF_HALO_SEND, BUF_HALO_RECV, BUF_CARRY_OUT, BUF_CARRY_IN, BUF_GRADS, BUF_VERTS, BUF_FILTERED,
- BUF_PARAMS) = range(9)
+ BUF_PARAMS, BUF_MEDIAN_HIST, BUF_MEDIAN_AUX) = range(11)
 LD3V = 20672
 V, F = 6890, 13776
 
@@ -86,6 +86,9 @@ def _load():
         'mh_refresh_filters_flag': (c_int32, [ctx, c_int32]),
         'mh_one_euro_filter': (c_int32, [ctx, c_void_p, c_void_p, c_int32, c_int64, c_float, c_float, c_float]),
         'mh_scene_depths': (c_int32, [ctx, c_int32, c_int32, c_void_p]),
+        'mh_scene_set_back': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+        'mh_scene_median_pass': (c_int32, [ctx, c_int32, c_int32, c_void_p]),
+        'mh_scene_median_finish': (c_int32, [ctx, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
         'mh_forward_only': (c_int32, [ctx, c_void_p]),
         'mh_debug_render': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p]),
         'mh_synth_planes': (c_int32, [ctx, c_float, c_float, c_void_p]),

@@ -61,6 +61,7 @@ extern "C" int mh_create(mh_ctx** out, const mh_dims* dims) {
     c->model_set = c->camera_set = c->coefs_set = c->ingested = c->has_filters = c->init_ready = false;
     c->optim_scale = true;
     c->rs = nullptr;
+    c->scene_state = nullptr;
     c->M = 0;
     c->events = nullptr; c->timing = false; c->timing_iter = 0;
     for (int k = 0; k < MH_NJR; ++k) c->w17[k] = 1.0f;
@@ -151,6 +152,7 @@ extern "C" void mh_destroy(mh_ctx* c) {
     cudaSetDevice(c->d.device);
     cudaDeviceSynchronize();
     mh_render_free(c);
+    mh_scene_free(c);
     if (c->events) { for (int i = 0; i < MH_TIMING_RING * MH_TIMING_EVENTS; ++i) cudaEventDestroy(c->events[i]); delete[] c->events; }
     for (void* p : c->allocs) cudaFree(p);
     if (c->stage) cudaFree(c->stage);
@@ -433,6 +435,7 @@ extern "C" int mh_device_view(mh_ctx* c, int which, void** ptr, int64_t* n) {
         case MH_BUF_VERTS: *ptr = c->verts; *n = (int64_t)c->nb * MH_LD3V; break;
         case MH_BUF_FILTERED: *ptr = c->filtered; *n = (int64_t)c->nb * MH_LD3V; break;
         case MH_BUF_PARAMS: *ptr = c->params; *n = c->n_params; break;
+        case MH_BUF_MEDIAN_HIST: case MH_BUF_MEDIAN_AUX: return mh_scene_views(c, which, ptr, n);
         default: MH_FAIL(c, MH_E_ARG, "mh_device_view: unknown buffer %d", which);
     }
     return MH_OK;
@@ -697,9 +700,10 @@ __global__ void k_scene_depths(const float* __restrict__ depth, const float* __r
     // min_z = softplus(zmin_lin) ; max_z = min_z + 1 + softplus(zmax_lin)   (optimizer.py:683-688, transforms.py:296)
     const float minz = logf(1.0f + expf(zmin_lin[t]));
     const float maxz = minz + 1.0f + logf(1.0f + expf(zmax_lin[t]));
-    const float a = 1.0f / minz - 1.0f / maxz, b = 1.0f / maxz;
+    const float ia = __fdiv_rn(1.0f, minz), b = __fdiv_rn(1.0f, maxz);
+    const float a = __fsub_rn(ia, b);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x)
-        out[(int64_t)t * HW + i] = 1.0f / (depth[(int64_t)t * HW + i] * a + b);           // optimizer.py:425-426
+        out[(int64_t)t * HW + i] = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(depth[(int64_t)t * HW + i], a), b));     // optimizer.py:425-426
 }
 
 extern "C" int mh_scene_depths(mh_ctx* c, int32_t t0, int32_t count, float* out_host) {

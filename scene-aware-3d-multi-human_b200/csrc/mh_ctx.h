@@ -111,6 +111,7 @@ struct mh_ctx {
     float* carry_in; float* carry_out; int64_t carry_floats;
     float* transfilt;          // (T*N*3) filtered translations (only a not-None flag upstream)
     MhRenderScratch* rs;
+    void* scene_state;         // mh_scene.cu
     // stage timing (bench)
     cudaEvent_t* events; bool timing; int64_t timing_iter;
 };
@@ -162,3 +163,6 @@ int mh_scene_from_depth(mh_ctx* c, const float* depth_dev, const uint8_t* mask_d
 int mh_ingest_compact(mh_ctx* c, int t0, int count, cudaStream_t st);
 int mh_ingest_derive(mh_ctx* c, cudaStream_t st);
 int mh_expand_planes(mh_ctx* c, int t, float* seg_dev, cudaStream_t st);
+// mh_scene.cu
+void mh_scene_free(mh_ctx* c);
+int mh_scene_views(mh_ctx* c, int which, void** ptr, int64_t* n);

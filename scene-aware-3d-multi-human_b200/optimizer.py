@@ -235,9 +235,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         self.h2d_bytes = 0
         B = None
         keep_scene = self.scene_update
-        if keep_scene:
-            self._images = np.zeros((self.T_local, H, W, 3), np.uint8)
-            self._backmasks = np.zeros((self.T_local, H, W), np.float32)
+        self._have_images = False
         for data in dataloader:
             idxs = np.asarray(data['idxs']).astype(np.int64).reshape(-1)
             if B is None:
@@ -264,8 +262,14 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
                 torch.cuda.current_stream(self.device).synchronize()       # the host buffers may be temporaries
                 self.h2d_bytes += dep.nbytes + seg.nbytes + p2d.nbytes + th.nbytes + vl.nbytes
                 if keep_scene:
-                    self._images[tl:tl + cnt] = arr['images'][j:e]
-                    self._backmasks[tl:tl + cnt] = arr['backmasks'][j:e] / 1.0
+                    # backmasks / images stay on the device for the scene median (optimizer.py:399-400, 579-582)
+                    bk = np.ascontiguousarray(np.asarray(arr['backmasks'][j:e]) != 0).astype(np.uint8)
+                    im = np.ascontiguousarray(arr['images'][j:e], dtype=np.uint8) if 'images' in arr else None
+                    assert bk.shape == (cnt, H, W) and (im is None or im.shape == (cnt, H, W, 3))
+                    ctx.call('mh_scene_set_back', tl, cnt, L.ptr(bk), L.ptr(im), st)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    self._have_images = im is not None
+                    self.h2d_bytes += bk.nbytes + (im.nbytes if im is not None else 0)
                 j = e
         if not seen[self.t0:self.t1].all() or not (seen.all() or getattr(self, 'partial_loader_ok', False)):
             raise RuntimeError(f'the dataloader did not deliver frames {np.nonzero(~seen)[0][:8]}...')
@@ -305,9 +309,12 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
             losses = ctx.read_losses(st)
             optim_log.append(sharding.log_from_loss_block(losses, n_batches))
         if ma is not None:
-            scene_img, scene_mask = ma[0].copy(), ma[2].copy()
-            while scene_mask.min() == 0:
-                scene_img, scene_mask = scene_ops.fillin_values(scene_img, scene_mask, filter_size=11)
+            # the median image only depends on constant inputs: evaluated once instead of every cycle (optimizer.py:581, 595-600)
+            scene_mask = ma[1].copy()
+            scene_img = self._device_median(1) if self._have_images else None
+            if scene_img is not None:
+                while scene_mask.min() == 0:
+                    scene_img, scene_mask = scene_ops.fillin_values(scene_img, scene_mask, filter_size=11)
             self.scene_img, self.scene_mask = scene_img, scene_mask
         return optim_log
 
@@ -341,29 +348,41 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         self.poses_T_filtered = True
         self.verts_filtered = True
 
+    def _device_median(self, which):
+        """Masked temporal median over ALL frames (``fhsog.py:180-202``) by exact radix selection on the device; the
+        per-pixel digit histograms are summed over the ranks between passes (``csrc/mh_scene.cu``)."""
+        ctx, st = self.ctx, self._stream()
+        HW = self.img_h * self.img_w
+        npass = 10 if which == 0 else 4
+        planes = 1 if which == 0 else 3
+        for p in range(npass):
+            ctx.call('mh_scene_median_pass', which, p, st)
+            if self.world > 1:
+                if p < npass - 1:
+                    hist = self._view(L.BUF_MEDIAN_HIST)[:(1 if p == 0 else 16 * planes) * HW]
+                    torch.distributed.all_reduce(hist, op=torch.distributed.ReduceOp.SUM, group=self.group)
+                else:
+                    aux = self._view(L.BUF_MEDIAN_AUX)
+                    torch.distributed.all_reduce(aux[:planes * HW], op=torch.distributed.ReduceOp.SUM, group=self.group)
+                    torch.distributed.all_reduce(aux[3 * HW:(3 + planes) * HW], op=torch.distributed.ReduceOp.MIN, group=self.group)
+        if which == 0:
+            depth = np.empty((self.img_h, self.img_w), np.float32)
+            mask = np.empty((self.img_h, self.img_w), np.uint8)
+            ctx.call('mh_scene_median_finish', 0, L.ptr(depth), L.ptr(mask), None, st)
+            return depth, mask.astype(bool)
+        img = np.empty((self.img_h, self.img_w, 3), np.uint8)
+        ctx.call('mh_scene_median_finish', 1, None, None, L.ptr(img), st)
+        return img
+
     def _update_scene_geometry(self):
-        """``optimizer.py:578-584``: masked temporal median of the per-frame scene depths -> post-processing -> cloud."""
-        depths = np.empty((self.T_local, self.img_h, self.img_w), np.float32)
-        self.ctx.call('mh_scene_depths', 0, self.T_local, L.ptr(depths))
-        images, backmasks = self._images, self._backmasks
-        if self.world > 1:
-            gathered = [None] * self.world if self.rank == 0 else None
-            torch.distributed.gather_object((depths, images, backmasks), gathered, dst=0, group=self.group)
-            if self.rank == 0:
-                depths = np.concatenate([g[0] for g in gathered], 0)
-                images = np.concatenate([g[1] for g in gathered], 0)
-                backmasks = np.concatenate([g[2] for g in gathered], 0)
-        out = [None]
-        if self.rank == 0:
-            ma_image, ma_depth, ma_mask = scene_ops.aggregate_scene_geometry_median(depths, images, backmasks)
-            scene_depth = scene_ops.postprocess_depthmap(ma_depth, ma_mask, use_bilateral_filter=True)
-            out = [(ma_image, ma_depth, ma_mask, scene_depth)]
-        if self.world > 1:
-            torch.distributed.broadcast_object_list(out, src=0, group=self.group)
-        ma_image, ma_depth, ma_mask, scene_depth = out[0]
+        """``optimizer.py:578-584``: masked temporal median of the per-frame scene depths (device) -> bilateral / edge /
+        fill-in post-processing of ONE depth map (host, ``scene.py``) -> scene point cloud (device).  Every rank computes
+        the same map."""
+        ma_depth, ma_mask = self._device_median(0)
+        scene_depth = scene_ops.postprocess_depthmap(ma_depth, ma_mask, use_bilateral_filter=True)
         self.scene_depth = scene_depth
         self.update_scene_pointcloud(scene_depth, ma_mask)
-        return ma_image, ma_depth, ma_mask
+        return ma_depth, ma_mask
 
     def update_scene_pointcloud(self, scene_depth, scene_mask):
         """``optimizer.py:605-616``: inverse-project the pixel centres with the scene depth, keep ``mask > 0.5``."""

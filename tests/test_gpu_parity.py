@@ -348,3 +348,100 @@ def test_empty_and_degenerate_frames(pkg, L):
     ctx.set_param(L.P_POSES_T, far, st)
     ctx.call('mh_fit_grads', 0, 0, st)
     assert np.all(np.isfinite(ctx.read_losses(st)))
+
+
+def _median_inputs(meta, seed=0):
+    """Random background masks / images with never-background pixels, odd and even counts and duplicated values."""
+    N, T, W, H = meta[:4]
+    rng = np.random.default_rng(seed)
+    back = (rng.random((T, H, W)) > 0.35).astype(np.uint8)
+    back[:, 3:7, 5:9] = 0                                                     # never background
+    back[1:, 10, :] = 0                                                        # a single sample
+    back[:, 12, :] = 1                                                         # all frames (even count for T = 4)
+    images = rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8)
+    images[:, 12, :8] = images[0, 12, :8]                                      # duplicates
+    return back, images
+
+
+def test_scene_median_on_device(n2, pkg, L):
+    """Exact radix-selection median (csrc/mh_scene.cu) vs np.ma.median (fhsog.py:180-202) on the same per-frame depths."""
+    import torch
+    opt, g, data, meta = n2
+    sc = sys.modules[pkg.__name__ + '.scene']
+    N, T, W, H = meta[:4]
+    ctx, st = opt.ctx, opt._stream()
+    c = 31
+    ctx.set_param(L.P_ZMIN_LIN, g[f'c{c}_p_zmin_lin'], st); ctx.set_param(L.P_ZMAX_LIN, g[f'c{c}_p_zmax_lin'], st)
+    back, images = _median_inputs(meta)
+    ctx.call('mh_scene_set_back', 0, T, L.ptr(back), L.ptr(images), st)
+    opt._have_images = True
+    depths = np.empty((T, H, W), np.float32)
+    ctx.call('mh_scene_depths', 0, T, L.ptr(depths))
+    ref_img, ref_depth, ref_mask = sc.aggregate_scene_geometry_median(depths, images, back.astype(np.float32))
+    depth, mask = opt._device_median(0)
+    img = opt._device_median(1)
+    assert np.array_equal(mask, ref_mask)
+    assert np.array_equal(depth, ref_depth)                                    # bit-exact, incl. 0 where never background
+    assert np.array_equal(img, ref_img)
+    # frame-sharded: two contexts with half the frames each, histograms summed between passes as the NCCL all-reduce does
+    halves = []
+    for r in range(2):
+        o = gh.make_optimizer(pkg, g, data, meta)
+        o.rank, o.world = r, 2
+        gh.prepare(o, g, data, meta)
+        sl = slice(o.t0, o.t1)
+        o.ctx.set_param(L.P_ZMIN_LIN, g[f'c{c}_p_zmin_lin'][sl], o._stream()); o.ctx.set_param(L.P_ZMAX_LIN, g[f'c{c}_p_zmax_lin'][sl], o._stream())
+        o.ctx.call('mh_scene_set_back', 0, o.T_local, L.ptr(np.ascontiguousarray(back[sl])), L.ptr(np.ascontiguousarray(images[sl])), o._stream())
+        halves.append(o)
+    HW = H * W
+    for which, npass, planes in ((0, 10, 1), (1, 4, 3)):
+        for p in range(npass):
+            for o in halves:
+                o.ctx.call('mh_scene_median_pass', which, p, o._stream())
+            torch.cuda.synchronize()
+            if p < npass - 1:
+                n = (1 if p == 0 else 16 * planes) * HW
+                tot = halves[0]._view(L.BUF_MEDIAN_HIST)[:n] + halves[1]._view(L.BUF_MEDIAN_HIST)[:n]
+                for o in halves:
+                    o._view(L.BUF_MEDIAN_HIST)[:n].copy_(tot)
+            else:
+                a0, a1 = halves[0]._view(L.BUF_MEDIAN_AUX), halves[1]._view(L.BUF_MEDIAN_AUX)
+                le = a0[:planes * HW] + a1[:planes * HW]
+                ab = torch.minimum(a0[3 * HW:(3 + planes) * HW], a1[3 * HW:(3 + planes) * HW])
+                for o in halves:
+                    o._view(L.BUF_MEDIAN_AUX)[:planes * HW].copy_(le)
+                    o._view(L.BUF_MEDIAN_AUX)[3 * HW:(3 + planes) * HW].copy_(ab)
+            torch.cuda.synchronize()
+        for o in halves:
+            if which == 0:
+                d2 = np.empty((H, W), np.float32); m2 = np.empty((H, W), np.uint8)
+                o.ctx.call('mh_scene_median_finish', 0, L.ptr(d2), L.ptr(m2), None, o._stream())
+                assert np.array_equal(d2, ref_depth) and np.array_equal(m2.astype(bool), ref_mask)
+            else:
+                i2 = np.empty((H, W, 3), np.uint8)
+                o.ctx.call('mh_scene_median_finish', 1, None, None, L.ptr(i2), o._stream())
+                assert np.array_equal(i2, ref_img)
+    for o in halves:
+        o.ctx.close()
+
+
+def test_full_fit_runs_like_the_reference(pkg, L):
+    """The whole drop-in call sequence on config C1 (init 30 iterations, fit 52 cycles with scene updates at cycle >= 30,
+    filters at cycle 50): output keys / shapes of optimizer.py:619-636 and loss levels of the reference's run.  Trajectories
+    are chaotic, so only levels are compared."""
+    g, data, meta = gh.load_fit('fit_c1.npz')
+    N, T, W, H, batch, num_iter, init_iter = meta
+    opt = gh.make_optimizer(pkg, g, data, meta)
+    opt.init_optimized_variables(data['pose2d'], data['poses_smpl'], data['betas_smpl'], data['valid_smpl'], num_iter=init_iter, batch_size=batch)
+    log = opt.fit(gh.ListLoader(data, batch), num_iter=num_iter)
+    assert len(log) == num_iter and list(log[0]) == ['loss_pose24j', 'loss_depth', 'loss_silhouette', 'reg_ref_poses', 'reg_scale',
+                                                      'reg_contact', 'reg_foot_sliding', 'reg_vel', 'reg_filter_verts']
+    for k in ('loss_pose24j', 'loss_depth', 'loss_silhouette'):
+        assert abs(log[0][k] - g['log_' + k][0]) <= 1e-4 * abs(g['log_' + k][0])                # the first cycle is exact
+        assert log[-1][k] <= 3.0 * g['log_' + k][-1] + 1e-6                                        # same level at the end
+    assert log[29]['reg_contact'] == 0 and log[31]['reg_contact'] > 0 and log[49]['reg_filter_verts'] == 0 and log[50]['reg_filter_verts'] > 0
+    v = opt.get_optimized_variables()
+    for k in ('scale_factor', 'poses_T', 'poses_smpl', 'betas_smpl', 'valid_smpl', 'min_z', 'max_z', 'scene_depth', 'scene_img', 'scene_mask'):
+        assert v[k].shape == g['final_' + k].shape, k
+    assert np.abs(v['poses_T'] - g['final_poses_T']).max() < 0.15                                 # metres; oracle-vs-reference spread is 0.035
+    assert v['scene_mask'].min() == 1
