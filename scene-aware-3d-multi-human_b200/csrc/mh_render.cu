@@ -185,10 +185,15 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         if (MODE == 1 && iter > 0) break;
         if (tid == 0) sint[0] = (MODE == 1) ? P.dbg_body : atomicAdd(P.counter, 1);
         __syncthreads();
-        const int i = sint[0];
+        const int wi = sint[0];
         __syncthreads();
-        if (i >= TN) break;
-        const int t = i / P.N, n = i % P.N;
+        if (wi >= TN) break;
+        // longest-first: work item w = (depth-order position q, frame t) -> the nearest (largest) persons of all frames are
+        // rasterised first, the small far ones fill the tail
+        int t, n;
+        if (MODE == 1) { t = wi / P.N; n = wi % P.N; }
+        else { t = wi % P.T; n = P.order[t * P.N + wi / P.T]; }
+        const int i = t * P.N + n;
         const size_t b = (size_t)i + P.N;                                // slot-major body (slot 0 is the halo)
         // ---- P0: TMA bulk copy of the vertex row, then world -> NDC in place ----
         if (tid == 0) {
