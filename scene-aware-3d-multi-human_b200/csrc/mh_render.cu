@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             __syncthreads();
             PROF(4);
             dkey[tid] = KEY_EMPTY;
+            if (tid == 0) sint[40] = 0;
 #pragma unroll
             for (int s = 0; s < 4; ++s) skey[s * R_THREADS + tid] = KEY_EMPTY;
             if (tid < TW) spx[tid] = (ox + tid < P.W) ? P.pix_x[ox + tid] : 0.f;
@@ -370,15 +371,21 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             __syncthreads();
             PROF(2);
             float4* wrec = swrec + warp * 10;
+            // faces are handed out dynamically (shared counter), two indices ahead of the one being processed
             int f = 0, fn1 = 0, fn2 = 0;
-            if (warp < cnt) f = binlist[off + warp];
-            if (warp + NW < cnt) fn1 = binlist[off + warp + NW];
-            if (warp < cnt && lane < 5) cp_async16(wrec + lane, frec + (size_t)f * 5 + lane);
+            int k0 = 0, k1 = 0, k2 = 0;
+            if (lane == 0) { k0 = atomicAdd(&sint[40], 1); k1 = atomicAdd(&sint[40], 1); }
+            k0 = __shfl_sync(0xffffffffu, k0, 0); k1 = __shfl_sync(0xffffffffu, k1, 0);
+            if (k0 < cnt) f = binlist[off + k0];
+            if (k1 < cnt) fn1 = binlist[off + k1];
+            if (k0 < cnt && lane < 5) cp_async16(wrec + lane, frec + (size_t)f * 5 + lane);
             asm volatile("cp.async.commit_group;" ::: "memory");
             int slot = 0;
-            for (int k = warp; k < cnt; k += NW, slot ^= 1) {
-                if (k + 2 * NW < cnt) fn2 = binlist[off + k + 2 * NW];    // face ids run two items ahead, records one item ahead
-                if (k + NW < cnt && lane < 5) cp_async16(wrec + (slot ^ 1) * 5 + lane, frec + (size_t)fn1 * 5 + lane);
+            for (; k0 < cnt; k0 = k1, k1 = k2, slot ^= 1) {
+                if (lane == 0) k2 = atomicAdd(&sint[40], 1);
+                k2 = __shfl_sync(0xffffffffu, k2, 0);
+                if (k2 < cnt) fn2 = binlist[off + k2];                    // face ids run two items ahead, records one item ahead
+                if (k1 < cnt && lane < 5) cp_async16(wrec + (slot ^ 1) * 5 + lane, frec + (size_t)fn1 * 5 + lane);
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
                 __syncwarp();
