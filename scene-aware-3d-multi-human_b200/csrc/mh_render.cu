@@ -272,8 +272,15 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const float pc0 = ceilf(pix_of(bxmax, P.W, P.rx) - 0.01f), pc1 = floorf(pix_of(bxmin, P.W, P.rx) + 0.01f);
                 const float pr0 = ceilf(pix_of(bymax, P.H, P.ry) - 0.01f), pr1 = floorf(pix_of(bymin, P.H, P.ry) + 0.01f);
                 if ((pc1 >= 0.f) && (pr1 >= 0.f) && (pc0 <= (float)(P.W - 1)) && (pr0 <= (float)(P.H - 1)) && (pc0 <= pc1) && (pr0 <= pr1)) {
-                    const int c0 = (int)fmaxf(pc0, 0.f), c1 = (int)fminf(pc1, (float)(P.W - 1));
-                    const int r0 = (int)fmaxf(pr0, 0.f), r1 = (int)fminf(pr1, (float)(P.H - 1));
+                    int c0 = (int)fmaxf(pc0, 0.f), c1 = (int)fminf(pc1, (float)(P.W - 1));
+                    int r0 = (int)fmaxf(pr0, 0.f), r1 = (int)fminf(pr1, (float)(P.H - 1));
+                    // make the rectangle EXACT for the oracle's bbox test (the 0.01 px slack can include one column / row too many),
+                    // so that the pair loop needs no per-pixel bbox test
+                    while (c0 <= c1 && (P.pix_x[c0] > bxmax || P.pix_x[c0] < bxmin)) ++c0;
+                    while (c1 >= c0 && (P.pix_x[c1] > bxmax || P.pix_x[c1] < bxmin)) --c1;
+                    while (r0 <= r1 && (P.pix_y[r0] > bymax || P.pix_y[r0] < bymin)) ++r0;
+                    while (r1 >= r0 && (P.pix_y[r1] > bymax || P.pix_y[r1] < bymin)) --r1;
+                    if (c0 > c1 || r0 > r1) { fbin[f] = fb; continue; }
                     const int bx_lo = max((c0 / TW - tx0) >> ks, 0), bx_hi = min((c1 / TW - tx0) >> ks, nbx - 1);
                     const int by_lo = max((r0 / TH - ty0) >> ks, 0), by_hi = min((r1 / TH - ty0) >> ks, nby - 1);
                     if (bx_lo <= bx_hi && by_lo <= by_hi) {
@@ -410,16 +417,18 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const float ex12 = MH_SUB(x2, x1), ey12 = MH_SUB(y2, y1);
                 const float ex20 = MH_SUB(x0, x2), ey20 = MH_SUB(y0, y2);
                 const float ex01 = MH_SUB(x1, x0), ey01 = MH_SUB(y1, y0);
-                const unsigned long long zkey = (unsigned long long)__float_as_uint(q4.w) << 32;
+                const unsigned zbits = __float_as_uint(q4.w);
+                const unsigned* keyhi = reinterpret_cast<const unsigned*>(dkey) + 1;      // high (depth) words of dkey / skey
                 for (int o = lane; o < npix; o += 32) {
                     const int row = (o * magic) >> 16;
                     const int col = o - row * w;
                     const int lx = c0 + col, ly = r0 + row;
-                    const float px = spx[lx], py = spy[ly];
-                    if (px > bxmax || px < bxmin || py > bymax || py < bymin) continue;
                     const int pix = ly * TW + lx;
+                    // prune on the depth words of the keys alone (conservative on ties): no fragment of this face can be nearer
+                    // than its nearest vertex
+                    if (zbits > keyhi[2 * pix] && zbits > keyhi[2 * (3 * R_THREADS + R_THREADS + pix)]) continue;
+                    const float px = spx[lx], py = spy[ly];
                     const unsigned long long dk = dkey[pix], sk = skey[3 * R_THREADS + pix];
-                    if (zkey > dk && zkey > sk) continue;
                     const float dx0 = MH_SUB(px, x0), dy0 = MH_SUB(py, y0);
                     const float dx1 = MH_SUB(px, x1), dy1 = MH_SUB(py, y1);
                     const float dx2 = MH_SUB(px, x2), dy2 = MH_SUB(py, y2);
