@@ -212,6 +212,7 @@ def cpu_problem(w, extra=None):
     def step():
         fr.cycle_grads(data, batches)
         opt.step()
+    step.fit_ref, step.data, step.batches, step.cam_K, step.start = fr, data, batches, cam_K, s      # for tests/test_gpu_fullsize.py
     return step, Ts * N
 
 
