@@ -394,9 +394,11 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'render_traffic.json')
     if os.path.exists(tp):
+        # dram__bytes_read + dram__bytes_write of ONE k_render<0> launch from the committed `ncu --set full` capture (workload c3s:
+        # the first 64 frames of c3, same persons / resolution / cloud), scaled by the person-frames of this launch
         tj = json.load(open(tp))
-        if tj.get('workload') == args.workload and tj.get('n_gpus') == world:
-            traffic = tj.get('dram_bytes_per_launch')
+        if args.workload in ('c3', 'c3s'):
+            traffic = tj['dram_bytes_per_person_frame'] * units
     line = {
         'metric': 'person_frame_optimizer_iters_per_sec', 'value': value, 'unit': 'person-frame-iters/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
