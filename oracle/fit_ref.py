@@ -24,7 +24,7 @@ def _t(a):
 
 class FitRef(object):
     def __init__(self, model, image_size, num_frames, cam_K, coefs, cam_dist_coef=None,
-                 joint_confidence_thr=0.5, eps=1e-3, znear=1.0, zfar=100.0):
+                 joint_confidence_thr=0.5, eps=1e-3, znear=1.0, zfar=100.0, pose17j_weights=None):
         """model: dict from ``oracle.synth.load_model_tensors``; image_size (W,H);
         coefs: dict over COEF_KEYS (``optimizer.py:159-167``)."""
         self.m = {k: (_t(v) if isinstance(v, np.ndarray) and v.dtype == np.float32 else v) for k, v in model.items()}
@@ -36,6 +36,8 @@ class FitRef(object):
         self.Kd = cam_dist_coef
         self.coefs = dict(coefs)
         self.thr = joint_confidence_thr
+        w17 = np.ones(17, np.float32) if pose17j_weights is None else np.asarray(pose17j_weights, np.float32)
+        self.pose_weights = _t((len(w17) * w17 / np.sum(w17)).astype(np.float32)).view(1, 1, 17, 1)      # optimizer.py:127-130, 259
         self.eps = eps
         self.Kndc = _t(rm.compute_calibration_matrix(znear, zfar, self.cam_K, image_size))   # :206
         self.scene_pcd = None
@@ -135,7 +137,8 @@ class FitRef(object):
         Kt = _t(self.cam_K)[None].expand(B * N, 3, 3)
         j2d = rm.camera_projection(joints_abs.view(B * N, -1, 3), Kt, self.Kd).view(B, N, -1, 2)
         norm = torch.tensor([[[[float(W), float(H)]]]])
-        loss_pose = torch.sum(torch.square(thr_scores * j2d / norm - thr_scores * pose2d[..., 0:2] / norm))
+        pmask = self.pose_weights * thr_scores                                            # :420
+        loss_pose = torch.sum(torch.square(pmask * j2d / norm - pmask * pose2d[..., 0:2] / norm))
         # raster terms :425-475
         target_disp = depths * (1.0 / min_z - 1.0 / max_z) + 1.0 / max_z
         zb, al = [], []

@@ -445,3 +445,81 @@ def test_full_fit_runs_like_the_reference(pkg, L):
         assert v[k].shape == g['final_' + k].shape, k
     assert np.abs(v['poses_T'] - g['final_poses_T']).max() < 0.15                                 # metres; oracle-vs-reference spread is 0.035
     assert v['scene_mask'].min() == 1
+
+
+def _oracle_cycle_custom(g, data, meta, cycle, T_use=None, **kw):
+    import torch
+    from oracle import fit_ref, synth
+    N, T, W, H, batch = meta[:5]
+    T_use = T if T_use is None else T_use
+    model = synth.load_model_tensors(gh.model_dir())
+    fr = fit_ref.FitRef(model, (W, H), T_use, g['cam_K'], gh.COEFS, **kw)
+    c = cycle
+    fr.set_variables(g[f'c{c}_p_poses_T'][:T_use], g[f'c{c}_p_poses_smpl'][:T_use], g[f'c{c}_p_betas'], data['valid_smpl'][:T_use],
+                     g[f'c{c}_p_zmin_lin'][:T_use], g[f'c{c}_p_zmax_lin'][:T_use], g[f'c{c}_p_xscale'])
+    fr.betas_ref = torch.from_numpy(g['init_betas'])
+    if len(g[f'c{c}_scene_pcd']):
+        fr.set_scene_pcd(g[f'c{c}_scene_pcd'])
+    d = {k: v[:T_use] for k, v in data.items()}
+    log, _ = fr.cycle_grads(d, [np.arange(s, min(s + batch, T_use)) for s in range(0, T_use, batch)])
+    return log, {nm: p.grad.numpy().copy() for nm, p in zip(gh.NAMES, fr.leaves())}
+
+
+def test_distortion_and_joint_weights(pkg, L):
+    """camera_projection_torch with the 5 distortion coefficients (transforms.py:78-90, the code's own y term) and non-uniform
+    pose17j_weights (optimizer.py:108-130, 420) vs the oracle."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch = meta[:5]
+    Kd = np.array([0.1, 0.01, 0.001, 0.002, 0.0001], np.float32)
+    w17 = np.linspace(0.5, 2.0, 17).astype(np.float32)
+    opt = gh.make_optimizer(pkg, g, data, meta, cam_dist_coef=Kd, pose17j_weights=w17)
+    log, grads = gh.teacher_forced_cycle(opt, g, data, meta, 31)
+    olog, ograds = _oracle_cycle_custom(g, data, meta, 31, cam_dist_coef=Kd, pose17j_weights=w17)
+    for k, v in log.items():
+        assert abs(v - olog[k]) <= 1e-4 * abs(olog[k]) + 1e-9, (k, v, olog[k])
+    for nm, gr in grads.items():
+        ref = ograds[nm].reshape(gr.shape)
+        assert np.abs(gr - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, nm
+    assert abs(log['loss_pose24j'] - float(g['c31_log_loss_pose24j'])) > 1e-3 * float(g['c31_log_loss_pose24j'])      # the options matter
+
+
+def test_single_frame_sequence(pkg, L):
+    """num_frames = 1: no temporal pairs, no foot-sliding pairs (optimizer.py:177-179, 512-518, 560)."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch, num_iter, init_iter = meta
+    d1 = {k: v[:1] for k, v in data.items()}
+    m1 = (N, 1, W, H, 1, num_iter, init_iter)
+    g1 = {k: (g[k][:1] if (k.startswith('c31_p_') and g[k].shape[0] == T) else g[k]) for k in g.files}
+    opt = gh.make_optimizer(pkg, g, d1, m1)
+    log, grads = gh.teacher_forced_cycle(opt, g1, d1, m1, 31)
+    olog, ograds = _oracle_cycle_custom(g, data, (N, T, W, H, 1), 31, T_use=1)
+    assert log['reg_vel'] == 0 and log['reg_foot_sliding'] == 0
+    for k, v in log.items():
+        assert abs(v - olog[k]) <= 1e-4 * abs(olog[k]) + 1e-9, (k, v, olog[k])
+    for nm, gr in grads.items():
+        ref = ograds[nm].reshape(gr.shape)
+        assert np.abs(gr - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, nm
+    y = opt.one_euro_filter(np.zeros((1, 5), np.float32), 0.01, 0.02)
+    assert tuple(y.shape) == (1, 5)
+
+
+def test_fixed_scale_factor_is_not_updated(pkg, L):
+    """scale_factor given to init_optimized_variables -> xscale_factor is not an optimised leaf (optimizer.py:279-282, 350-353)."""
+    g, data, meta = gh.load_fit('fit_c1.npz')
+    N, T, W, H, batch = meta[:5]
+    opt = gh.make_optimizer(pkg, g, data, meta)
+    sf = np.full(N, 1.21, np.float32)
+    opt.init_optimized_variables(data['pose2d'], data['poses_smpl'], data['betas_smpl'], data['valid_smpl'], scale_factor=sf, num_iter=2,
+                                 batch_size=batch)
+    assert opt.optim_scale_factor is False
+    x0 = opt.ctx.get_param(L.P_XSCALE, (N,))
+    assert np.allclose(x0, 2.0, atol=1e-5)                                     # 1.1^2 = 1.21
+    opt._ingest(gh.ListLoader(data, batch))
+    st = opt._stream()
+    opt.ctx.call('mh_reset_optimizer', st)
+    p0 = opt.ctx.get_param(L.P_POSES_T, (T, N, 3))
+    opt.ctx.call('mh_fit_grads', 0, 0, st)
+    opt.ctx.call('mh_fit_update', 0.01, st)
+    assert np.array_equal(opt.ctx.get_param(L.P_XSCALE, (N,)), x0)
+    assert np.abs(opt.ctx.get_param(L.P_POSES_T, (T, N, 3)) - p0).max() > 0
+    assert np.allclose(opt.get_optimized_variables()['scale_factor'].reshape(-1), 1.21, atol=1e-5)
