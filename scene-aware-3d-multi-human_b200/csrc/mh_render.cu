@@ -41,6 +41,8 @@ struct MhRenderScratch {
     size_t smem;
     int* counter;
     long long* prof;
+    int maxbins;               // tile bins per body before the binning granularity is coarsened (<= R_MAXBINS)
+    int bincap_use, wcap_use;  // capacities handed to the kernel (<= the allocated ones; testing aid)
 };
 
 struct RenderParams {
@@ -61,6 +63,7 @@ struct RenderParams {
     float blur_d, blur_s, r_d, sigma, eps;
     float coef_depth, coef_sil;
     float* dbg_zbuf; float* dbg_alpha; int dbg_body;
+    int maxbins;
     long long* prof;              // optional: per-phase cycle counters (8 per CTA)
 };
 
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             const int tx0 = c0 / TW, tx1 = c1 / TW, ty0 = r0 / TH, ty1 = r1 / TH;
             int ntx = max(tx1 - tx0 + 1, 0), nty = max(ty1 - ty0 + 1, 0);
             int ks = 0;
-            while ((((ntx + (1 << ks) - 1) >> ks) * ((nty + (1 << ks) - 1) >> ks)) > R_MAXBINS) ++ks;
+            while ((((ntx + (1 << ks) - 1) >> ks) * ((nty + (1 << ks) - 1) >> ks)) > P.maxbins) ++ks;
             sint[1] = tx0; sint[2] = ty0; sint[3] = ntx; sint[4] = nty; sint[5] = ks;
             sint[6] = 0;     // winner count
             sint[7] = 0;     // overflow flag
@@ -612,6 +615,8 @@ int mh_render_alloc(mh_ctx* c) {
     memset(rs, 0, sizeof(*rs));
     c->rs = rs;
     rs->nctas = c->num_sms;
+    rs->maxbins = R_MAXBINS;
+    rs->bincap_use = 0; rs->wcap_use = 0;
     rs->bincap = 1 << 20;
     rs->wcap = c->d.H * c->d.W;
     const size_t n = (size_t)rs->nctas;
@@ -658,6 +663,9 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.pfout = c->pfout; P.devflags = c->devflags;
     P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.frec = c->rs->frec; P.fbin = c->rs->fbin; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
     P.counter = c->rs->counter;
+    P.maxbins = c->rs->maxbins;
+    if (c->rs->bincap_use) P.bincap = c->rs->bincap_use;
+    if (c->rs->wcap_use) P.wcap = c->rs->wcap_use;
     P.prof = c->rs->prof;
     P.T = d.T; P.N = d.N; P.H = d.H; P.W = d.W;
     P.k00 = c->Kndc[0]; P.k02 = c->Kndc[2]; P.k11 = c->Kndc[5]; P.k12 = c->Kndc[6];
@@ -715,5 +723,20 @@ extern "C" int mh_render_profile(mh_ctx* c, int32_t on, long long* out8_host) {
     if (on && !rs->prof) MH_CUDA(c, cudaMalloc((void**)&rs->prof, n * sizeof(long long)));
     if (on) MH_CUDA(c, cudaMemset(rs->prof, 0, n * sizeof(long long)));
     if (!on && rs->prof) { cudaFree(rs->prof); rs->prof = nullptr; }
+    return MH_OK;
+}
+
+// Testing aid: shrink the render capacities so that small inputs exercise the coarse-binning path (maxbins) and the
+// capacity-error paths (tile-list entries, depth-winner entries).  0 keeps a value.
+extern "C" int mh_debug_set_render_caps(mh_ctx* c, int32_t maxbins, int32_t bincap, int32_t wcap) {
+    if (!c || !c->rs) return MH_E_ARG;
+    MhRenderScratch* rs = c->rs;
+    if (maxbins < 0 || maxbins > R_MAXBINS || bincap < 0 || bincap > (1 << 20) || wcap < 0 || wcap > c->d.H * c->d.W)
+        MH_FAIL(c, MH_E_ARG, "mh_debug_set_render_caps: capacities can only be reduced");
+    if (maxbins) rs->maxbins = maxbins;
+    if (bincap) rs->bincap_use = bincap;
+    if (wcap) rs->wcap_use = wcap;
+    cudaSetDevice(c->d.device);
+    MH_CUDA(c, cudaMemset(c->devflags + 1, 0, sizeof(int)));
     return MH_OK;
 }

@@ -523,3 +523,25 @@ def test_fixed_scale_factor_is_not_updated(pkg, L):
     assert np.array_equal(opt.ctx.get_param(L.P_XSCALE, (N,)), x0)
     assert np.abs(opt.ctx.get_param(L.P_POSES_T, (T, N, 3)) - p0).max() > 0
     assert np.allclose(opt.get_optimized_variables()['scale_factor'].reshape(-1), 1.21, atol=1e-5)
+
+
+def test_coarse_binning_and_capacity_errors(pkg, L):
+    """Bodies whose tile count exceeds the bin table use coarser bins (same results); exceeding the tile-list or the
+    depth-winner capacity is reported as MH_E_CAPACITY, never silently dropped."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    opt = gh.make_optimizer(pkg, g, data, meta)
+    ref_log, ref_grads = gh.teacher_forced_cycle(opt, g, data, meta, 31)
+    opt.ctx.call('mh_debug_set_render_caps', 2, 0, 0)                          # at most 2 bins per body -> binning granularity is coarsened
+    log, grads = gh.teacher_forced_cycle(opt, g, data, meta, 31)
+    for k in log:
+        assert abs(log[k] - ref_log[k]) <= 1e-6 * abs(ref_log[k]) + 1e-12, k
+    for nm in grads:
+        assert np.abs(grads[nm] - ref_grads[nm]).max() <= 1e-5 * np.abs(ref_grads[nm]).max() + 1e-9, nm
+    opt.ctx.call('mh_debug_set_render_caps', 0, 0, 16)                         # 16 depth winners per body
+    with pytest.raises(L.MhError, match='capacity'):
+        gh.teacher_forced_cycle(opt, g, data, meta, 31)
+    opt2 = gh.make_optimizer(pkg, g, data, meta)
+    gh.prepare(opt2, g, data, meta)
+    opt2.ctx.call('mh_debug_set_render_caps', 0, 64, 0)                        # 64 tile-list entries per body
+    with pytest.raises(L.MhError, match='capacity'):
+        gh.teacher_forced_cycle(opt2, g, data, meta, 31)
