@@ -40,6 +40,7 @@ struct MhRenderScratch {
     int nctas;
     size_t smem;
     int* counter;
+    float* gsg; int gred;
     long long* prof;
     int maxbins;               // tile bins per body before the binning granularity is coarsened (<= R_MAXBINS)
     int bincap_use, wcap_use;  // capacities handed to the kernel (<= the allocated ones; testing aid)
@@ -53,6 +54,7 @@ struct RenderParams {
     const uint8_t* pose2d_valid; const uint8_t* mask_valid;
     const float* zmin_lin; const float* zmax_lin;
     float* pfout; int* devflags;
+    float* gsg;                   // GRED: per-CTA NDC-gradient rows (MH_LD3V floats each)
     uint16_t* binlist; int bincap;
     float4* frec; uint2* fbin;    // per-CTA scratch: 5 float4 per face (set-up record), packed bin range + depth slab per face
     int* wpix; int* wface; float* wz; int wcap;
@@ -60,7 +62,7 @@ struct RenderParams {
     int T, N, H, W;
     float k00, k02, k11, k12;
     float rx, ry;                 // NDC extent of the x / y axis (2 on the short side)
-    float blur_d, blur_s, r_d, sigma, eps;
+    float blur_d, blur_s, r_d, r_s, sigma, eps;    // r_s: conservative (x 1.001) radius of the silhouette raster
     float coef_depth, coef_sil;
     float* dbg_zbuf; float* dbg_alpha; int dbg_body;
     int maxbins;
@@ -148,12 +150,20 @@ __device__ __forceinline__ void frag_values(const float* sv, const int32_t* __re
     *sd = inside ? -d : d;
 }
 
-template <int MODE>      // 0: losses + gradients ; 1: dense zbuf / alpha planes of one body
+// gradient scatter: shared-memory float atomics are compare-and-swap loops (ATOMS.CAST.SPIN) that retry when the pixels of
+// a warp hit the same vertex; GRED = 1 sends them as fire-and-forget reductions (RED.E.ADD.F32) to a per-CTA row that stays in L2
+template <int GRED>
+__device__ __forceinline__ void grad_add(float* p, float v) {
+    if (GRED) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    else atomicAdd(p, v);
+}
+
+template <int MODE, int GRED>      // MODE 0: losses + gradients ; 1: dense zbuf / alpha planes of one body
 __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sv = reinterpret_cast<float*>(smem_raw);                                   // MH_LD3V  NDC vertices
-    float* sg = sv + MH_LD3V;                                                         // MH_LD3V  NDC gradients
-    unsigned long long* dkey = reinterpret_cast<unsigned long long*>(sg + MH_LD3V);   // R_THREADS     nearest depth fragment
+    float* sg = GRED ? P.gsg + (size_t)blockIdx.x * MH_LD3V : sv + MH_LD3V;           // MH_LD3V  NDC gradients (GRED: global, zero on entry)
+    unsigned long long* dkey = reinterpret_cast<unsigned long long*>(sv + 2 * MH_LD3V);   // R_THREADS     nearest depth fragment
     unsigned long long* skey = dkey + R_THREADS;                                      // 4 x R_THREADS nearest silhouette fragments
     int* tcount = reinterpret_cast<int*>(skey + 4 * R_THREADS);                            // R_MAXBINS + 1 (exclusive offsets after the scan)
     int* tcur = tcount + R_MAXBINS + 1;                                               // R_MAXBINS
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                          "l"(P.verts + b * MH_LD3V), "r"(bytes), "r"(smem_u32(&mbar))
                          : "memory");
         }
-        for (int e = tid; e < MH_LD3V; e += R_THREADS) sg[e] = 0.f;
+        if (!GRED) for (int e = tid; e < MH_LD3V; e += R_THREADS) sg[e] = 0.f;
         {
             uint32_t done = 0;
             while (!done) {
@@ -298,9 +308,16 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         rec[0] = make_float4(x0, y0, x1, y1);
                         rec[1] = make_float4(x2, y2, z0, z1);
                         rec[2] = make_float4(z2, __frcp_rn(den), l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), l02 <= MH_KEPS ? 0.f : __frcp_rn(l02));
-                        rec[3] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), bxmin, bxmax, bymin);
+                        // inner rectangle: the only pixels where the face can be a SILHOUETTE fragment (bbox inflated by the
+                        // silhouette radius x 1.001, 0.01 px slack: conservative, the exact distance test follows per pixel)
+                        int ic0 = (int)fmaxf(ceilf(pix_of(bxmax - P.r_d + P.r_s, P.W, P.rx) - 0.01f), (float)c0);
+                        int ic1 = (int)fminf(floorf(pix_of(bxmin + P.r_d - P.r_s, P.W, P.rx) + 0.01f), (float)c1);
+                        int ir0 = (int)fmaxf(ceilf(pix_of(bymax - P.r_d + P.r_s, P.H, P.ry) - 0.01f), (float)r0);
+                        int ir1 = (int)fminf(floorf(pix_of(bymin + P.r_d - P.r_s, P.H, P.ry) + 0.01f), (float)r1);
+                        if (ic0 > ic1 || ir0 > ir1) { ic0 = 1; ic1 = 0; ir0 = 1; ir1 = 0; }
+                        rec[3] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), __int_as_float(ic0 | (ic1 << 16)), __int_as_float(ir0 | (ir1 << 16)), 0.f);
                         // no fragment of a face can be nearer than its nearest vertex
-                        rec[4] = make_float4(bymax, __int_as_float(c0 | (c1 << 16)), __int_as_float(r0 | (r1 << 16)),
+                        rec[4] = make_float4(0.f, __int_as_float(c0 | (c1 << 16)), __int_as_float(r0 | (r1 << 16)),
                                              __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))));
                     }
                 }
@@ -369,17 +386,34 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             const int ox = (tx0 + ttx) * TW, oy = (ty0 + tty) * TH;       // tile origin (pixels)
             __syncthreads();
             PROF(4);
-            dkey[tid] = KEY_EMPTY;
+            // this thread's pixel (the same in the tile set-up and in P3): what the loss needs there.  A pixel that needs no
+            // depth fragment (outside the eroded instance mask, optimizer.py:434-438) or no silhouette fragments (hidden by the
+            // masks of nearer persons or gated off, :459-475) gets key 0 = "nothing can improve it": P2 prunes every face there
+            unsigned pflags;                                              // bit 0 need depth, 1 need silhouette, 2 seg bit, 3 in image
+            {
+                const int xip = ox + (tid & (TW - 1)), yip = oy + (tid >> 5);
+                const bool inimg = (xip < P.W) && (yip < P.H);
+                pflags = inimg ? 0xbu : 0u;
+                if (MODE == 0 && inimg) {
+                    const size_t pidx = plane + (size_t)yip * P.W + xip;
+                    const uint32_t cb = P.cbits[pidx], eb = P.ebits[pidx];
+                    pflags = 8u | ((pvalid && ((eb >> n) & 1u)) ? 1u : 0u) | ((gate && ((cb & pre) == 0u)) ? 2u : 0u) | (((cb >> n) & 1u) << 2);
+                }
+            }
+            const bool need_d = pflags & 1u, need_s = pflags & 2u;
+            dkey[tid] = need_d ? KEY_EMPTY : 0ull;
             if (tid == 0) sint[40] = 0;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) skey[s * R_THREADS + tid] = KEY_EMPTY;
+            for (int s = 0; s < 3; ++s) skey[s * R_THREADS + tid] = KEY_EMPTY;
+            skey[3 * R_THREADS + tid] = need_s ? KEY_EMPTY : 0ull;
             if (tid < TW) spx[tid] = (ox + tid < P.W) ? P.pix_x[ox + tid] : 0.f;
             if (tid >= 64 && tid < 64 + TH) spy[tid - 64] = (oy + tid - 64 < P.H) ? P.pix_y[oy + tid - 64] : 0.f;
             const int txmax = min(TW, P.W - ox) - 1, tymax = min(TH, P.H - oy) - 1;     // last valid local column / row
             // ---- P2: scatter -- each warp takes one face of the tile at a time (set-up evaluated redundantly by the lanes, no
             //      staging barrier) and spreads the face's pixel rectangle over its lanes, 32 pixels per pass ----
-            __syncthreads();
+            const int tile_needed = __syncthreads_or(need_d || need_s);
             PROF(2);
+            if (!tile_needed) continue;                                   // uniform: nothing the loss reads in this tile
             float4* wrec = swrec + warp * 10;
             // faces are handed out dynamically (shared counter), two indices ahead of the one being processed
             int f = 0, fn1 = 0, fn2 = 0;
@@ -406,13 +440,16 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 f = fn1; fn1 = fn2;
                 const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y, z0 = q1.z, z1 = q1.w, z2 = q2.x;
                 const float inv_den = q2.y, il01 = q2.z, il02 = q2.w, il12 = q3.x;
-                const float bxmin = q3.y, bxmax = q3.z, bymin = q3.w, bymax = q4.x;
                 const int cc = __float_as_int(q4.y), rr = __float_as_int(q4.z);
+                const int ci = __float_as_int(q3.y), ri = __float_as_int(q3.z);
                 // the face's pixel rectangle clipped to the tile
                 const int c0 = max((cc & 0xffff) - ox, 0), c1 = min((cc >> 16) - ox, txmax);
                 const int r0 = max((rr & 0xffff) - oy, 0), r1 = min((rr >> 16) - oy, tymax);
                 const int w = c1 - c0 + 1, h = r1 - r0 + 1;
                 if (w <= 0 || h <= 0) continue;
+                // inner (silhouette) rectangle in tile coordinates; extent 0 when empty
+                const int jc0 = (ci & 0xffff) - ox, jr0 = (ri & 0xffff) - oy;
+                const unsigned jw = (unsigned)max((ci >> 16) - (ci & 0xffff) + 1, 0), jh = (unsigned)max((ri >> 16) - (ri & 0xffff) + 1, 0);
                 const int npix = w * h;
                 const int magic = c_magic[w];
                 const bool dpos = inv_den > 0.f;
@@ -428,10 +465,12 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const int lx = c0 + col, ly = r0 + row;
                     const int pix = ly * TW + lx;
                     // prune on the depth words of the keys alone (conservative on ties): no fragment of this face can be nearer
-                    // than its nearest vertex
-                    if (zbits > keyhi[2 * pix] && zbits > keyhi[2 * (3 * R_THREADS + R_THREADS + pix)]) continue;
+                    // than its nearest vertex; outside the inner rectangle it cannot be a silhouette fragment at all
+                    const bool inner = ((unsigned)(lx - jc0) < jw) && ((unsigned)(ly - jr0) < jh);
+                    const bool pd = zbits <= keyhi[2 * pix];
+                    const bool ps = inner && (zbits <= keyhi[2 * (3 * R_THREADS + R_THREADS + pix)]);
+                    if (!pd && !ps) continue;
                     const float px = spx[lx], py = spy[ly];
-                    const unsigned long long dk = dkey[pix], sk = skey[3 * R_THREADS + pix];
                     const float dx0 = MH_SUB(px, x0), dy0 = MH_SUB(py, y0);
                     const float dx1 = MH_SUB(px, x1), dy1 = MH_SUB(py, y1);
                     const float dx2 = MH_SUB(px, x2), dy2 = MH_SUB(py, y2);
@@ -439,6 +478,14 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const float e0 = MH_SUB(MH_MUL(dx1, ey12), MH_MUL(dy1, ex12));
                     const float e1 = MH_SUB(MH_MUL(dx2, ey20), MH_MUL(dy2, ex20));
                     const float e2 = MH_SUB(MH_MUL(dx0, ey01), MH_MUL(dy0, ex01));
+                    // depth first: a fragment that cannot displace a key needs no distance test
+                    const float c0w = __saturatef(e0 * inv_den), c1w = __saturatef(e1 * inv_den), c2w = __saturatef(e2 * inv_den);
+                    const float pz = __fdividef(c0w * z0 + c1w * z1 + c2w * z2, fmaxf(c0w + c1w + c2w, 1e-5f));
+                    if (!(pz >= 0.f)) continue;
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)fcur;
+                    const bool wd = pd && (key < dkey[pix]);
+                    const bool ws = ps && (key < skey[3 * R_THREADS + pix]);
+                    if (!wd && !ws) continue;
                     const bool inside = (e0 != 0.f) && (e1 != 0.f) && (e2 != 0.f) && ((e0 > 0.f) == dpos) && ((e1 > 0.f) == dpos) && ((e2 > 0.f) == dpos);
                     bool vd = inside, vs = inside;
                     if (!inside) {
@@ -454,27 +501,20 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                             load_face(sv, P.faces, fcur, P.r_d, &fc, iv);
                             mh_face_eval(fc, px, py, &fr);
                             vd = fr.dist < P.blur_d; vs = fr.dist < P.blur_s;
-                            if (!vd) continue;
                         }
                     }
-                    const float c0w = __saturatef(e0 * inv_den), c1w = __saturatef(e1 * inv_den), c2w = __saturatef(e2 * inv_den);
-                    const float pz = __fdividef(c0w * z0 + c1w * z1 + c2w * z2, fmaxf(c0w + c1w + c2w, 1e-5f));
-                    if (!(pz >= 0.f)) continue;
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)fcur;
-                    if (vd && key < dk) atomicMin(&dkey[pix], key);
-                    if (vs && key < sk) key_insert4(skey + pix, key);
+                    if (vd && wd) atomicMin(&dkey[pix], key);
+                    if (vs && ws) key_insert4(skey + pix, key);
                 }
             }
             __syncthreads();
             PROF(3);
             // ---- P3: one thread per pixel: exact fragments of the winners, losses, silhouette backward ----
-            const int lx = tid & (TW - 1), ly = tid >> 5;
-            const int xi = ox + lx, yi = oy + ly;
-            if (xi >= P.W || yi >= P.H) continue;
-            const float pxn = spx[lx], pyn = spy[ly];
-            const size_t pidx = plane + (size_t)yi * P.W + xi;
+            if (!(pflags & 8u)) continue;
+            const int xi = ox + (tid & (TW - 1)), yi = oy + (tid >> 5);
+            const float pxn = spx[tid & (TW - 1)], pyn = spy[tid >> 5];
             float dz = -1.0f; int df = -1;
-            if (dkey[tid] != KEY_EMPTY) {
+            if ((pflags & 1u) && dkey[tid] != KEY_EMPTY) {
                 df = (int)(dkey[tid] & 0xffffffffull);
                 float sdu;
                 frag_values(sv, P.faces, df, pxn, pyn, &dz, &sdu);
@@ -483,7 +523,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             float prod = 1.0f;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const unsigned long long k = skey[s * R_THREADS + tid];
+                const unsigned long long k = (pflags & 2u) ? skey[s * R_THREADS + tid] : KEY_EMPTY;
                 sf[s] = -1; sd[s] = 0.f; pk[s] = 0.f;
                 if (k != KEY_EMPTY) {
                     sf[s] = (int)(k & 0xffffffffull);
@@ -499,14 +539,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 P.dbg_alpha[(size_t)yi * P.W + xi] = alpha;
                 continue;
             }
-            const uint32_t cb = P.cbits[pidx];
             // ---- depth term (optimizer.py:431-442) ----
-            if (df >= 0 && dz > 0.f && pvalid && ((P.ebits[pidx] >> n) & 1u)) {
+            if (df >= 0 && dz > 0.f) {                                  // need_d: pose2d-valid person, pixel inside the eroded mask
                 const float zc = fmaxf(dz + 0.2f, P.eps);
                 const float zdisp = 1.0f / zc;
                 aS += 1.0f;
                 aA += logf(fmaxf(zdisp, P.eps));
-                const float dd = P.depth[pidx];
+                const float dd = P.depth[plane + (size_t)yi * P.W + xi];
                 const float td = dd * tda + izmax;                        // target_disp (:425)
                 aC += logf(fmaxf(td, P.eps));
                 if (td >= P.eps) { aGmin += dd / td; aGmax += (1.0f - dd) / td; }
@@ -518,8 +557,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 }
             }
             // ---- silhouette term (optimizer.py:459-475, losses.py:35-38) ----
-            if (gate && (cb & pre) == 0u) {
-                const float seg = (float)((cb >> n) & 1u);
+            if (pflags & 2u) {                                           // gate && (cb & pre) == 0
+                const float seg = (float)((pflags >> 2) & 1u);
                 const float df_ = alpha - seg;
                 aSil += df_ * df_;
                 aCnt += seg;
@@ -541,8 +580,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         mh_face_bwd(fc, pxn, pyn, 0.f, gdist, g);
 #pragma unroll
                         for (int e = 0; e < 3; ++e) {
-                            if (g[3 * e] != 0.f) atomicAdd(&sg[3 * iv[e]], g[3 * e]);
-                            if (g[3 * e + 1] != 0.f) atomicAdd(&sg[3 * iv[e] + 1], g[3 * e + 1]);
+                            if (g[3 * e] != 0.f) grad_add<GRED>(&sg[3 * iv[e]], g[3 * e]);
+                            if (g[3 * e + 1] != 0.f) grad_add<GRED>(&sg[3 * iv[e] + 1], g[3 * e + 1]);
                         }
                     }
                 }
@@ -586,16 +625,23 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 mh_face_bwd(fc, P.pix_x[xi], P.pix_y[yi], kappa * wz[e], 0.f, g);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) if (g[k] != 0.f) atomicAdd(&sg[3 * iv[k / 3] + (k % 3)], g[k]);
+                for (int k = 0; k < 9; ++k) if (g[k] != 0.f) grad_add<GRED>(&sg[3 * iv[k / 3] + (k % 3)], g[k]);
             }
         }
         __syncthreads();
         PROF(5);
         // ---- P5: NDC -> camera-space chain rule, accumulate into dL/dV (this CTA owns the row) ----
+        if (GRED) { __threadfence(); __syncthreads(); }
         const float* vw = P.verts + b * MH_LD3V;
         float* dv = P.dverts + b * MH_LD3V;
         for (int v = tid; v < MH_V; v += R_THREADS) {
-            const float gx = sg[3 * v], gy = sg[3 * v + 1], gz = sg[3 * v + 2];
+            float gx, gy, gz;
+            if (GRED) {                                                   // read at L2 (where the reductions landed), clear for the next body
+                gx = __ldcg(&sg[3 * v]); gy = __ldcg(&sg[3 * v + 1]); gz = __ldcg(&sg[3 * v + 2]);
+                if (gx != 0.f) sg[3 * v] = 0.f;
+                if (gy != 0.f) sg[3 * v + 1] = 0.f;
+                if (gz != 0.f) sg[3 * v + 2] = 0.f;
+            } else { gx = sg[3 * v]; gy = sg[3 * v + 1]; gz = sg[3 * v + 2]; }
             if (gx == 0.f && gy == 0.f && gz == 0.f) continue;
             const float X = vw[3 * v], Y = vw[3 * v + 1], Z = vw[3 * v + 2];
             const float iz = 1.0f / Z;
@@ -627,6 +673,9 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wface, n * rs->wcap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wz, n * rs->wcap * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->gsg, n * MH_LD3V * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(float));
+    { const char* v = getenv("MH_RENDER_GRED"); rs->gred = v ? atoi(v) : 0; }     // development switch
     rs->prof = nullptr;
     {
         int magic[TW + 1];
@@ -637,8 +686,9 @@ int mh_render_alloc(mh_ctx* c) {
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
     rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) +
                (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (256 + TW + TH) * sizeof(float) + 64 * sizeof(int) + (size_t)(R_THREADS / 32) * 10 * sizeof(float4) + 128;
-    e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
+    e = cudaFuncSetAttribute(k_render<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render: %zu bytes of shared memory: %s", rs->smem, cudaGetErrorString(e));
     return MH_OK;
 }
@@ -646,7 +696,7 @@ int mh_render_alloc(mh_ctx* c) {
 void mh_render_free(mh_ctx* c) {
     if (!c->rs) return;
     if (c->rs->prof) cudaFree(c->rs->prof);
-    cudaFree(c->rs->frec); cudaFree(c->rs->fbin);
+    cudaFree(c->rs->frec); cudaFree(c->rs->fbin); cudaFree(c->rs->gsg);
     cudaFree(c->rs->binlist); cudaFree(c->rs->wpix); cudaFree(c->rs->wface); cudaFree(c->rs->wz); cudaFree(c->rs->counter);
     delete c->rs;
     c->rs = nullptr;
@@ -662,7 +712,7 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.zmin_lin = c->params + c->off[MH_P_ZMIN_LIN]; P.zmax_lin = c->params + c->off[MH_P_ZMAX_LIN];
     P.pfout = c->pfout; P.devflags = c->devflags;
     P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.frec = c->rs->frec; P.fbin = c->rs->fbin; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
-    P.counter = c->rs->counter;
+    P.counter = c->rs->counter; P.gsg = c->rs->gsg;
     P.maxbins = c->rs->maxbins;
     if (c->rs->bincap_use) P.bincap = c->rs->bincap_use;
     if (c->rs->wcap_use) P.wcap = c->rs->wcap_use;
@@ -672,6 +722,7 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.rx = d.W > d.H ? (float)(2.0 * d.W / d.H) : 2.0f;
     P.ry = d.H > d.W ? (float)(2.0 * d.H / d.W) : 2.0f;
     P.blur_d = blur_d; P.blur_s = blur_s; P.r_d = sqrtf(blur_d > blur_s ? blur_d : blur_s);
+    P.r_s = fminf(sqrtf(blur_s) * 1.001f, P.r_d);
     P.sigma = 1e-4f;                 // BlendParams default used by SoftSilhouetteShader
     P.eps = c->c.eps;
     P.coef_depth = c->c.depth; P.coef_sil = c->c.silhouette;
@@ -682,7 +733,8 @@ int mh_render_all(mh_ctx* c, cudaStream_t st) {
     RenderParams P = render_params(c, 1e-4f, 2e-5f);          // optimizer.py:213, 223
     MH_CUDA(c, cudaMemsetAsync(c->rs->counter, 0, sizeof(int), st));
     const int grid = std::min(c->rs->nctas, c->d.T * c->d.N);
-    k_render<0><<<grid, R_THREADS, c->rs->smem, st>>>(P);
+    if (c->rs->gred) k_render<0, 1><<<grid, R_THREADS, c->rs->smem, st>>>(P);
+    else k_render<0, 0><<<grid, R_THREADS, c->rs->smem, st>>>(P);
     MH_LAUNCHED(c);
     return MH_OK;
 }
@@ -697,7 +749,7 @@ int mh_render_planes(mh_ctx* c, int t, int n, float* zbuf_dev, float* alpha_dev,
     const int64_t HW = (int64_t)c->d.H * c->d.W;
     k_fill2<<<mh_cdiv(HW, 1024), 256, 0, st>>>(zbuf_dev, -1.0f, alpha_dev, 0.0f, HW);
     MH_LAUNCHED(c);
-    k_render<1><<<1, R_THREADS, c->rs->smem, st>>>(P);
+    k_render<1, 0><<<1, R_THREADS, c->rs->smem, st>>>(P);
     MH_LAUNCHED(c);
     return MH_OK;
 }

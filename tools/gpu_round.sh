@@ -1,0 +1,26 @@
+#!/bin/bash
+# Runs ON the GPU box (through gpurun): variant benches on the c3 profiling slice, parity suite, full c3 line.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
+set -u
+TAG=${1:-x}
+mkdir -p gpurun_out
+B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e"
+timeout 300 $B --workload c3s --render-profile > gpurun_out/${TAG}_c3s_v0.json 2> gpurun_out/${TAG}_c3s_v0.err
+MH_RENDER_GRED=1 timeout 300 $B --workload c3s --render-profile > gpurun_out/${TAG}_c3s_v1.json 2> gpurun_out/${TAG}_c3s_v1.err
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1
+tail -3 gpurun_out/${TAG}_tests.log
+MH_RENDER_GRED=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/${TAG}_tests_v1.log 2>&1
+tail -3 gpurun_out/${TAG}_tests_v1.log
+timeout 600 python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_c3.json 2> gpurun_out/${TAG}_c3.err
+for f in gpurun_out/${TAG}_c3s_v0 gpurun_out/${TAG}_c3s_v1 gpurun_out/${TAG}_c3; do
+  python - "$f" <<'PY'
+import json, sys
+f = sys.argv[1]
+try:
+    j = json.loads(open(f + '.json').read().strip().splitlines()[-1])
+    print(f, 'value', round(j['value']), 'ms', round(j['ms_per_step'], 2), 'render', round(j['stage_ms']['render'], 2), 'e2e', j.get('e2e', {}).get('value'))
+except Exception as e:
+    print(f, 'FAILED', e)
+print(open(f + '.err').read()[-400:])
+PY
+done
