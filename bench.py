@@ -375,8 +375,14 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     if args.render_profile:
-        prof = np.zeros(8, np.int64)
+        prof = np.zeros(32, np.int64)
         ctx.call('mh_render_profile', 0, L.ptr(prof))
+        if prof[8:].any():
+            pf = float(opt.T_local * w['N'] * args.steps)
+            sn = ['items', 'slots', 'warp-passes', 'lanes past prune', 'warp-passes past prune', 'lanes past key test', 'warp-passes past key test',
+                  'depth atomics', 'sil inserts', 'not-inside distance evals', 'lanes past prune (inner)', '-']
+            print('pair statistics per person-frame:', {n_: round(float(v) / pf, 1) for n_, v in zip(sn, prof[8:20])}, file=sys.stderr)
+        prof = prof[:8]
         names = ['load+ndc', 'binning', 'staging', 'pairs', 'per-pixel', 'sums+depth-bwd', 'chain', '-']
         print('render phases (% of CTA cycles):', {n_: round(100.0 * float(v) / max(float(prof.sum()), 1.0), 1) for n_, v in zip(names, prof)}, file=sys.stderr)
     stage = ctx.read_timing(min(args.steps, 64))

@@ -226,7 +226,7 @@ int mh_read_timing(mh_ctx* ctx, float* out_ms, int32_t* n_cycles);
 /* development aid: per-phase cycle counters of the render kernel summed over its CTAs (8 int64: load+NDC | binning |
  * tile staging | pair scatter | per-pixel + silhouette backward | sums + depth backward | chain rule | unused);
  * `on` (re)starts / stops counting, out8_host (may be NULL) receives the counters accumulated so far. */
-int mh_render_profile(mh_ctx* ctx, int32_t on, long long* out8_host);
+int mh_render_profile(mh_ctx* ctx, int32_t on, long long* out32_host);
 /* testing aid: REDUCE the render capacities (0 keeps a value) so that small inputs reach the coarse-binning path (maxbins)
  * and the MH_E_CAPACITY paths (tile-list entries per body, depth-winner entries per body); clears the capacity flag */
 int mh_debug_set_render_caps(mh_ctx* ctx, int32_t maxbins, int32_t bincap, int32_t wcap);

@@ -40,7 +40,7 @@ struct MhRenderScratch {
     int nctas;
     size_t smem;
     int* counter;
-    float* gsg; int gred;
+    float* gsg; int gred; int vflags;
     long long* prof;
     int maxbins;               // tile bins per body before the binning granularity is coarsened (<= R_MAXBINS)
     int bincap_use, wcap_use;  // capacities handed to the kernel (<= the allocated ones; testing aid)
@@ -55,6 +55,7 @@ struct RenderParams {
     const float* zmin_lin; const float* zmax_lin;
     float* pfout; int* devflags;
     float* gsg;                   // GRED: per-CTA NDC-gradient rows (MH_LD3V floats each)
+    int vflags;                   // development switches (MH_RENDER_FLAGS): 1 block-level prune, 2 CAS-first key updates
     uint16_t* binlist; int bincap;
     float4* frec; uint2* fbin;    // per-CTA scratch: 5 float4 per face (set-up record), packed bin range + depth slab per face
     int* wpix; int* wface; float* wz; int wcap;
@@ -112,8 +113,23 @@ __device__ __forceinline__ void load_face(const float* sv, const int32_t* __rest
     mh_face_setup(sv + 3 * iv[0], sv + 3 * iv[1], sv + 3 * iv[2], r, fc);
 }
 
-__device__ __forceinline__ void key_insert4(unsigned long long* slot /*stride R_THREADS*/, unsigned long long x) {
-    // concurrent sorted insertion: every slot keeps the minimum of what reaches it and passes the rest on
+// one native shared-memory add (the compiler's atomicAdd(p, 1) expands to a ~20-instruction match / elect / popc sequence)
+__device__ __forceinline__ int atoms_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+
+// 64-bit shared-memory minimum is a compare-and-swap loop anyway: start it from the value already read (key < cur)
+__device__ __forceinline__ void key_min(unsigned long long* p, unsigned long long cur, unsigned long long key) {
+    for (;;) {
+        const unsigned long long old = atomicCAS(p, cur, key);
+        if (old == cur || old <= key) return;
+        cur = old;
+    }
+}
+
+__device__ __forceinline__ void key_insert4_min(unsigned long long* slot /*stride R_THREADS*/, unsigned long long x) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const unsigned long long old = atomicMin(slot + s * R_THREADS, x);
@@ -122,7 +138,35 @@ __device__ __forceinline__ void key_insert4(unsigned long long* slot /*stride R_
     }
 }
 
-#define PROF(k) do { if (P.prof && tid == 0) { const long long now_ = clock64(); P.prof[blockIdx.x * 8 + (k)] += now_ - tprof; tprof = now_; } } while (0)
+__device__ __forceinline__ void key_insert4(unsigned long long* slot /*stride R_THREADS*/, unsigned long long x) {
+    // concurrent sorted insertion: every slot keeps the minimum of what reaches it and passes the rest on
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        unsigned long long cur = slot[s * R_THREADS];
+        while (x < cur) {
+            const unsigned long long old = atomicCAS(slot + s * R_THREADS, cur, x);
+            if (old == cur) { x = cur; break; }                          // took the slot: the displaced key moves on
+            cur = old;
+        }
+        if (x == KEY_EMPTY) break;
+    }
+}
+
+// -DMH_RSTATS: (face, pixel)-pair statistics of P2 in slots 8.. of the profile buffer (instrumented build only)
+#ifdef MH_RSTATS
+#define RS_DECL long long rs_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define RS_ADD(k, v) (rs_[k] += (v))
+#define RS_WARP(k) do { const unsigned am_ = __activemask(); if ((am_ & (0u - am_)) == (1u << lane)) rs_[k] += 1; } while (0)
+#define RS_FLUSH do { if (P.prof) for (int k_ = 0; k_ < 12; ++k_) if (rs_[k_]) atomicAdd((unsigned long long*)&P.prof[blockIdx.x * MH_NPROF + 8 + k_], (unsigned long long)rs_[k_]); } while (0)
+#else
+#define RS_DECL
+#define RS_ADD(k, v)
+#define RS_WARP(k)
+#define RS_FLUSH
+#endif
+#define MH_NPROF 32
+
+#define PROF(k) do { if (P.prof && tid == 0) { const long long now_ = clock64(); P.prof[blockIdx.x * MH_NPROF + (k)] += now_ - tprof; tprof = now_; } } while (0)
 
 // depth and signed squared edge distance of one (face, pixel) fragment with reciprocal multiplies (values only: every
 // DECISION was taken in P2 with the oracle's exact arithmetic)
@@ -171,7 +215,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     float* spx = sred + 256;                                                          // TW
     float* spy = spx + TW;                                                            // TH
     int* sint = reinterpret_cast<int*>(spy + TH);                                     // 64
-    float4* swrec = reinterpret_cast<float4*>(smem_raw + ((reinterpret_cast<size_t>(sint + 64) - reinterpret_cast<size_t>(smem_raw) + 15) & ~size_t(15)));   // NW x 2 x 5                                     // 32
+    float4* swrec = reinterpret_cast<float4*>(smem_raw + ((reinterpret_cast<size_t>(sint + 96) - reinterpret_cast<size_t>(smem_raw) + 15) & ~size_t(15)));   // NW x 2 x 5                                     // 32
     __shared__ __align__(8) unsigned long long mbar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -187,6 +231,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     const float blur_s_lo = P.blur_s * (1.0f - 1e-5f), blur_s_hi = P.blur_s * (1.0f + 1e-5f);
     uint32_t phase = 0;
     long long tprof = clock64();
+    RS_DECL;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -300,7 +345,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         const int slab = min(max((int)((zmin - zlo) * zscale), 0), R_NSLAB - 1);
                         fb = make_uint2((unsigned)bx_lo | ((unsigned)bx_hi << 16), (unsigned)by_lo | ((unsigned)by_hi << 10) | ((unsigned)slab << 20) | 0x80000000u);
                         for (int by = by_lo; by <= by_hi; ++by)
-                            for (int bx = bx_lo; bx <= bx_hi; ++bx) atomicAdd(&tcount[by * nbx + bx], 1);
+                            for (int bx = bx_lo; bx <= bx_hi; ++bx) atoms_add(&tcount[by * nbx + bx], 1);
                         const float den = MH_ADD(area, MH_KEPS);
                         const float ex12 = x2 - x1, ey12 = y2 - y1, ex20 = x0 - x2, ey20 = y0 - y2, ex01 = x1 - x0, ey01 = y1 - y0;
                         const float l01 = ex01 * ex01 + ey01 * ey01, l02 = ex20 * ex20 + ey20 * ey20, l12 = ex12 * ex12 + ey12 * ey12;
@@ -352,7 +397,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const int bx_lo = fb.x & 0xffff, bx_hi = fb.x >> 16, by_lo = fb.y & 1023, by_hi = (fb.y >> 10) & 1023;
                 for (int by = by_lo; by <= by_hi; ++by)
                     for (int bx = bx_lo; bx <= bx_hi; ++bx) {
-                        const int pos = atomicAdd(&tcur[by * nbx + bx], 1);
+                        const int pos = atoms_add(&tcur[by * nbx + bx], 1);
                         if (pos < P.bincap) binlist[pos] = (uint16_t)f;
                     }
             }
@@ -384,6 +429,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             const int off = tcount[bin], cnt = tcount[bin + 1] - off;
             if (cnt == 0) continue;
             const int ox = (tx0 + ttx) * TW, oy = (ty0 + tty) * TH;       // tile origin (pixels)
+            // hz[0..15] / hz[16..31]: per 8x8-pixel block, an upper bound of the depth words of the depth keys / of the 4th
+            // silhouette keys.  Keys only decrease, so a stale value stays a valid bound; warps refresh blocks as they go
+            unsigned* hz = reinterpret_cast<unsigned*>(sint + 48);
+            if (tid < 32) hz[tid] = 0u;
             __syncthreads();
             PROF(4);
             // this thread's pixel (the same in the tile set-up and in P3): what the loss needs there.  A pixel that needs no
@@ -401,6 +450,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 }
             }
             const bool need_d = pflags & 1u, need_s = pflags & 2u;
+            {
+                const int blk = ((tid >> 8) << 2) | ((tid & 31) >> 3);    // 8x8 block of this thread's pixel: rows tid >> 5, cols tid & 31
+                if (need_d) hz[blk] = 0xffffffffu;
+                if (need_s) hz[16 + blk] = 0xffffffffu;
+            }
             dkey[tid] = need_d ? KEY_EMPTY : 0ull;
             if (tid == 0) sint[40] = 0;
 #pragma unroll
@@ -418,7 +472,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             // faces are handed out dynamically (shared counter), two indices ahead of the one being processed
             int f = 0, fn1 = 0, fn2 = 0;
             int k0 = 0, k1 = 0, k2 = 0;
-            if (lane == 0) { k0 = atomicAdd(&sint[40], 1); k1 = atomicAdd(&sint[40], 1); }
+            if (lane == 0) { k0 = atoms_add(&sint[40], 2); k1 = k0 + 1; }
             k0 = __shfl_sync(0xffffffffu, k0, 0); k1 = __shfl_sync(0xffffffffu, k1, 0);
             if (k0 < cnt) f = binlist[off + k0];
             if (k1 < cnt) fn1 = binlist[off + k1];
@@ -426,7 +480,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             asm volatile("cp.async.commit_group;" ::: "memory");
             int slot = 0;
             for (; k0 < cnt; k0 = k1, k1 = k2, slot ^= 1) {
-                if (lane == 0) k2 = atomicAdd(&sint[40], 1);
+                if (lane == 0) k2 = atoms_add(&sint[40], 1);
                 k2 = __shfl_sync(0xffffffffu, k2, 0);
                 if (k2 < cnt) fn2 = binlist[off + k2];                    // face ids run two items ahead, records one item ahead
                 if (k1 < cnt && lane < 5) cp_async16(wrec + (slot ^ 1) * 5 + lane, frec + (size_t)fn1 * 5 + lane);
@@ -443,13 +497,31 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const int cc = __float_as_int(q4.y), rr = __float_as_int(q4.z);
                 const int ci = __float_as_int(q3.y), ri = __float_as_int(q3.z);
                 // the face's pixel rectangle clipped to the tile
-                const int c0 = max((cc & 0xffff) - ox, 0), c1 = min((cc >> 16) - ox, txmax);
-                const int r0 = max((rr & 0xffff) - oy, 0), r1 = min((rr >> 16) - oy, tymax);
-                const int w = c1 - c0 + 1, h = r1 - r0 + 1;
+                int c0 = max((cc & 0xffff) - ox, 0), c1 = min((cc >> 16) - ox, txmax);
+                int r0 = max((rr & 0xffff) - oy, 0), r1 = min((rr >> 16) - oy, tymax);
+                int w = c1 - c0 + 1, h = r1 - r0 + 1;
                 if (w <= 0 || h <= 0) continue;
                 // inner (silhouette) rectangle in tile coordinates; extent 0 when empty
                 const int jc0 = (ci & 0xffff) - ox, jr0 = (ri & 0xffff) - oy;
                 const unsigned jw = (unsigned)max((ci >> 16) - (ci & 0xffff) + 1, 0), jh = (unsigned)max((ri >> 16) - (ri & 0xffff) + 1, 0);
+                const unsigned zbits = __float_as_uint(q4.w);
+                if (P.vflags & 1) {
+                    // block-level prune: can the face still improve a key anywhere in the 8x8 blocks its rectangle touches?
+                    unsigned hd = 0u, hs = 0u;
+                    if (lane < 16) {
+                        const int bx = lane & 3, by = lane >> 2;
+                        if (bx >= (c0 >> 3) && bx <= (c1 >> 3) && by >= (r0 >> 3) && by <= (r1 >> 3)) { hd = hz[lane]; hs = hz[16 + lane]; }
+                    }
+                    hd = __reduce_max_sync(0xffffffffu, hd); hs = __reduce_max_sync(0xffffffffu, hs);
+                    if (zbits > hd) {
+                        if (zbits > hs) { RS_WARP(11); continue; }        // nothing to gain in this tile
+                        // depth cannot improve: only the inner rectangle matters
+                        c0 = max(c0, jc0); c1 = min(c1, jc0 + (int)jw - 1); r0 = max(r0, jr0); r1 = min(r1, jr0 + (int)jh - 1);
+                        w = c1 - c0 + 1; h = r1 - r0 + 1;
+                        if (w <= 0 || h <= 0) continue;
+                    }
+                }
+                if (lane == 0) { RS_ADD(0, 1); RS_ADD(1, w * h); }
                 const int npix = w * h;
                 const int magic = c_magic[w];
                 const bool dpos = inv_den > 0.f;
@@ -457,9 +529,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const float ex12 = MH_SUB(x2, x1), ey12 = MH_SUB(y2, y1);
                 const float ex20 = MH_SUB(x0, x2), ey20 = MH_SUB(y0, y2);
                 const float ex01 = MH_SUB(x1, x0), ey01 = MH_SUB(y1, y0);
-                const unsigned zbits = __float_as_uint(q4.w);
                 const unsigned* keyhi = reinterpret_cast<const unsigned*>(dkey) + 1;      // high (depth) words of dkey / skey
                 for (int o = lane; o < npix; o += 32) {
+                    RS_WARP(2);
                     const int row = (o * magic) >> 16;
                     const int col = o - row * w;
                     const int lx = c0 + col, ly = r0 + row;
@@ -470,6 +542,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const bool pd = zbits <= keyhi[2 * pix];
                     const bool ps = inner && (zbits <= keyhi[2 * (3 * R_THREADS + R_THREADS + pix)]);
                     if (!pd && !ps) continue;
+                    RS_ADD(3, 1); RS_WARP(4); if (inner) RS_ADD(10, 1);
                     const float px = spx[lx], py = spy[ly];
                     const float dx0 = MH_SUB(px, x0), dy0 = MH_SUB(py, y0);
                     const float dx1 = MH_SUB(px, x1), dy1 = MH_SUB(py, y1);
@@ -483,9 +556,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const float pz = __fdividef(c0w * z0 + c1w * z1 + c2w * z2, fmaxf(c0w + c1w + c2w, 1e-5f));
                     if (!(pz >= 0.f)) continue;
                     const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)fcur;
-                    const bool wd = pd && (key < dkey[pix]);
+                    const unsigned long long dk = dkey[pix];
+                    const bool wd = pd && (key < dk);
                     const bool ws = ps && (key < skey[3 * R_THREADS + pix]);
                     if (!wd && !ws) continue;
+                    RS_ADD(5, 1); RS_WARP(6);
                     const bool inside = (e0 != 0.f) && (e1 != 0.f) && (e2 != 0.f) && ((e0 > 0.f) == dpos) && ((e1 > 0.f) == dpos) && ((e2 > 0.f) == dpos);
                     bool vd = inside, vs = inside;
                     if (!inside) {
@@ -503,8 +578,26 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                             vd = fr.dist < P.blur_d; vs = fr.dist < P.blur_s;
                         }
                     }
-                    if (vd && wd) atomicMin(&dkey[pix], key);
-                    if (vs && ws) key_insert4(skey + pix, key);
+                    if (!inside) RS_ADD(9, 1);
+                    if (vd && wd) RS_ADD(7, 1);
+                    if (vs && ws) RS_ADD(8, 1);
+                    if (P.vflags & 2) {
+                        if (vd && wd) key_min(&dkey[pix], dk, key);
+                        if (vs && ws) key_insert4(skey + pix, key);
+                    } else {
+                        if (vd && wd) atomicMin(&dkey[pix], key);
+                        if (vs && ws) key_insert4_min(skey + pix, key);
+                    }
+                }
+                __syncwarp();
+                if (P.vflags & 1) {
+                    // refresh the bounds of the block under the centre of the rectangle just processed (2 pixels per lane)
+                    const int bx = (c0 + c1) >> 4, by = (r0 + r1) >> 4;
+                    const int p0 = ((by << 3) + (lane >> 3)) * TW + (bx << 3) + (lane & 7);
+                    unsigned md = max(keyhi[2 * p0], keyhi[2 * (p0 + 4 * TW)]);
+                    unsigned ms = max(keyhi[2 * (4 * R_THREADS + p0)], keyhi[2 * (4 * R_THREADS + p0 + 4 * TW)]);
+                    md = __reduce_max_sync(0xffffffffu, md); ms = __reduce_max_sync(0xffffffffu, ms);
+                    if (lane == 0) { hz[(by << 2) | bx] = md; hz[16 + ((by << 2) | bx)] = ms; }
                 }
             }
             __syncthreads();
@@ -552,7 +645,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 // d log(clamp(1 / clamp(z + .2, eps), eps)) / dz
                 const float gfac = (dz + 0.2f >= P.eps && zdisp >= P.eps) ? -1.0f / zc : 0.f;
                 if (gfac != 0.f) {
-                    const int wq = atomicAdd(&sint[6], 1);
+                    const int wq = atoms_add(&sint[6], 1);
                     if (wq < P.wcap) { wpix[wq] = yi * P.W + xi; wface[wq] = df; wz[wq] = gfac; }
                 }
             }
@@ -653,6 +746,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         __syncthreads();
         PROF(6);
     }
+    RS_FLUSH;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -676,6 +770,7 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->gsg, n * MH_LD3V * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(float));
     { const char* v = getenv("MH_RENDER_GRED"); rs->gred = v ? atoi(v) : 0; }     // development switch
+    { const char* v = getenv("MH_RENDER_FLAGS"); rs->vflags = v ? atoi(v) : 3; }
     rs->prof = nullptr;
     {
         int magic[TW + 1];
@@ -685,7 +780,7 @@ int mh_render_alloc(mh_ctx* c) {
     }
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
     rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) +
-               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (256 + TW + TH) * sizeof(float) + 64 * sizeof(int) + (size_t)(R_THREADS / 32) * 10 * sizeof(float4) + 128;
+               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (256 + TW + TH) * sizeof(float) + 96 * sizeof(int) + (size_t)(R_THREADS / 32) * 10 * sizeof(float4) + 128;
     e = cudaFuncSetAttribute(k_render<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
@@ -712,7 +807,7 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.zmin_lin = c->params + c->off[MH_P_ZMIN_LIN]; P.zmax_lin = c->params + c->off[MH_P_ZMAX_LIN];
     P.pfout = c->pfout; P.devflags = c->devflags;
     P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.frec = c->rs->frec; P.fbin = c->rs->fbin; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
-    P.counter = c->rs->counter; P.gsg = c->rs->gsg;
+    P.counter = c->rs->counter; P.gsg = c->rs->gsg; P.vflags = c->rs->vflags;
     P.maxbins = c->rs->maxbins;
     if (c->rs->bincap_use) P.bincap = c->rs->bincap_use;
     if (c->rs->wcap_use) P.wcap = c->rs->wcap_use;
@@ -761,16 +856,16 @@ int mh_render_debug(mh_ctx* c, int t, int n, float* zbuf_dev, float* alpha_dev, 
 
 // Development aid: per-phase cycle counters of the render kernel, summed over the CTAs (8 slots:
 // load+ndc | binning | tile staging | pair scatter | per-pixel + silhouette backward | sums + depth backward | chain rule | -).
-extern "C" int mh_render_profile(mh_ctx* c, int32_t on, long long* out8_host) {
+extern "C" int mh_render_profile(mh_ctx* c, int32_t on, long long* out8_host /* 32 values */) {
     if (!c || !c->rs) return MH_E_ARG;
     cudaSetDevice(c->d.device);
     MhRenderScratch* rs = c->rs;
-    const size_t n = (size_t)rs->nctas * 8;
+    const size_t n = (size_t)rs->nctas * MH_NPROF;
     if (out8_host && rs->prof) {
         std::vector<long long> h(n);
         MH_CUDA(c, cudaDeviceSynchronize());
         MH_CUDA(c, cudaMemcpy(h.data(), rs->prof, n * sizeof(long long), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < 8; ++k) { out8_host[k] = 0; for (int b = 0; b < rs->nctas; ++b) out8_host[k] += h[(size_t)b * 8 + k]; }
+        for (int k = 0; k < MH_NPROF; ++k) { out8_host[k] = 0; for (int b = 0; b < rs->nctas; ++b) out8_host[k] += h[(size_t)b * MH_NPROF + k]; }
     }
     if (on && !rs->prof) MH_CUDA(c, cudaMalloc((void**)&rs->prof, n * sizeof(long long)));
     if (on) MH_CUDA(c, cudaMemset(rs->prof, 0, n * sizeof(long long)));
