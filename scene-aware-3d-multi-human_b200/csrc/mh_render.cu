@@ -35,12 +35,12 @@
 
 struct MhRenderScratch {
     uint16_t* binlist; int bincap;
-    float4* frec; uint2* fbin;
+    uint2* fbin;
     int* wpix; int* wface; float* wz; int wcap;
     int nctas;
     size_t smem;
     int* counter;
-    float* gsg; int gred; int vflags;
+    float* gsg; int vflags;
     long long* prof;
     int maxbins;               // tile bins per body before the binning granularity is coarsened (<= R_MAXBINS)
     int bincap_use, wcap_use;  // capacities handed to the kernel (<= the allocated ones; testing aid)
@@ -54,10 +54,10 @@ struct RenderParams {
     const uint8_t* pose2d_valid; const uint8_t* mask_valid;
     const float* zmin_lin; const float* zmax_lin;
     float* pfout; int* devflags;
-    float* gsg;                   // GRED: per-CTA NDC-gradient rows (MH_LD3V floats each)
+    float* gsg;                   // per-CTA NDC-gradient rows (MH_LD3V floats each), zero between bodies
     int vflags;                   // development switches (MH_RENDER_FLAGS): 1 block-level prune, 2 CAS-first key updates
     uint16_t* binlist; int bincap;
-    float4* frec; uint2* fbin;    // per-CTA scratch: 5 float4 per face (set-up record), packed bin range + depth slab per face
+    uint2* fbin;                  // per-CTA scratch: packed bin range + depth slab per face
     int* wpix; int* wface; float* wz; int wcap;
     int* counter;
     int T, N, H, W;
@@ -85,10 +85,6 @@ struct FaceRec {
 __constant__ int c_magic[TW + 1];      // ceil(65536 / w): row = (o * magic) >> 16 for o < 512
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
 
 __device__ __forceinline__ float wsum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -120,34 +116,12 @@ __device__ __forceinline__ int atoms_add(int* p, int v) {
     return old;
 }
 
-// 64-bit shared-memory minimum is a compare-and-swap loop anyway: start it from the value already read (key < cur)
-__device__ __forceinline__ void key_min(unsigned long long* p, unsigned long long cur, unsigned long long key) {
-    for (;;) {
-        const unsigned long long old = atomicCAS(p, cur, key);
-        if (old == cur || old <= key) return;
-        cur = old;
-    }
-}
-
-__device__ __forceinline__ void key_insert4_min(unsigned long long* slot /*stride R_THREADS*/, unsigned long long x) {
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const unsigned long long old = atomicMin(slot + s * R_THREADS, x);
-        x = old > x ? old : x;
-        if (x == KEY_EMPTY) break;
-    }
-}
-
 __device__ __forceinline__ void key_insert4(unsigned long long* slot /*stride R_THREADS*/, unsigned long long x) {
     // concurrent sorted insertion: every slot keeps the minimum of what reaches it and passes the rest on
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        unsigned long long cur = slot[s * R_THREADS];
-        while (x < cur) {
-            const unsigned long long old = atomicCAS(slot + s * R_THREADS, cur, x);
-            if (old == cur) { x = cur; break; }                          // took the slot: the displaced key moves on
-            cur = old;
-        }
+        const unsigned long long old = atomicMin(slot + s * R_THREADS, x);
+        x = old > x ? old : x;
         if (x == KEY_EMPTY) break;
     }
 }
@@ -194,35 +168,74 @@ __device__ __forceinline__ void frag_values(const float* sv, const int32_t* __re
     *sd = inside ? -d : d;
 }
 
-// gradient scatter: shared-memory float atomics are compare-and-swap loops (ATOMS.CAST.SPIN) that retry when the pixels of
-// a warp hit the same vertex; GRED = 1 sends them as fire-and-forget reductions (RED.E.ADD.F32) to a per-CTA row that stays in L2
-template <int GRED>
+// gradient scatter: shared-memory float atomics are compare-and-swap loops (ATOMS.CAST.SPIN) that retry when the pixels of a
+// warp hit the same vertex; the gradients go instead as fire-and-forget reductions (RED.E.ADD.F32) to a per-CTA row that stays in L2
 __device__ __forceinline__ void grad_add(float* p, float v) {
-    if (GRED) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-    else atomicAdd(p, v);
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-template <int MODE, int GRED>      // MODE 0: losses + gradients ; 1: dense zbuf / alpha planes of one body
+#define R_DESC 1024               // (face, tile) descriptors staged per chunk (5 float4 each)
+
+// Descriptor of one (face, tile) item -- everything P2 needs, computed ONCE by one thread (the tile's faces are spread over
+// the 1024 threads) instead of redundantly by the 32 lanes of the warp that rasterises the face:
+//   d0 = x0 y0 x1 y1 | d1 = x2 y2 z0 z1 | d2 = z2 1/den 1/|e01|^2 1/|e02|^2 | d3 = 1/|e12|^2 rect inner zbits | d4 = face magic - -
+// rect  = c0 | r0 << 5 | w << 10 | h << 16 : the face's pixel rectangle inside the tile, EXACT for the oracle's bbox test (bbox
+//         inflated by sqrt(blur) of the depth raster), so the pair loop needs no per-pixel bbox test; w = 0: nothing in this tile
+// inner = same packing: the only pixels where the face can be a SILHOUETTE fragment (bbox inflated by the silhouette radius x 1.001
+//         and 0.01 px: conservative, the exact distance test follows per pixel)
+// zbits = bits of a lower bound of every fragment depth of the face (its nearest vertex)
+__device__ __forceinline__ void make_desc(const RenderParams& P, const float* sv, int f, int ox, int oy, int txmax, int tymax, float4* d) {
+    const int i0 = P.faces[3 * f], i1 = P.faces[3 * f + 1], i2 = P.faces[3 * f + 2];
+    const float x0 = sv[3 * i0], y0 = sv[3 * i0 + 1], z0 = sv[3 * i0 + 2];
+    const float x1 = sv[3 * i1], y1 = sv[3 * i1 + 1], z1 = sv[3 * i1 + 2];
+    const float x2 = sv[3 * i2], y2 = sv[3 * i2 + 1], z2 = sv[3 * i2 + 2];
+    const float bxmin = MH_SUB(fminf(fminf(x0, x1), x2), P.r_d), bxmax = MH_ADD(fmaxf(fmaxf(x0, x1), x2), P.r_d);
+    const float bymin = MH_SUB(fminf(fminf(y0, y1), y2), P.r_d), bymax = MH_ADD(fmaxf(fmaxf(y0, y1), y2), P.r_d);
+    // pixel rectangle of the inflated bbox (conservative by 0.01 px), clipped to the tile, then made exact
+    int c0 = max((int)fmaxf(ceilf(pix_of(bxmax, P.W, P.rx) - 0.01f), 0.f), ox), c1 = min((int)fminf(floorf(pix_of(bxmin, P.W, P.rx) + 0.01f), (float)(P.W - 1)), ox + txmax);
+    int r0 = max((int)fmaxf(ceilf(pix_of(bymax, P.H, P.ry) - 0.01f), 0.f), oy), r1 = min((int)fminf(floorf(pix_of(bymin, P.H, P.ry) + 0.01f), (float)(P.H - 1)), oy + tymax);
+    while (c0 <= c1 && (P.pix_x[c0] > bxmax || P.pix_x[c0] < bxmin)) ++c0;
+    while (c1 >= c0 && (P.pix_x[c1] > bxmax || P.pix_x[c1] < bxmin)) --c1;
+    while (r0 <= r1 && (P.pix_y[r0] > bymax || P.pix_y[r0] < bymin)) ++r0;
+    while (r1 >= r0 && (P.pix_y[r1] > bymax || P.pix_y[r1] < bymin)) --r1;
+    if (c0 > c1 || r0 > r1) { d[3] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+    int ic0 = max((int)fmaxf(ceilf(pix_of(bxmax - P.r_d + P.r_s, P.W, P.rx) - 0.01f), 0.f), c0), ic1 = min((int)fminf(floorf(pix_of(bxmin + P.r_d - P.r_s, P.W, P.rx) + 0.01f), (float)(P.W - 1)), c1);
+    int ir0 = max((int)fmaxf(ceilf(pix_of(bymax - P.r_d + P.r_s, P.H, P.ry) - 0.01f), 0.f), r0), ir1 = min((int)fminf(floorf(pix_of(bymin + P.r_d - P.r_s, P.H, P.ry) + 0.01f), (float)(P.H - 1)), r1);
+    int inner = 0;
+    if (ic0 <= ic1 && ir0 <= ir1) inner = (ic0 - ox) | ((ir0 - oy) << 5) | ((ic1 - ic0 + 1) << 10) | ((ir1 - ir0 + 1) << 16);
+    const int w = c1 - c0 + 1;
+    const int rect = (c0 - ox) | ((r0 - oy) << 5) | (w << 10) | ((r1 - r0 + 1) << 16);
+    const float den = MH_ADD(mh_edge(x2, y2, x0, y0, x1, y1), MH_KEPS);
+    const float ex12 = x2 - x1, ey12 = y2 - y1, ex20 = x0 - x2, ey20 = y0 - y2, ex01 = x1 - x0, ey01 = y1 - y0;
+    const float l01 = ex01 * ex01 + ey01 * ey01, l02 = ex20 * ex20 + ey20 * ey20, l12 = ex12 * ex12 + ey12 * ey12;
+    const float zmin = fminf(z0, fminf(z1, z2));
+    d[0] = make_float4(x0, y0, x1, y1);
+    d[1] = make_float4(x2, y2, z0, z1);
+    d[2] = make_float4(z2, __frcp_rn(den), l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), l02 <= MH_KEPS ? 0.f : __frcp_rn(l02));
+    d[3] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), __int_as_float(rect), __int_as_float(inner), __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))));
+    d[4] = make_float4(__int_as_float(f), __int_as_float((65536 + w - 1) / w), 0.f, 0.f);
+}
+
+template <int MODE>      // MODE 0: losses + gradients ; 1: dense zbuf / alpha planes of one body
 __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sv = reinterpret_cast<float*>(smem_raw);                                   // MH_LD3V  NDC vertices
-    float* sg = GRED ? P.gsg + (size_t)blockIdx.x * MH_LD3V : sv + MH_LD3V;           // MH_LD3V  NDC gradients (GRED: global, zero on entry)
-    unsigned long long* dkey = reinterpret_cast<unsigned long long*>(sv + 2 * MH_LD3V);   // R_THREADS     nearest depth fragment
+    float* sg = P.gsg + (size_t)blockIdx.x * MH_LD3V;                                 // MH_LD3V  NDC gradients: global (L2), zero on entry
+    unsigned long long* dkey = reinterpret_cast<unsigned long long*>(sv + MH_LD3V);   // R_THREADS     nearest depth fragment
     unsigned long long* skey = dkey + R_THREADS;                                      // 4 x R_THREADS nearest silhouette fragments
-    int* tcount = reinterpret_cast<int*>(skey + 4 * R_THREADS);                            // R_MAXBINS + 1 (exclusive offsets after the scan)
+    int* tcount = reinterpret_cast<int*>(skey + 4 * R_THREADS);                       // R_MAXBINS + 1 (exclusive offsets after the scan)
     int* tcur = tcount + R_MAXBINS + 1;                                               // R_MAXBINS
-    float* sred = reinterpret_cast<float*>(tcur + R_MAXBINS + 3);                     // 128
+    float* sred = reinterpret_cast<float*>(tcur + R_MAXBINS + 3);                     // 256
     float* spx = sred + 256;                                                          // TW
     float* spy = spx + TW;                                                            // TH
-    int* sint = reinterpret_cast<int*>(spy + TH);                                     // 64
-    float4* swrec = reinterpret_cast<float4*>(smem_raw + ((reinterpret_cast<size_t>(sint + 96) - reinterpret_cast<size_t>(smem_raw) + 15) & ~size_t(15)));   // NW x 2 x 5                                     // 32
+    int* sint = reinterpret_cast<int*>(spy + TH);                                     // 96
+    float4* sdesc = reinterpret_cast<float4*>(smem_raw + ((reinterpret_cast<size_t>(sint + 96) - reinterpret_cast<size_t>(smem_raw) + 15) & ~size_t(15)));   // R_DESC x 5
     __shared__ __align__(8) unsigned long long mbar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = R_THREADS / 32;
     const int TN = P.T * P.N;
     uint16_t* binlist = P.binlist + (size_t)blockIdx.x * P.bincap;
-    float4* frec = P.frec + (size_t)blockIdx.x * MH_F * 5;
     uint2* fbin = P.fbin + (size_t)blockIdx.x * MH_F;
     int* wpix = P.wpix + (size_t)blockIdx.x * P.wcap;
     int* wface = P.wface + (size_t)blockIdx.x * P.wcap;
@@ -262,7 +275,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                          "l"(P.verts + b * MH_LD3V), "r"(bytes), "r"(smem_u32(&mbar))
                          : "memory");
         }
-        if (!GRED) for (int e = tid; e < MH_LD3V; e += R_THREADS) sg[e] = 0.f;
         {
             uint32_t done = 0;
             while (!done) {
@@ -314,7 +326,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         for (int e = tid; e <= nbins; e += R_THREADS) tcount[e] = 0;
         __syncthreads();
         const float zlo = sred[6 * NW], zscale = sred[6 * NW + 1];
-        // pass 0: per-face set-up record (once per body), bin range + depth slab, per-bin counts
+        // pass 0: bin range (conservative by 0.01 px) + depth slab per face, per-bin counts
         for (int f = tid; f < MH_F; f += R_THREADS) {
             const int i0 = P.faces[3 * f], i1 = P.faces[3 * f + 1], i2 = P.faces[3 * f + 2];
             const float x0 = sv[3 * i0], y0 = sv[3 * i0 + 1], z0 = sv[3 * i0 + 2];
@@ -326,19 +338,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             if ((zmax >= 0.f) && !((area <= MH_KEPS) && (area >= -MH_KEPS)) && nbins > 0) {
                 const float bxmin = MH_SUB(fminf(fminf(x0, x1), x2), P.r_d), bxmax = MH_ADD(fmaxf(fmaxf(x0, x1), x2), P.r_d);
                 const float bymin = MH_SUB(fminf(fminf(y0, y1), y2), P.r_d), bymax = MH_ADD(fmaxf(fmaxf(y0, y1), y2), P.r_d);
-                // pixel rectangle of the inflated bbox (conservative by 0.01 px; the exact test is per pixel)
                 const float pc0 = ceilf(pix_of(bxmax, P.W, P.rx) - 0.01f), pc1 = floorf(pix_of(bxmin, P.W, P.rx) + 0.01f);
                 const float pr0 = ceilf(pix_of(bymax, P.H, P.ry) - 0.01f), pr1 = floorf(pix_of(bymin, P.H, P.ry) + 0.01f);
                 if ((pc1 >= 0.f) && (pr1 >= 0.f) && (pc0 <= (float)(P.W - 1)) && (pr0 <= (float)(P.H - 1)) && (pc0 <= pc1) && (pr0 <= pr1)) {
-                    int c0 = (int)fmaxf(pc0, 0.f), c1 = (int)fminf(pc1, (float)(P.W - 1));
-                    int r0 = (int)fmaxf(pr0, 0.f), r1 = (int)fminf(pr1, (float)(P.H - 1));
-                    // make the rectangle EXACT for the oracle's bbox test (the 0.01 px slack can include one column / row too many),
-                    // so that the pair loop needs no per-pixel bbox test
-                    while (c0 <= c1 && (P.pix_x[c0] > bxmax || P.pix_x[c0] < bxmin)) ++c0;
-                    while (c1 >= c0 && (P.pix_x[c1] > bxmax || P.pix_x[c1] < bxmin)) --c1;
-                    while (r0 <= r1 && (P.pix_y[r0] > bymax || P.pix_y[r0] < bymin)) ++r0;
-                    while (r1 >= r0 && (P.pix_y[r1] > bymax || P.pix_y[r1] < bymin)) --r1;
-                    if (c0 > c1 || r0 > r1) { fbin[f] = fb; continue; }
+                    const int c0 = (int)fmaxf(pc0, 0.f), c1 = (int)fminf(pc1, (float)(P.W - 1));
+                    const int r0 = (int)fmaxf(pr0, 0.f), r1 = (int)fminf(pr1, (float)(P.H - 1));
                     const int bx_lo = max((c0 / TW - tx0) >> ks, 0), bx_hi = min((c1 / TW - tx0) >> ks, nbx - 1);
                     const int by_lo = max((r0 / TH - ty0) >> ks, 0), by_hi = min((r1 / TH - ty0) >> ks, nby - 1);
                     if (bx_lo <= bx_hi && by_lo <= by_hi) {
@@ -346,24 +350,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         fb = make_uint2((unsigned)bx_lo | ((unsigned)bx_hi << 16), (unsigned)by_lo | ((unsigned)by_hi << 10) | ((unsigned)slab << 20) | 0x80000000u);
                         for (int by = by_lo; by <= by_hi; ++by)
                             for (int bx = bx_lo; bx <= bx_hi; ++bx) atoms_add(&tcount[by * nbx + bx], 1);
-                        const float den = MH_ADD(area, MH_KEPS);
-                        const float ex12 = x2 - x1, ey12 = y2 - y1, ex20 = x0 - x2, ey20 = y0 - y2, ex01 = x1 - x0, ey01 = y1 - y0;
-                        const float l01 = ex01 * ex01 + ey01 * ey01, l02 = ex20 * ex20 + ey20 * ey20, l12 = ex12 * ex12 + ey12 * ey12;
-                        float4* rec = frec + (size_t)f * 5;
-                        rec[0] = make_float4(x0, y0, x1, y1);
-                        rec[1] = make_float4(x2, y2, z0, z1);
-                        rec[2] = make_float4(z2, __frcp_rn(den), l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), l02 <= MH_KEPS ? 0.f : __frcp_rn(l02));
-                        // inner rectangle: the only pixels where the face can be a SILHOUETTE fragment (bbox inflated by the
-                        // silhouette radius x 1.001, 0.01 px slack: conservative, the exact distance test follows per pixel)
-                        int ic0 = (int)fmaxf(ceilf(pix_of(bxmax - P.r_d + P.r_s, P.W, P.rx) - 0.01f), (float)c0);
-                        int ic1 = (int)fminf(floorf(pix_of(bxmin + P.r_d - P.r_s, P.W, P.rx) + 0.01f), (float)c1);
-                        int ir0 = (int)fmaxf(ceilf(pix_of(bymax - P.r_d + P.r_s, P.H, P.ry) - 0.01f), (float)r0);
-                        int ir1 = (int)fminf(floorf(pix_of(bymin + P.r_d - P.r_s, P.H, P.ry) + 0.01f), (float)r1);
-                        if (ic0 > ic1 || ir0 > ir1) { ic0 = 1; ic1 = 0; ir0 = 1; ir1 = 0; }
-                        rec[3] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), __int_as_float(ic0 | (ic1 << 16)), __int_as_float(ir0 | (ir1 << 16)), 0.f);
-                        // no fragment of a face can be nearer than its nearest vertex
-                        rec[4] = make_float4(0.f, __int_as_float(c0 | (c1 << 16)), __int_as_float(r0 | (r1 << 16)),
-                                             __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))));
                     }
                 }
             }
@@ -463,67 +449,58 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             if (tid < TW) spx[tid] = (ox + tid < P.W) ? P.pix_x[ox + tid] : 0.f;
             if (tid >= 64 && tid < 64 + TH) spy[tid - 64] = (oy + tid - 64 < P.H) ? P.pix_y[oy + tid - 64] : 0.f;
             const int txmax = min(TW, P.W - ox) - 1, tymax = min(TH, P.H - oy) - 1;     // last valid local column / row
-            // ---- P2: scatter -- each warp takes one face of the tile at a time (set-up evaluated redundantly by the lanes, no
-            //      staging barrier) and spreads the face's pixel rectangle over its lanes, 32 pixels per pass ----
+            // ---- descriptors of the first chunk of the tile's faces: one thread per face ----
+            if (tid < cnt) make_desc(P, sv, binlist[off + tid], ox, oy, txmax, tymax, sdesc + tid * 5);
             const int tile_needed = __syncthreads_or(need_d || need_s);
             PROF(2);
             if (!tile_needed) continue;                                   // uniform: nothing the loss reads in this tile
-            float4* wrec = swrec + warp * 10;
-            // faces are handed out dynamically (shared counter), two indices ahead of the one being processed
-            int f = 0, fn1 = 0, fn2 = 0;
-            int k0 = 0, k1 = 0, k2 = 0;
-            if (lane == 0) { k0 = atoms_add(&sint[40], 2); k1 = k0 + 1; }
-            k0 = __shfl_sync(0xffffffffu, k0, 0); k1 = __shfl_sync(0xffffffffu, k1, 0);
-            if (k0 < cnt) f = binlist[off + k0];
-            if (k1 < cnt) fn1 = binlist[off + k1];
-            if (k0 < cnt && lane < 5) cp_async16(wrec + lane, frec + (size_t)f * 5 + lane);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            int slot = 0;
-            for (; k0 < cnt; k0 = k1, k1 = k2, slot ^= 1) {
-                if (lane == 0) k2 = atoms_add(&sint[40], 1);
-                k2 = __shfl_sync(0xffffffffu, k2, 0);
-                if (k2 < cnt) fn2 = binlist[off + k2];                    // face ids run two items ahead, records one item ahead
-                if (k1 < cnt && lane < 5) cp_async16(wrec + (slot ^ 1) * 5 + lane, frec + (size_t)fn1 * 5 + lane);
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-                __syncwarp();
-                const float4* rec = wrec + slot * 5;
-                const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4];
-                __syncwarp();
-                const int fcur = f;
-                f = fn1; fn1 = fn2;
+            // ---- P2: scatter -- each warp takes one face of the chunk at a time (dynamic hand-out) and spreads the face's pixel
+            //      rectangle over its lanes, 32 pixels per pass ----
+            for (int base = 0; base < cnt; base += R_DESC) {
+              if (base > 0) {
+                __syncthreads();                                          // everybody is done with the previous chunk
+                if (tid == 0) sint[40] = 0;
+                if (base + tid < cnt) make_desc(P, sv, binlist[off + base + tid], ox, oy, txmax, tymax, sdesc + tid * 5);
+                __syncthreads();
+              }
+              const int ccnt = min(cnt - base, R_DESC);
+              int kn = 0;
+              if (lane == 0) kn = atoms_add(&sint[40], 1);
+              kn = __shfl_sync(0xffffffffu, kn, 0);
+              while (kn < ccnt) {
+                const float4* dsc = sdesc + kn * 5;
+                if (lane == 0) kn = atoms_add(&sint[40], 1);              // the next item: the atomic's latency hides behind this one
+                const float4 q0 = dsc[0], q1 = dsc[1], q2 = dsc[2], q3 = dsc[3], q4 = dsc[4];
+                kn = __shfl_sync(0xffffffffu, kn, 0);
+                const int rect = __float_as_int(q3.y);
+                int w = (rect >> 10) & 63;
+                if (w == 0) continue;                                     // binned conservatively: nothing of the face in this tile
+                int c0 = rect & 31, r0 = (rect >> 5) & 31, h = (rect >> 16) & 63;
+                const int inner = __float_as_int(q3.z);
+                const int jc0 = inner & 31, jr0 = (inner >> 5) & 31;
+                const unsigned jw = (inner >> 10) & 63, jh = (inner >> 16) & 63;
                 const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y, z0 = q1.z, z1 = q1.w, z2 = q2.x;
                 const float inv_den = q2.y, il01 = q2.z, il02 = q2.w, il12 = q3.x;
-                const int cc = __float_as_int(q4.y), rr = __float_as_int(q4.z);
-                const int ci = __float_as_int(q3.y), ri = __float_as_int(q3.z);
-                // the face's pixel rectangle clipped to the tile
-                int c0 = max((cc & 0xffff) - ox, 0), c1 = min((cc >> 16) - ox, txmax);
-                int r0 = max((rr & 0xffff) - oy, 0), r1 = min((rr >> 16) - oy, tymax);
-                int w = c1 - c0 + 1, h = r1 - r0 + 1;
-                if (w <= 0 || h <= 0) continue;
-                // inner (silhouette) rectangle in tile coordinates; extent 0 when empty
-                const int jc0 = (ci & 0xffff) - ox, jr0 = (ri & 0xffff) - oy;
-                const unsigned jw = (unsigned)max((ci >> 16) - (ci & 0xffff) + 1, 0), jh = (unsigned)max((ri >> 16) - (ri & 0xffff) + 1, 0);
-                const unsigned zbits = __float_as_uint(q4.w);
+                const unsigned zbits = __float_as_uint(q3.w);
+                const int fcur = __float_as_int(q4.x);
+                int magic = __float_as_int(q4.y);
                 if (P.vflags & 1) {
                     // block-level prune: can the face still improve a key anywhere in the 8x8 blocks its rectangle touches?
                     unsigned hd = 0u, hs = 0u;
                     if (lane < 16) {
                         const int bx = lane & 3, by = lane >> 2;
-                        if (bx >= (c0 >> 3) && bx <= (c1 >> 3) && by >= (r0 >> 3) && by <= (r1 >> 3)) { hd = hz[lane]; hs = hz[16 + lane]; }
+                        if (bx >= (c0 >> 3) && bx <= ((c0 + w - 1) >> 3) && by >= (r0 >> 3) && by <= ((r0 + h - 1) >> 3)) { hd = hz[lane]; hs = hz[16 + lane]; }
                     }
                     hd = __reduce_max_sync(0xffffffffu, hd); hs = __reduce_max_sync(0xffffffffu, hs);
                     if (zbits > hd) {
-                        if (zbits > hs) { RS_WARP(11); continue; }        // nothing to gain in this tile
+                        if (zbits > hs || jw == 0u) { RS_WARP(11); continue; }   // nothing to gain in this tile
                         // depth cannot improve: only the inner rectangle matters
-                        c0 = max(c0, jc0); c1 = min(c1, jc0 + (int)jw - 1); r0 = max(r0, jr0); r1 = min(r1, jr0 + (int)jh - 1);
-                        w = c1 - c0 + 1; h = r1 - r0 + 1;
-                        if (w <= 0 || h <= 0) continue;
+                        c0 = jc0; r0 = jr0; w = (int)jw; h = (int)jh;
+                        magic = c_magic[w];
                     }
                 }
                 if (lane == 0) { RS_ADD(0, 1); RS_ADD(1, w * h); }
                 const int npix = w * h;
-                const int magic = c_magic[w];
                 const bool dpos = inv_den > 0.f;
                 // edge vectors exactly as the oracle rounds them
                 const float ex12 = MH_SUB(x2, x1), ey12 = MH_SUB(y2, y1);
@@ -556,8 +533,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const float pz = __fdividef(c0w * z0 + c1w * z1 + c2w * z2, fmaxf(c0w + c1w + c2w, 1e-5f));
                     if (!(pz >= 0.f)) continue;
                     const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)fcur;
-                    const unsigned long long dk = dkey[pix];
-                    const bool wd = pd && (key < dk);
+                    const bool wd = pd && (key < dkey[pix]);
                     const bool ws = ps && (key < skey[3 * R_THREADS + pix]);
                     if (!wd && !ws) continue;
                     RS_ADD(5, 1); RS_WARP(6);
@@ -581,24 +557,20 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     if (!inside) RS_ADD(9, 1);
                     if (vd && wd) RS_ADD(7, 1);
                     if (vs && ws) RS_ADD(8, 1);
-                    if (P.vflags & 2) {
-                        if (vd && wd) key_min(&dkey[pix], dk, key);
-                        if (vs && ws) key_insert4(skey + pix, key);
-                    } else {
-                        if (vd && wd) atomicMin(&dkey[pix], key);
-                        if (vs && ws) key_insert4_min(skey + pix, key);
-                    }
+                    if (vd && wd) atomicMin(&dkey[pix], key);
+                    if (vs && ws) key_insert4(skey + pix, key);
                 }
                 __syncwarp();
                 if (P.vflags & 1) {
                     // refresh the bounds of the block under the centre of the rectangle just processed (2 pixels per lane)
-                    const int bx = (c0 + c1) >> 4, by = (r0 + r1) >> 4;
+                    const int bx = (2 * c0 + w - 1) >> 4, by = (2 * r0 + h - 1) >> 4;
                     const int p0 = ((by << 3) + (lane >> 3)) * TW + (bx << 3) + (lane & 7);
                     unsigned md = max(keyhi[2 * p0], keyhi[2 * (p0 + 4 * TW)]);
                     unsigned ms = max(keyhi[2 * (4 * R_THREADS + p0)], keyhi[2 * (4 * R_THREADS + p0 + 4 * TW)]);
                     md = __reduce_max_sync(0xffffffffu, md); ms = __reduce_max_sync(0xffffffffu, ms);
                     if (lane == 0) { hz[(by << 2) | bx] = md; hz[16 + ((by << 2) | bx)] = ms; }
                 }
+              }
             }
             __syncthreads();
             PROF(3);
@@ -673,8 +645,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         mh_face_bwd(fc, pxn, pyn, 0.f, gdist, g);
 #pragma unroll
                         for (int e = 0; e < 3; ++e) {
-                            if (g[3 * e] != 0.f) grad_add<GRED>(&sg[3 * iv[e]], g[3 * e]);
-                            if (g[3 * e + 1] != 0.f) grad_add<GRED>(&sg[3 * iv[e] + 1], g[3 * e + 1]);
+                            if (g[3 * e] != 0.f) grad_add(&sg[3 * iv[e]], g[3 * e]);
+                            if (g[3 * e + 1] != 0.f) grad_add(&sg[3 * iv[e] + 1], g[3 * e + 1]);
                         }
                     }
                 }
@@ -718,23 +690,22 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 mh_face_bwd(fc, P.pix_x[xi], P.pix_y[yi], kappa * wz[e], 0.f, g);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) if (g[k] != 0.f) grad_add<GRED>(&sg[3 * iv[k / 3] + (k % 3)], g[k]);
+                for (int k = 0; k < 9; ++k) if (g[k] != 0.f) grad_add(&sg[3 * iv[k / 3] + (k % 3)], g[k]);
             }
         }
         __syncthreads();
         PROF(5);
         // ---- P5: NDC -> camera-space chain rule, accumulate into dL/dV (this CTA owns the row) ----
-        if (GRED) { __threadfence(); __syncthreads(); }
+        __threadfence();
+        __syncthreads();
         const float* vw = P.verts + b * MH_LD3V;
         float* dv = P.dverts + b * MH_LD3V;
         for (int v = tid; v < MH_V; v += R_THREADS) {
-            float gx, gy, gz;
-            if (GRED) {                                                   // read at L2 (where the reductions landed), clear for the next body
-                gx = __ldcg(&sg[3 * v]); gy = __ldcg(&sg[3 * v + 1]); gz = __ldcg(&sg[3 * v + 2]);
-                if (gx != 0.f) sg[3 * v] = 0.f;
-                if (gy != 0.f) sg[3 * v + 1] = 0.f;
-                if (gz != 0.f) sg[3 * v + 2] = 0.f;
-            } else { gx = sg[3 * v]; gy = sg[3 * v + 1]; gz = sg[3 * v + 2]; }
+            // read at L2 (where the reductions landed), clear for the next body
+            const float gx = __ldcg(&sg[3 * v]), gy = __ldcg(&sg[3 * v + 1]), gz = __ldcg(&sg[3 * v + 2]);
+            if (gx != 0.f) sg[3 * v] = 0.f;
+            if (gy != 0.f) sg[3 * v + 1] = 0.f;
+            if (gz != 0.f) sg[3 * v + 2] = 0.f;
             if (gx == 0.f && gy == 0.f && gz == 0.f) continue;
             const float X = vw[3 * v], Y = vw[3 * v + 1], Z = vw[3 * v + 2];
             const float iz = 1.0f / Z;
@@ -761,7 +732,6 @@ int mh_render_alloc(mh_ctx* c) {
     rs->wcap = c->d.H * c->d.W;
     const size_t n = (size_t)rs->nctas;
     cudaError_t e = cudaMalloc((void**)&rs->binlist, n * rs->bincap * sizeof(uint16_t));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->frec, n * MH_F * 5 * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->fbin, n * MH_F * sizeof(uint2));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wpix, n * rs->wcap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wface, n * rs->wcap * sizeof(int));
@@ -769,7 +739,6 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->gsg, n * MH_LD3V * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(float));
-    { const char* v = getenv("MH_RENDER_GRED"); rs->gred = v ? atoi(v) : 0; }     // development switch
     { const char* v = getenv("MH_RENDER_FLAGS"); rs->vflags = v ? atoi(v) : 3; }
     rs->prof = nullptr;
     {
@@ -779,11 +748,10 @@ int mh_render_alloc(mh_ctx* c) {
         if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_magic, magic, sizeof(magic));
     }
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
-    rs->smem = (size_t)2 * MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) +
-               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (256 + TW + TH) * sizeof(float) + 96 * sizeof(int) + (size_t)(R_THREADS / 32) * 10 * sizeof(float4) + 128;
-    e = cudaFuncSetAttribute(k_render<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
+    rs->smem = (size_t)MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) +
+               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (256 + TW + TH) * sizeof(float) + 96 * sizeof(int) + (size_t)R_DESC * 5 * sizeof(float4) + 128;
+    e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render: %zu bytes of shared memory: %s", rs->smem, cudaGetErrorString(e));
     return MH_OK;
 }
@@ -791,7 +759,7 @@ int mh_render_alloc(mh_ctx* c) {
 void mh_render_free(mh_ctx* c) {
     if (!c->rs) return;
     if (c->rs->prof) cudaFree(c->rs->prof);
-    cudaFree(c->rs->frec); cudaFree(c->rs->fbin); cudaFree(c->rs->gsg);
+    cudaFree(c->rs->fbin); cudaFree(c->rs->gsg);
     cudaFree(c->rs->binlist); cudaFree(c->rs->wpix); cudaFree(c->rs->wface); cudaFree(c->rs->wz); cudaFree(c->rs->counter);
     delete c->rs;
     c->rs = nullptr;
@@ -806,7 +774,7 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.pose2d_valid = c->pose2d_valid; P.mask_valid = c->mask_valid;
     P.zmin_lin = c->params + c->off[MH_P_ZMIN_LIN]; P.zmax_lin = c->params + c->off[MH_P_ZMAX_LIN];
     P.pfout = c->pfout; P.devflags = c->devflags;
-    P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.frec = c->rs->frec; P.fbin = c->rs->fbin; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
+    P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.fbin = c->rs->fbin; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
     P.counter = c->rs->counter; P.gsg = c->rs->gsg; P.vflags = c->rs->vflags;
     P.maxbins = c->rs->maxbins;
     if (c->rs->bincap_use) P.bincap = c->rs->bincap_use;
@@ -828,8 +796,7 @@ int mh_render_all(mh_ctx* c, cudaStream_t st) {
     RenderParams P = render_params(c, 1e-4f, 2e-5f);          // optimizer.py:213, 223
     MH_CUDA(c, cudaMemsetAsync(c->rs->counter, 0, sizeof(int), st));
     const int grid = std::min(c->rs->nctas, c->d.T * c->d.N);
-    if (c->rs->gred) k_render<0, 1><<<grid, R_THREADS, c->rs->smem, st>>>(P);
-    else k_render<0, 0><<<grid, R_THREADS, c->rs->smem, st>>>(P);
+    k_render<0><<<grid, R_THREADS, c->rs->smem, st>>>(P);
     MH_LAUNCHED(c);
     return MH_OK;
 }
@@ -844,7 +811,7 @@ int mh_render_planes(mh_ctx* c, int t, int n, float* zbuf_dev, float* alpha_dev,
     const int64_t HW = (int64_t)c->d.H * c->d.W;
     k_fill2<<<mh_cdiv(HW, 1024), 256, 0, st>>>(zbuf_dev, -1.0f, alpha_dev, 0.0f, HW);
     MH_LAUNCHED(c);
-    k_render<1, 0><<<1, R_THREADS, c->rs->smem, st>>>(P);
+    k_render<1><<<1, R_THREADS, c->rs->smem, st>>>(P);
     MH_LAUNCHED(c);
     return MH_OK;
 }

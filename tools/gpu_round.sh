@@ -1,16 +1,14 @@
 #!/bin/bash
-# Runs ON the GPU box (through gpurun): variant benches on the c3 profiling slice, parity suite, full c3 line.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
+# Runs ON the GPU box (through gpurun): the c3 profiling slice under both settings of the block-level prune, the parity suite,
+# the full c3 line.      gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
 set -u
 TAG=${1:-x}
 mkdir -p gpurun_out
 B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e"
-timeout 300 $B --workload c3s --render-profile > gpurun_out/${TAG}_c3s_v0.json 2> gpurun_out/${TAG}_c3s_v0.err
-MH_RENDER_GRED=1 timeout 300 $B --workload c3s --render-profile > gpurun_out/${TAG}_c3s_v1.json 2> gpurun_out/${TAG}_c3s_v1.err
+MH_RENDER_FLAGS=0 timeout 300 $B --workload c3s --render-profile > gpurun_out/${TAG}_c3s_v0.json 2> gpurun_out/${TAG}_c3s_v0.err
+MH_RENDER_FLAGS=1 timeout 300 $B --workload c3s --render-profile > gpurun_out/${TAG}_c3s_v1.json 2> gpurun_out/${TAG}_c3s_v1.err
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1
 tail -3 gpurun_out/${TAG}_tests.log
-MH_RENDER_GRED=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/${TAG}_tests_v1.log 2>&1
-tail -3 gpurun_out/${TAG}_tests_v1.log
 timeout 600 python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_c3.json 2> gpurun_out/${TAG}_c3.err
 for f in gpurun_out/${TAG}_c3s_v0 gpurun_out/${TAG}_c3s_v1 gpurun_out/${TAG}_c3; do
   python - "$f" <<'PY'
