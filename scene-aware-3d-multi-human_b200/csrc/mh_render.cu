@@ -32,6 +32,7 @@
 #define R_NSLAB 8             // depth slabs: the tile lists are ordered near -> far so that later faces are pruned early
 #define R_ITEMS (R_CHUNK * (TW * TH / 32))   // 32-pixel groups of one staged chunk (a face covers at most the whole tile)
 #define KEY_EMPTY 0xffffffffffffffffull
+#define R_DESC 1024               // (face, tile) descriptors staged per chunk (5 float4 each)
 
 struct MhRenderScratch {
     uint16_t* binlist; int bincap;
@@ -109,21 +110,54 @@ __device__ __forceinline__ void load_face(const float* sv, const int32_t* __rest
     mh_face_setup(sv + 3 * iv[0], sv + 3 * iv[1], sv + 3 * iv[2], r, fc);
 }
 
-// one native shared-memory add (the compiler's atomicAdd(p, 1) expands to a ~20-instruction match / elect / popc sequence)
-__device__ __forceinline__ int atoms_add(int* p, int v) {
+// Shared-memory accesses of the hot loops, in the shared state space with 32-bit window addresses.  Through generic pointers
+// the compiler rebuilds the generic base of the dynamic array (S2R SR_CgaCtaId, shifts, adds) next to the accesses, inside the
+// pair loop; the atomics additionally expand to match / elect / popc sequences.
+template <int OFF> __device__ __forceinline__ unsigned lds32(uint32_t a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ float ldsf(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ unsigned long long lds64(uint32_t a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1+%2];" : "=l"(v) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ void sts32(uint32_t a, unsigned v) { asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "r"(v) : "memory"); }
+template <int OFF> __device__ __forceinline__ unsigned long long atoms_min64(uint32_t a, unsigned long long v) {
+    unsigned long long old;
+    asm volatile("atom.shared.min.u64 %0, [%1+%2], %3;" : "=l"(old) : "r"(a), "n"(OFF), "l"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ int atoms_add(uint32_t a, int v) {
     int old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
     return old;
 }
 
-__device__ __forceinline__ void key_insert4(unsigned long long* slot /*stride R_THREADS*/, unsigned long long x) {
+// offsets of the dynamic shared-memory regions (bytes)
+constexpr int SO_DKEY = MH_LD3V * 4;                                   // R_THREADS     nearest depth fragment
+constexpr int SO_SKEY = SO_DKEY + R_THREADS * 8;                       // 4 x R_THREADS nearest silhouette fragments
+constexpr int SO_TCOUNT = SO_SKEY + 4 * R_THREADS * 8;                 // R_MAXBINS + 1 (exclusive offsets after the scan)
+constexpr int SO_TCUR = SO_TCOUNT + (R_MAXBINS + 1) * 4;               // R_MAXBINS (+ 3 pad)
+constexpr int SO_SRED = SO_TCUR + (R_MAXBINS + 3) * 4;                 // 256 floats
+constexpr int SO_SPX = SO_SRED + 256 * 4;                              // TW
+constexpr int SO_SPY = SO_SPX + TW * 4;                                // TH
+constexpr int SO_SINT = SO_SPY + TH * 4;                               // 96 ints
+constexpr int SO_SDESC = (SO_SINT + 96 * 4 + 15) & ~15;                // R_DESC x 5 float4
+constexpr int SO_END = SO_SDESC + R_DESC * 80;
+constexpr int SK_STRIDE = R_THREADS * 8;                               // bytes between the slot planes of the keys
+
+__device__ __forceinline__ void key_insert4(uint32_t a /* slot 0 of the pixel */, unsigned long long x) {
     // concurrent sorted insertion: every slot keeps the minimum of what reaches it and passes the rest on
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const unsigned long long old = atomicMin(slot + s * R_THREADS, x);
-        x = old > x ? old : x;
-        if (x == KEY_EMPTY) break;
-    }
+    unsigned long long old = atoms_min64<0>(a, x);
+    x = old > x ? old : x;
+    if (x == KEY_EMPTY) return;
+    old = atoms_min64<SK_STRIDE>(a, x);
+    x = old > x ? old : x;
+    if (x == KEY_EMPTY) return;
+    old = atoms_min64<2 * SK_STRIDE>(a, x);
+    x = old > x ? old : x;
+    if (x == KEY_EMPTY) return;
+    atoms_min64<3 * SK_STRIDE>(a, x);
 }
 
 // -DMH_RSTATS: (face, pixel)-pair statistics of P2 in slots 8.. of the profile buffer (instrumented build only)
@@ -174,7 +208,6 @@ __device__ __forceinline__ void grad_add(float* p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-#define R_DESC 1024               // (face, tile) descriptors staged per chunk (5 float4 each)
 
 // Descriptor of one (face, tile) item -- everything P2 needs, computed ONCE by one thread (the tile's faces are spread over
 // the 1024 threads) instead of redundantly by the 32 lanes of the warp that rasterises the face:
@@ -221,15 +254,19 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sv = reinterpret_cast<float*>(smem_raw);                                   // MH_LD3V  NDC vertices
     float* sg = P.gsg + (size_t)blockIdx.x * MH_LD3V;                                 // MH_LD3V  NDC gradients: global (L2), zero on entry
-    unsigned long long* dkey = reinterpret_cast<unsigned long long*>(sv + MH_LD3V);   // R_THREADS     nearest depth fragment
-    unsigned long long* skey = dkey + R_THREADS;                                      // 4 x R_THREADS nearest silhouette fragments
-    int* tcount = reinterpret_cast<int*>(skey + 4 * R_THREADS);                       // R_MAXBINS + 1 (exclusive offsets after the scan)
-    int* tcur = tcount + R_MAXBINS + 1;                                               // R_MAXBINS
-    float* sred = reinterpret_cast<float*>(tcur + R_MAXBINS + 3);                     // 256
-    float* spx = sred + 256;                                                          // TW
-    float* spy = spx + TW;                                                            // TH
-    int* sint = reinterpret_cast<int*>(spy + TH);                                     // 96
-    float4* sdesc = reinterpret_cast<float4*>(smem_raw + ((reinterpret_cast<size_t>(sint + 96) - reinterpret_cast<size_t>(smem_raw) + 15) & ~size_t(15)));   // R_DESC x 5
+    unsigned long long* dkey = reinterpret_cast<unsigned long long*>(smem_raw + SO_DKEY);
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw + SO_SKEY);
+    int* tcount = reinterpret_cast<int*>(smem_raw + SO_TCOUNT);
+    int* tcur = reinterpret_cast<int*>(smem_raw + SO_TCUR);
+    float* sred = reinterpret_cast<float*>(smem_raw + SO_SRED);
+    float* spx = reinterpret_cast<float*>(smem_raw + SO_SPX);
+    float* spy = reinterpret_cast<float*>(smem_raw + SO_SPY);
+    int* sint = reinterpret_cast<int*>(smem_raw + SO_SINT);
+    float4* sdesc = reinterpret_cast<float4*>(smem_raw + SO_SDESC);
+    // shared-window address of the dynamic array.  ptxas builds it from SR_CgaCtaId (S2R + 3 ALU) and would rematerialise that
+    // inside the pair loop; a volatile asm pins it to ONE evaluation
+    uint32_t sb;
+    asm volatile("mov.u32 %0, smem_raw;" : "=r"(sb));
     __shared__ __align__(8) unsigned long long mbar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -349,7 +386,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         const int slab = min(max((int)((zmin - zlo) * zscale), 0), R_NSLAB - 1);
                         fb = make_uint2((unsigned)bx_lo | ((unsigned)bx_hi << 16), (unsigned)by_lo | ((unsigned)by_hi << 10) | ((unsigned)slab << 20) | 0x80000000u);
                         for (int by = by_lo; by <= by_hi; ++by)
-                            for (int bx = bx_lo; bx <= bx_hi; ++bx) atoms_add(&tcount[by * nbx + bx], 1);
+                            for (int bx = bx_lo; bx <= bx_hi; ++bx) atoms_add(sb + SO_TCOUNT + 4 * (by * nbx + bx), 1);
                     }
                 }
             }
@@ -383,7 +420,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const int bx_lo = fb.x & 0xffff, bx_hi = fb.x >> 16, by_lo = fb.y & 1023, by_hi = (fb.y >> 10) & 1023;
                 for (int by = by_lo; by <= by_hi; ++by)
                     for (int bx = bx_lo; bx <= bx_hi; ++bx) {
-                        const int pos = atoms_add(&tcur[by * nbx + bx], 1);
+                        const int pos = atoms_add(sb + SO_TCUR + 4 * (by * nbx + bx), 1);
                         if (pos < P.bincap) binlist[pos] = (uint16_t)f;
                     }
             }
@@ -465,12 +502,12 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
               }
               const int ccnt = min(cnt - base, R_DESC);
               int kn = 0;
-              if (lane == 0) kn = atoms_add(&sint[40], 1);
+              if (lane == 0) kn = atoms_add(sb + SO_SINT + 4 * 40, 1);
               kn = __shfl_sync(0xffffffffu, kn, 0);
               while (kn < ccnt) {
-                const float4* dsc = sdesc + kn * 5;
-                if (lane == 0) kn = atoms_add(&sint[40], 1);              // the next item: the atomic's latency hides behind this one
-                const float4 q0 = dsc[0], q1 = dsc[1], q2 = dsc[2], q3 = dsc[3], q4 = dsc[4];
+                const uint32_t da = sb + SO_SDESC + kn * 80;
+                if (lane == 0) kn = atoms_add(sb + SO_SINT + 4 * 40, 1);  // the next item: the atomic's latency hides behind this one
+                const float4 q0 = lds128<0>(da), q1 = lds128<16>(da), q2 = lds128<32>(da), q3 = lds128<48>(da), q4 = lds128<64>(da);
                 kn = __shfl_sync(0xffffffffu, kn, 0);
                 const int rect = __float_as_int(q3.y);
                 int w = (rect >> 10) & 63;
@@ -489,7 +526,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     unsigned hd = 0u, hs = 0u;
                     if (lane < 16) {
                         const int bx = lane & 3, by = lane >> 2;
-                        if (bx >= (c0 >> 3) && bx <= ((c0 + w - 1) >> 3) && by >= (r0 >> 3) && by <= ((r0 + h - 1) >> 3)) { hd = hz[lane]; hs = hz[16 + lane]; }
+                        if (bx >= (c0 >> 3) && bx <= ((c0 + w - 1) >> 3) && by >= (r0 >> 3) && by <= ((r0 + h - 1) >> 3)) {
+                            hd = lds32<SO_SINT + 4 * 48>(sb + 4 * lane); hs = lds32<SO_SINT + 4 * 64>(sb + 4 * lane);
+                        }
                     }
                     hd = __reduce_max_sync(0xffffffffu, hd); hs = __reduce_max_sync(0xffffffffu, hs);
                     if (zbits > hd) {
@@ -506,21 +545,20 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const float ex12 = MH_SUB(x2, x1), ey12 = MH_SUB(y2, y1);
                 const float ex20 = MH_SUB(x0, x2), ey20 = MH_SUB(y0, y2);
                 const float ex01 = MH_SUB(x1, x0), ey01 = MH_SUB(y1, y0);
-                const unsigned* keyhi = reinterpret_cast<const unsigned*>(dkey) + 1;      // high (depth) words of dkey / skey
                 for (int o = lane; o < npix; o += 32) {
                     RS_WARP(2);
                     const int row = (o * magic) >> 16;
                     const int col = o - row * w;
                     const int lx = c0 + col, ly = r0 + row;
-                    const int pix = ly * TW + lx;
+                    const uint32_t ka = sb + 8 * (ly * TW + lx);          // + SO_DKEY: depth key of the pixel, + SO_SKEY + s * SK_STRIDE: silhouette keys
                     // prune on the depth words of the keys alone (conservative on ties): no fragment of this face can be nearer
                     // than its nearest vertex; outside the inner rectangle it cannot be a silhouette fragment at all
                     const bool inner = ((unsigned)(lx - jc0) < jw) && ((unsigned)(ly - jr0) < jh);
-                    const bool pd = zbits <= keyhi[2 * pix];
-                    const bool ps = inner && (zbits <= keyhi[2 * (3 * R_THREADS + R_THREADS + pix)]);
+                    const bool pd = zbits <= lds32<SO_DKEY + 4>(ka);
+                    const bool ps = inner && (zbits <= lds32<SO_SKEY + 3 * SK_STRIDE + 4>(ka));
                     if (!pd && !ps) continue;
                     RS_ADD(3, 1); RS_WARP(4); if (inner) RS_ADD(10, 1);
-                    const float px = spx[lx], py = spy[ly];
+                    const float px = ldsf<SO_SPX>(sb + 4 * lx), py = ldsf<SO_SPY>(sb + 4 * ly);
                     const float dx0 = MH_SUB(px, x0), dy0 = MH_SUB(py, y0);
                     const float dx1 = MH_SUB(px, x1), dy1 = MH_SUB(py, y1);
                     const float dx2 = MH_SUB(px, x2), dy2 = MH_SUB(py, y2);
@@ -533,8 +571,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const float pz = __fdividef(c0w * z0 + c1w * z1 + c2w * z2, fmaxf(c0w + c1w + c2w, 1e-5f));
                     if (!(pz >= 0.f)) continue;
                     const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)fcur;
-                    const bool wd = pd && (key < dkey[pix]);
-                    const bool ws = ps && (key < skey[3 * R_THREADS + pix]);
+                    const bool wd = pd && (key < lds64<SO_DKEY>(ka));
+                    const bool ws = ps && (key < lds64<SO_SKEY + 3 * SK_STRIDE>(ka));
                     if (!wd && !ws) continue;
                     RS_ADD(5, 1); RS_WARP(6);
                     const bool inside = (e0 != 0.f) && (e1 != 0.f) && (e2 != 0.f) && ((e0 > 0.f) == dpos) && ((e1 > 0.f) == dpos) && ((e2 > 0.f) == dpos);
@@ -557,18 +595,18 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     if (!inside) RS_ADD(9, 1);
                     if (vd && wd) RS_ADD(7, 1);
                     if (vs && ws) RS_ADD(8, 1);
-                    if (vd && wd) atomicMin(&dkey[pix], key);
-                    if (vs && ws) key_insert4(skey + pix, key);
+                    if (vd && wd) atoms_min64<SO_DKEY>(ka, key);
+                    if (vs && ws) key_insert4(ka + SO_SKEY, key);
                 }
                 __syncwarp();
                 if (P.vflags & 1) {
                     // refresh the bounds of the block under the centre of the rectangle just processed (2 pixels per lane)
                     const int bx = (2 * c0 + w - 1) >> 4, by = (2 * r0 + h - 1) >> 4;
-                    const int p0 = ((by << 3) + (lane >> 3)) * TW + (bx << 3) + (lane & 7);
-                    unsigned md = max(keyhi[2 * p0], keyhi[2 * (p0 + 4 * TW)]);
-                    unsigned ms = max(keyhi[2 * (4 * R_THREADS + p0)], keyhi[2 * (4 * R_THREADS + p0 + 4 * TW)]);
+                    const uint32_t pa = sb + 8 * (((by << 3) + (lane >> 3)) * TW + (bx << 3) + (lane & 7));
+                    unsigned md = max(lds32<SO_DKEY + 4>(pa), lds32<SO_DKEY + 4 + 8 * 4 * TW>(pa));
+                    unsigned ms = max(lds32<SO_SKEY + 3 * SK_STRIDE + 4>(pa), lds32<SO_SKEY + 3 * SK_STRIDE + 4 + 8 * 4 * TW>(pa));
                     md = __reduce_max_sync(0xffffffffu, md); ms = __reduce_max_sync(0xffffffffu, ms);
-                    if (lane == 0) { hz[(by << 2) | bx] = md; hz[16 + ((by << 2) | bx)] = ms; }
+                    if (lane == 0) { sts32<SO_SINT + 4 * 48>(sb + 4 * ((by << 2) | bx), md); sts32<SO_SINT + 4 * 64>(sb + 4 * ((by << 2) | bx), ms); }
                 }
               }
             }
@@ -617,7 +655,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 // d log(clamp(1 / clamp(z + .2, eps), eps)) / dz
                 const float gfac = (dz + 0.2f >= P.eps && zdisp >= P.eps) ? -1.0f / zc : 0.f;
                 if (gfac != 0.f) {
-                    const int wq = atoms_add(&sint[6], 1);
+                    const int wq = atoms_add(sb + SO_SINT + 4 * 6, 1);
                     if (wq < P.wcap) { wpix[wq] = yi * P.W + xi; wface[wq] = df; wz[wq] = gfac; }
                 }
             }
@@ -748,8 +786,7 @@ int mh_render_alloc(mh_ctx* c) {
         if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_magic, magic, sizeof(magic));
     }
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
-    rs->smem = (size_t)MH_LD3V * sizeof(float) + (size_t)5 * R_THREADS * sizeof(unsigned long long) +
-               (size_t)(2 * R_MAXBINS + 4) * sizeof(int) + (256 + TW + TH) * sizeof(float) + 96 * sizeof(int) + (size_t)R_DESC * 5 * sizeof(float4) + 128;
+    rs->smem = (size_t)SO_END + 128;
     e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render: %zu bytes of shared memory: %s", rs->smem, cudaGetErrorString(e));
