@@ -41,7 +41,7 @@ struct MhRenderScratch {
     int nctas;
     size_t smem;
     int* counter;
-    float* gsg; int vflags;
+    float* gsg;
     long long* prof;
     int maxbins;               // tile bins per body before the binning granularity is coarsened (<= R_MAXBINS)
     int bincap_use, wcap_use;  // capacities handed to the kernel (<= the allocated ones; testing aid)
@@ -56,7 +56,6 @@ struct RenderParams {
     const float* zmin_lin; const float* zmax_lin;
     float* pfout; int* devflags;
     float* gsg;                   // per-CTA NDC-gradient rows (MH_LD3V floats each), zero between bodies
-    int vflags;                   // development switches (MH_RENDER_FLAGS): 1 block-level prune, 2 CAS-first key updates
     uint16_t* binlist; int bincap;
     uint2* fbin;                  // per-CTA scratch: packed bin range + depth slab per face
     int* wpix; int* wface; float* wz; int wcap;
@@ -141,8 +140,8 @@ constexpr int SO_TCUR = SO_TCOUNT + (R_MAXBINS + 1) * 4;               // R_MAXB
 constexpr int SO_SRED = SO_TCUR + (R_MAXBINS + 3) * 4;                 // 256 floats
 constexpr int SO_SPX = SO_SRED + 256 * 4;                              // TW
 constexpr int SO_SPY = SO_SPX + TW * 4;                                // TH
-constexpr int SO_SINT = SO_SPY + TH * 4;                               // 96 ints
-constexpr int SO_SDESC = (SO_SINT + 96 * 4 + 15) & ~15;                // R_DESC x 5 float4
+constexpr int SO_SINT = SO_SPY + TH * 4;                               // 64 ints
+constexpr int SO_SDESC = (SO_SINT + 64 * 4 + 15) & ~15;                // R_DESC x 5 float4
 constexpr int SO_END = SO_SDESC + R_DESC * 80;
 constexpr int SK_STRIDE = R_THREADS * 8;                               // bytes between the slot planes of the keys
 
@@ -249,6 +248,31 @@ __device__ __forceinline__ void make_desc(const RenderParams& P, const float* sv
     d[4] = make_float4(__int_as_float(f), __int_as_float((65536 + w - 1) / w), 0.f, 0.f);
 }
 
+// Backward of the unsigned squared edge distance of one silhouette fragment: d = |p - a - t (b - a)|^2 on the nearest edge
+// (first minimum in the order 01, 02, 12, as mh_face_bwd), dd/da = -2 q (1 - t), dd/db = -2 q t.  Reciprocal multiplies: the
+// gradient tolerance (1e-3 of the maximum) does not need the oracle's divisions.
+__device__ __forceinline__ void sil_grad(float* sg, const float* sv, const int32_t* __restrict__ faces, int f, float px, float py, float gd) {
+    const int iv[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
+    const float vx[3] = {sv[3 * iv[0]], sv[3 * iv[1]], sv[3 * iv[2]]};
+    const float vy[3] = {sv[3 * iv[0] + 1], sv[3 * iv[1] + 1], sv[3 * iv[2] + 1]};
+    float best = INFINITY, bt = 0.f, bqx = 0.f, bqy = 0.f;
+    int ia = 0, ib = 1;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const int a = (e == 2) ? 1 : 0, b = (e == 0) ? 1 : 2;
+        const float bax = vx[b] - vx[a], bay = vy[b] - vy[a];
+        const float l2 = bax * bax + bay * bay;
+        const float t = (l2 <= MH_KEPS) ? 1.0f : __saturatef(__fdividef(bax * (px - vx[a]) + bay * (py - vy[a]), l2));
+        const float qx = px - (vx[a] + t * bax), qy = py - (vy[a] + t * bay);
+        const float d = qx * qx + qy * qy;
+        if (d < best) { best = d; bt = t; bqx = qx; bqy = qy; ia = a; ib = b; }
+    }
+    const float g = -2.0f * gd;
+    const float ga = g * (1.0f - bt), gb = g * bt;
+    if (ga != 0.f) { grad_add(&sg[3 * iv[ia]], ga * bqx); grad_add(&sg[3 * iv[ia] + 1], ga * bqy); }
+    if (gb != 0.f) { grad_add(&sg[3 * iv[ib]], gb * bqx); grad_add(&sg[3 * iv[ib] + 1], gb * bqy); }
+}
+
 template <int MODE>      // MODE 0: losses + gradients ; 1: dense zbuf / alpha planes of one body
 __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -347,8 +371,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             int r0 = (int)floorf(fminf(fmaxf(pix_of(by1 + P.r_d, P.H, P.ry) - 1.f, 0.f), (float)(P.H - 1)));
             int r1 = (int)ceilf(fminf(fmaxf(pix_of(by0 - P.r_d, P.H, P.ry) + 1.f, 0.f), (float)(P.H - 1)));
             if (!(bx0 <= bx1)) { c0 = 1; c1 = 0; r0 = 1; r1 = 0; }          // nothing in front of the camera
-            const int tx0 = c0 / TW, tx1 = c1 / TW, ty0 = r0 / TH, ty1 = r1 / TH;
-            int ntx = max(tx1 - tx0 + 1, 0), nty = max(ty1 - ty0 + 1, 0);
+            // the tile grid starts at the body's own bounding box (not at multiples of the tile size): fewer, fuller tiles
+            const int tx0 = c0, ty0 = r0;
+            int ntx = (c1 >= c0) ? (c1 - c0) / TW + 1 : 0, nty = (r1 >= r0) ? (r1 - r0) / TH + 1 : 0;
             int ks = 0;
             while ((((ntx + (1 << ks) - 1) >> ks) * ((nty + (1 << ks) - 1) >> ks)) > P.maxbins) ++ks;
             sint[1] = tx0; sint[2] = ty0; sint[3] = ntx; sint[4] = nty; sint[5] = ks;
@@ -380,8 +405,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 if ((pc1 >= 0.f) && (pr1 >= 0.f) && (pc0 <= (float)(P.W - 1)) && (pr0 <= (float)(P.H - 1)) && (pc0 <= pc1) && (pr0 <= pr1)) {
                     const int c0 = (int)fmaxf(pc0, 0.f), c1 = (int)fminf(pc1, (float)(P.W - 1));
                     const int r0 = (int)fmaxf(pr0, 0.f), r1 = (int)fminf(pr1, (float)(P.H - 1));
-                    const int bx_lo = max((c0 / TW - tx0) >> ks, 0), bx_hi = min((c1 / TW - tx0) >> ks, nbx - 1);
-                    const int by_lo = max((r0 / TH - ty0) >> ks, 0), by_hi = min((r1 / TH - ty0) >> ks, nby - 1);
+                    const int bx_lo = max(((c0 - tx0) / TW) >> ks, 0), bx_hi = min(((c1 - tx0) / TW) >> ks, nbx - 1);
+                    const int by_lo = max(((r0 - ty0) / TH) >> ks, 0), by_hi = min(((r1 - ty0) / TH) >> ks, nby - 1);
                     if (bx_lo <= bx_hi && by_lo <= by_hi) {
                         const int slab = min(max((int)((zmin - zlo) * zscale), 0), R_NSLAB - 1);
                         fb = make_uint2((unsigned)bx_lo | ((unsigned)bx_hi << 16), (unsigned)by_lo | ((unsigned)by_hi << 10) | ((unsigned)slab << 20) | 0x80000000u);
@@ -451,11 +476,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             const int bin = (tty >> ks) * nbx + (ttx >> ks);
             const int off = tcount[bin], cnt = tcount[bin + 1] - off;
             if (cnt == 0) continue;
-            const int ox = (tx0 + ttx) * TW, oy = (ty0 + tty) * TH;       // tile origin (pixels)
-            // hz[0..15] / hz[16..31]: per 8x8-pixel block, an upper bound of the depth words of the depth keys / of the 4th
-            // silhouette keys.  Keys only decrease, so a stale value stays a valid bound; warps refresh blocks as they go
-            unsigned* hz = reinterpret_cast<unsigned*>(sint + 48);
-            if (tid < 32) hz[tid] = 0u;
+            const int ox = tx0 + ttx * TW, oy = ty0 + tty * TH;           // tile origin (pixels)
             __syncthreads();
             PROF(4);
             // this thread's pixel (the same in the tile set-up and in P3): what the loss needs there.  A pixel that needs no
@@ -473,11 +494,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 }
             }
             const bool need_d = pflags & 1u, need_s = pflags & 2u;
-            {
-                const int blk = ((tid >> 8) << 2) | ((tid & 31) >> 3);    // 8x8 block of this thread's pixel: rows tid >> 5, cols tid & 31
-                if (need_d) hz[blk] = 0xffffffffu;
-                if (need_s) hz[16 + blk] = 0xffffffffu;
-            }
             dkey[tid] = need_d ? KEY_EMPTY : 0ull;
             if (tid == 0) sint[40] = 0;
 #pragma unroll
@@ -510,9 +526,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const float4 q0 = lds128<0>(da), q1 = lds128<16>(da), q2 = lds128<32>(da), q3 = lds128<48>(da), q4 = lds128<64>(da);
                 kn = __shfl_sync(0xffffffffu, kn, 0);
                 const int rect = __float_as_int(q3.y);
-                int w = (rect >> 10) & 63;
+                const int w = (rect >> 10) & 63;
                 if (w == 0) continue;                                     // binned conservatively: nothing of the face in this tile
-                int c0 = rect & 31, r0 = (rect >> 5) & 31, h = (rect >> 16) & 63;
+                const int c0 = rect & 31, r0 = (rect >> 5) & 31, h = (rect >> 16) & 63;
                 const int inner = __float_as_int(q3.z);
                 const int jc0 = inner & 31, jr0 = (inner >> 5) & 31;
                 const unsigned jw = (inner >> 10) & 63, jh = (inner >> 16) & 63;
@@ -520,24 +536,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const float inv_den = q2.y, il01 = q2.z, il02 = q2.w, il12 = q3.x;
                 const unsigned zbits = __float_as_uint(q3.w);
                 const int fcur = __float_as_int(q4.x);
-                int magic = __float_as_int(q4.y);
-                if (P.vflags & 1) {
-                    // block-level prune: can the face still improve a key anywhere in the 8x8 blocks its rectangle touches?
-                    unsigned hd = 0u, hs = 0u;
-                    if (lane < 16) {
-                        const int bx = lane & 3, by = lane >> 2;
-                        if (bx >= (c0 >> 3) && bx <= ((c0 + w - 1) >> 3) && by >= (r0 >> 3) && by <= ((r0 + h - 1) >> 3)) {
-                            hd = lds32<SO_SINT + 4 * 48>(sb + 4 * lane); hs = lds32<SO_SINT + 4 * 64>(sb + 4 * lane);
-                        }
-                    }
-                    hd = __reduce_max_sync(0xffffffffu, hd); hs = __reduce_max_sync(0xffffffffu, hs);
-                    if (zbits > hd) {
-                        if (zbits > hs || jw == 0u) { RS_WARP(11); continue; }   // nothing to gain in this tile
-                        // depth cannot improve: only the inner rectangle matters
-                        c0 = jc0; r0 = jr0; w = (int)jw; h = (int)jh;
-                        magic = c_magic[w];
-                    }
-                }
+                const int magic = __float_as_int(q4.y);
                 if (lane == 0) { RS_ADD(0, 1); RS_ADD(1, w * h); }
                 const int npix = w * h;
                 const bool dpos = inv_den > 0.f;
@@ -597,16 +596,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     if (vs && ws) RS_ADD(8, 1);
                     if (vd && wd) atoms_min64<SO_DKEY>(ka, key);
                     if (vs && ws) key_insert4(ka + SO_SKEY, key);
-                }
-                __syncwarp();
-                if (P.vflags & 1) {
-                    // refresh the bounds of the block under the centre of the rectangle just processed (2 pixels per lane)
-                    const int bx = (2 * c0 + w - 1) >> 4, by = (2 * r0 + h - 1) >> 4;
-                    const uint32_t pa = sb + 8 * (((by << 3) + (lane >> 3)) * TW + (bx << 3) + (lane & 7));
-                    unsigned md = max(lds32<SO_DKEY + 4>(pa), lds32<SO_DKEY + 4 + 8 * 4 * TW>(pa));
-                    unsigned ms = max(lds32<SO_SKEY + 3 * SK_STRIDE + 4>(pa), lds32<SO_SKEY + 3 * SK_STRIDE + 4 + 8 * 4 * TW>(pa));
-                    md = __reduce_max_sync(0xffffffffu, md); ms = __reduce_max_sync(0xffffffffu, ms);
-                    if (lane == 0) { sts32<SO_SINT + 4 * 48>(sb + 4 * ((by << 2) | bx), md); sts32<SO_SINT + 4 * 64>(sb + 4 * ((by << 2) | bx), ms); }
                 }
               }
             }
@@ -677,15 +666,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         const float gsd = ga * others * (-pk[s] * (1.0f - pk[s]) / P.sigma);
                         const float gdist = sd[s] < 0.f ? -gsd : gsd;     // signed = inside ? -dist : dist
                         if (gdist == 0.f) continue;
-                        MhFace fc; int iv[3];
-                        load_face(sv, P.faces, sf[s], P.r_d, &fc, iv);
-                        float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        mh_face_bwd(fc, pxn, pyn, 0.f, gdist, g);
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) {
-                            if (g[3 * e] != 0.f) grad_add(&sg[3 * iv[e]], g[3 * e]);
-                            if (g[3 * e + 1] != 0.f) grad_add(&sg[3 * iv[e] + 1], g[3 * e + 1]);
-                        }
+                        sil_grad(sg, sv, P.faces, sf[s], pxn, pyn, gdist);
                     }
                 }
             }
@@ -777,7 +758,6 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->gsg, n * MH_LD3V * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(float));
-    { const char* v = getenv("MH_RENDER_FLAGS"); rs->vflags = v ? atoi(v) : 3; }
     rs->prof = nullptr;
     {
         int magic[TW + 1];
@@ -812,7 +792,7 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.zmin_lin = c->params + c->off[MH_P_ZMIN_LIN]; P.zmax_lin = c->params + c->off[MH_P_ZMAX_LIN];
     P.pfout = c->pfout; P.devflags = c->devflags;
     P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.fbin = c->rs->fbin; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
-    P.counter = c->rs->counter; P.gsg = c->rs->gsg; P.vflags = c->rs->vflags;
+    P.counter = c->rs->counter; P.gsg = c->rs->gsg;
     P.maxbins = c->rs->maxbins;
     if (c->rs->bincap_use) P.bincap = c->rs->bincap_use;
     if (c->rs->wcap_use) P.wcap = c->rs->wcap_use;
