@@ -29,7 +29,7 @@
 #define R_THREADS 1024        // one thread per tile pixel in the per-pixel phases
 #define R_MAXBINS 1024
 #define R_CHUNK 256
-#define R_NSLAB 8             // depth slabs: the tile lists are ordered near -> far so that later faces are pruned early
+#define R_NSLAB 64            // depth slabs (at most): the tile lists are ordered near -> far so that later faces are pruned early
 #define R_ITEMS (R_CHUNK * (TW * TH / 32))   // 32-pixel groups of one staged chunk (a face covers at most the whole tile)
 #define KEY_EMPTY 0xffffffffffffffffull
 #define R_DESC 1024               // (face, tile) descriptors staged per chunk (5 float4 each)
@@ -41,7 +41,7 @@ struct MhRenderScratch {
     int nctas;
     size_t smem;
     int* counter;
-    float* gsg;
+    float* gsg; int nslab;
     long long* prof;
     int maxbins;               // tile bins per body before the binning granularity is coarsened (<= R_MAXBINS)
     int bincap_use, wcap_use;  // capacities handed to the kernel (<= the allocated ones; testing aid)
@@ -55,6 +55,7 @@ struct RenderParams {
     const uint8_t* pose2d_valid; const uint8_t* mask_valid;
     const float* zmin_lin; const float* zmax_lin;
     float* pfout; int* devflags;
+    int nslab;                    // depth slabs of the tile lists (<= 256)
     float* gsg;                   // per-CTA NDC-gradient rows (MH_LD3V floats each), zero between bodies
     uint16_t* binlist; int bincap;
     uint2* fbin;                  // per-CTA scratch: packed bin range + depth slab per face
@@ -124,6 +125,11 @@ template <int OFF> __device__ __forceinline__ void sts32(uint32_t a, unsigned v)
 template <int OFF> __device__ __forceinline__ unsigned long long atoms_min64(uint32_t a, unsigned long long v) {
     unsigned long long old;
     asm volatile("atom.shared.min.u64 %0, [%1+%2], %3;" : "=l"(old) : "r"(a), "n"(OFF), "l"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ int atoms_inc(uint32_t a) {        // old value, then + 1 (ptxas leaves .inc alone; a uniform-address .add becomes vote + popc + shuffle)
+    int old;
+    asm volatile("atom.shared.inc.u32 %0, [%1], 0xffffffff;" : "=r"(old) : "r"(a) : "memory");
     return old;
 }
 __device__ __forceinline__ int atoms_add(uint32_t a, int v) {
@@ -281,7 +287,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     unsigned long long* dkey = reinterpret_cast<unsigned long long*>(smem_raw + SO_DKEY);
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw + SO_SKEY);
     int* tcount = reinterpret_cast<int*>(smem_raw + SO_TCOUNT);
-    int* tcur = reinterpret_cast<int*>(smem_raw + SO_TCUR);
     float* sred = reinterpret_cast<float*>(smem_raw + SO_SRED);
     float* spx = reinterpret_cast<float*>(smem_raw + SO_SPX);
     float* spy = reinterpret_cast<float*>(smem_raw + SO_SPY);
@@ -364,7 +369,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 bx0 = fminf(bx0, sred[w]); bx1 = fmaxf(bx1, sred[NW + w]); by0 = fminf(by0, sred[2 * NW + w]); by1 = fmaxf(by1, sred[3 * NW + w]);
                 bz0 = fminf(bz0, sred[4 * NW + w]); bz1 = fmaxf(bz1, sred[5 * NW + w]);
             }
-            sred[6 * NW] = bz0; sred[6 * NW + 1] = (bz1 > bz0) ? (float)R_NSLAB / (bz1 - bz0) : 0.f;
             // pixel bbox of the body (NDC x / y decrease with the pixel index), inflated by the blur radius + 1 px
             int c0 = (int)floorf(fminf(fmaxf(pix_of(bx1 + P.r_d, P.W, P.rx) - 1.f, 0.f), (float)(P.W - 1)));
             int c1 = (int)ceilf(fminf(fmaxf(pix_of(bx0 - P.r_d, P.W, P.rx) + 1.f, 0.f), (float)(P.W - 1)));
@@ -376,7 +380,12 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             int ntx = (c1 >= c0) ? (c1 - c0) / TW + 1 : 0, nty = (r1 >= r0) ? (r1 - r0) / TH + 1 : 0;
             int ks = 0;
             while ((((ntx + (1 << ks) - 1) >> ks) * ((nty + (1 << ks) - 1) >> ks)) > P.maxbins) ++ks;
-            sint[1] = tx0; sint[2] = ty0; sint[3] = ntx; sint[4] = nty; sint[5] = ks;
+            // depth slabs per bin: the tile lists are counting-sorted by (bin, slab) in ONE fill pass; as many slabs as the
+            // counter array holds
+            const int nb = max(((ntx + (1 << ks) - 1) >> ks) * ((nty + (1 << ks) - 1) >> ks), 1);
+            const int S = max(min(P.nslab, (2 * R_MAXBINS) / nb), 1);
+            sred[6 * NW] = bz0; sred[6 * NW + 1] = (bz1 > bz0) ? (float)S / (bz1 - bz0) : 0.f;
+            sint[1] = tx0; sint[2] = ty0; sint[3] = ntx; sint[4] = nty; sint[5] = ks; sint[41] = S;
             sint[6] = 0;     // winner count
             sint[7] = 0;     // overflow flag
         }
@@ -384,8 +393,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         PROF(0);
         const int tx0 = sint[1], ty0 = sint[2], ntx = sint[3], nty = sint[4], ks = sint[5];
         const int nbx = (ntx + (1 << ks) - 1) >> ks, nby = (nty + (1 << ks) - 1) >> ks, nbins = nbx * nby;
+        const int S = sint[41], K = nbins * S;                           // counters: (bin, slab), bin-major
         // ---- P1: bin the faces ----
-        for (int e = tid; e <= nbins; e += R_THREADS) tcount[e] = 0;
+        for (int e = tid; e <= K; e += R_THREADS) tcount[e] = 0;
         __syncthreads();
         const float zlo = sred[6 * NW], zscale = sred[6 * NW + 1];
         // pass 0: bin range (conservative by 0.01 px) + depth slab per face, per-bin counts
@@ -408,10 +418,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const int bx_lo = max(((c0 - tx0) / TW) >> ks, 0), bx_hi = min(((c1 - tx0) / TW) >> ks, nbx - 1);
                     const int by_lo = max(((r0 - ty0) / TH) >> ks, 0), by_hi = min(((r1 - ty0) / TH) >> ks, nby - 1);
                     if (bx_lo <= bx_hi && by_lo <= by_hi) {
-                        const int slab = min(max((int)((zmin - zlo) * zscale), 0), R_NSLAB - 1);
+                        const int slab = min(max((int)((zmin - zlo) * zscale), 0), S - 1);
                         fb = make_uint2((unsigned)bx_lo | ((unsigned)bx_hi << 16), (unsigned)by_lo | ((unsigned)by_hi << 10) | ((unsigned)slab << 20) | 0x80000000u);
                         for (int by = by_lo; by <= by_hi; ++by)
-                            for (int bx = bx_lo; bx <= bx_hi; ++bx) atoms_add(sb + SO_TCOUNT + 4 * (by * nbx + bx), 1);
+                            for (int bx = bx_lo; bx <= bx_hi; ++bx) atoms_add(sb + SO_TCOUNT + 4 * ((by * nbx + bx) * S + slab), 1);
                     }
                 }
             }
@@ -419,10 +429,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         }
         __syncthreads();
         {
-            // exclusive scan of tcount[0..nbins) -> offsets ; tcount[nbins] = total
-            const int per = (nbins + R_THREADS - 1) / R_THREADS;
+            // exclusive scan of tcount[0..K) -> start offsets of every (bin, slab) run
+            const int per = (K + R_THREADS - 1) / R_THREADS;
             int local = 0;
-            for (int k = 0; k < per; ++k) { const int e = tid * per + k; if (e < nbins) local += tcount[e]; }
+            for (int k = 0; k < per; ++k) { const int e = tid * per + k; if (e < K) local += tcount[e]; }
             int incl = local;
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
             if (lane == 31) sint[8 + warp] = incl;
@@ -432,25 +442,25 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             int run = wbase + incl - local;
             for (int k = 0; k < per; ++k) {
                 const int e = tid * per + k;
-                if (e < nbins) { const int cnt = tcount[e]; tcount[e] = run; tcur[e] = run; run += cnt; }
+                if (e < K) { const int cnt = tcount[e]; tcount[e] = run; run += cnt; }
             }
-            if (tid == R_THREADS - 1) { tcount[nbins] = run; if (run > P.bincap) sint[7] = 1; }
+            if (tid == R_THREADS - 1 && run > P.bincap) sint[7] = 1;
             __syncthreads();
         }
-        // pass 1: fill the tile lists slab by slab (near -> far)
-        for (int slab = 0; slab < R_NSLAB; ++slab) {
-            for (int f = tid; f < MH_F; f += R_THREADS) {
-                const uint2 fb = fbin[f];
-                if (!(fb.y & 0x80000000u) || (int)((fb.y >> 20) & 15u) != slab) continue;
-                const int bx_lo = fb.x & 0xffff, bx_hi = fb.x >> 16, by_lo = fb.y & 1023, by_hi = (fb.y >> 10) & 1023;
-                for (int by = by_lo; by <= by_hi; ++by)
-                    for (int bx = bx_lo; bx <= bx_hi; ++bx) {
-                        const int pos = atoms_add(sb + SO_TCUR + 4 * (by * nbx + bx), 1);
-                        if (pos < P.bincap) binlist[pos] = (uint16_t)f;
-                    }
-            }
-            __syncthreads();
+        // pass 1: fill -- the start offsets serve as cursors, so afterwards tcount[k] is the END of run k (= start of run k + 1):
+        // bin b owns binlist[ (b ? tcount[b S - 1] : 0) .. tcount[b S + S - 1] ), ordered near -> far by slab
+        for (int f = tid; f < MH_F; f += R_THREADS) {
+            const uint2 fb = fbin[f];
+            if (!(fb.y & 0x80000000u)) continue;
+            const int slab = (int)((fb.y >> 20) & 255u);
+            const int bx_lo = fb.x & 0xffff, bx_hi = fb.x >> 16, by_lo = fb.y & 1023, by_hi = (fb.y >> 10) & 1023;
+            for (int by = by_lo; by <= by_hi; ++by)
+                for (int bx = bx_lo; bx <= bx_hi; ++bx) {
+                    const int pos = atoms_add(sb + SO_TCOUNT + 4 * ((by * nbx + bx) * S + slab), 1);
+                    if (pos < P.bincap) binlist[pos] = (uint16_t)f;
+                }
         }
+        __syncthreads();
         PROF(1);
         const bool overflow = sint[7] != 0;
         if (overflow && tid == 0) atomicAdd(P.devflags + 1, 1);
@@ -474,7 +484,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         for (int tile = 0; tile < ntiles; ++tile) {
             const int ttx = tile % ntx, tty = tile / ntx;
             const int bin = (tty >> ks) * nbx + (ttx >> ks);
-            const int off = tcount[bin], cnt = tcount[bin + 1] - off;
+            const int off = bin ? tcount[bin * S - 1] : 0, cnt = tcount[bin * S + S - 1] - off;
             if (cnt == 0) continue;
             const int ox = tx0 + ttx * TW, oy = ty0 + tty * TH;           // tile origin (pixels)
             __syncthreads();
@@ -518,11 +528,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
               }
               const int ccnt = min(cnt - base, R_DESC);
               int kn = 0;
-              if (lane == 0) kn = atoms_add(sb + SO_SINT + 4 * 40, 1);
+              if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);
               kn = __shfl_sync(0xffffffffu, kn, 0);
               while (kn < ccnt) {
                 const uint32_t da = sb + SO_SDESC + kn * 80;
-                if (lane == 0) kn = atoms_add(sb + SO_SINT + 4 * 40, 1);  // the next item: the atomic's latency hides behind this one
+                if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);     // the next item: the atomic's latency hides behind this one
                 const float4 q0 = lds128<0>(da), q1 = lds128<16>(da), q2 = lds128<32>(da), q3 = lds128<48>(da), q4 = lds128<64>(da);
                 kn = __shfl_sync(0xffffffffu, kn, 0);
                 const int rect = __float_as_int(q3.y);
@@ -758,6 +768,7 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->gsg, n * MH_LD3V * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(float));
+    { const char* v = getenv("MH_RENDER_NSLAB"); rs->nslab = v ? std::min(std::max(atoi(v), 1), 256) : R_NSLAB; }     // development switch
     rs->prof = nullptr;
     {
         int magic[TW + 1];
@@ -792,7 +803,7 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.zmin_lin = c->params + c->off[MH_P_ZMIN_LIN]; P.zmax_lin = c->params + c->off[MH_P_ZMAX_LIN];
     P.pfout = c->pfout; P.devflags = c->devflags;
     P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.fbin = c->rs->fbin; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
-    P.counter = c->rs->counter; P.gsg = c->rs->gsg;
+    P.counter = c->rs->counter; P.gsg = c->rs->gsg; P.nslab = c->rs->nslab;
     P.maxbins = c->rs->maxbins;
     if (c->rs->bincap_use) P.bincap = c->rs->bincap_use;
     if (c->rs->wcap_use) P.wcap = c->rs->wcap_use;
