@@ -33,6 +33,7 @@
 #define R_ITEMS (R_CHUNK * (TW * TH / 32))   // 32-pixel groups of one staged chunk (a face covers at most the whole tile)
 #define KEY_EMPTY 0xffffffffffffffffull
 #define R_DESC 1024               // (face, tile) descriptors staged per chunk (5 float4 each)
+#define R_QUEUE 64                // survivor queue entries per warp (fewer than 32 wait, a pass adds at most 32)
 
 struct MhRenderScratch {
     uint16_t* binlist; int bincap;
@@ -148,7 +149,8 @@ constexpr int SO_SPX = SO_SRED + 256 * 4;                              // TW
 constexpr int SO_SPY = SO_SPX + TW * 4;                                // TH
 constexpr int SO_SINT = SO_SPY + TH * 4;                               // 64 ints
 constexpr int SO_SDESC = (SO_SINT + 64 * 4 + 15) & ~15;                // R_DESC x 5 float4
-constexpr int SO_END = SO_SDESC + R_DESC * 80;
+constexpr int SO_QUEUE = SO_SDESC + R_DESC * 80;                       // per-warp survivor queues (R_QUEUE words each)
+constexpr int SO_END = SO_QUEUE + (R_THREADS / 32) * R_QUEUE * 4;
 constexpr int SK_STRIDE = R_THREADS * 8;                               // bytes between the slot planes of the keys
 
 __device__ __forceinline__ void key_insert4(uint32_t a /* slot 0 of the pixel */, unsigned long long x) {
@@ -216,7 +218,7 @@ __device__ __forceinline__ void grad_add(float* p, float v) {
 
 // Descriptor of one (face, tile) item -- everything P2 needs, computed ONCE by one thread (the tile's faces are spread over
 // the 1024 threads) instead of redundantly by the 32 lanes of the warp that rasterises the face:
-//   d0 = x0 y0 x1 y1 | d1 = x2 y2 z0 z1 | d2 = z2 1/den 1/|e01|^2 1/|e02|^2 | d3 = 1/|e12|^2 rect inner zbits | d4 = face magic - -
+//   d0 = x0 y0 x1 y1 | d1 = x2 y2 z0 z1 | d2 = z2 1/den 1/|e01|^2 1/|e02|^2 | d3 = rect inner zbits magic | d4 = 1/|e12|^2 face - -
 // rect  = c0 | r0 << 5 | w << 10 | h << 16 : the face's pixel rectangle inside the tile, EXACT for the oracle's bbox test (bbox
 //         inflated by sqrt(blur) of the depth raster), so the pair loop needs no per-pixel bbox test; w = 0: nothing in this tile
 // inner = same packing: the only pixels where the face can be a SILHOUETTE fragment (bbox inflated by the silhouette radius x 1.001
@@ -250,8 +252,8 @@ __device__ __forceinline__ void make_desc(const RenderParams& P, const float* sv
     d[0] = make_float4(x0, y0, x1, y1);
     d[1] = make_float4(x2, y2, z0, z1);
     d[2] = make_float4(z2, __frcp_rn(den), l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), l02 <= MH_KEPS ? 0.f : __frcp_rn(l02));
-    d[3] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), __int_as_float(rect), __int_as_float(inner), __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))));
-    d[4] = make_float4(__int_as_float(f), __int_as_float((65536 + w - 1) / w), 0.f, 0.f);
+    d[3] = make_float4(__int_as_float(rect), __int_as_float(inner), __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))), __int_as_float((65536 + w - 1) / w));
+    d[4] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), __int_as_float(f), 0.f, 0.f);
 }
 
 // Backward of the unsigned squared edge distance of one silhouette fragment: d = |p - a - t (b - a)|^2 on the nearest edge
@@ -527,35 +529,40 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 __syncthreads();
               }
               const int ccnt = min(cnt - base, R_DESC);
+              // Two stages per warp.  PRUNE: the current face's pixel rectangle is walked 32 pixels per pass; a pixel survives when the
+              // face's nearest vertex is not behind the keys it could displace; survivors (descriptor, pixel) are appended to a
+              // per-warp queue (ballot + popc, no divergence).  EVALUATE: as soon as 32 survivors are queued -- from whichever faces --
+              // they are evaluated with all lanes busy, each lane loading its own face from the descriptor.
+              const uint32_t qa = sb + SO_QUEUE + warp * (R_QUEUE * 4);
+              const unsigned ltmask = (1u << lane) - 1u;
+              int qn = 0;                                                 // queued survivors (warp-uniform)
               int kn = 0;
               if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);
-              kn = __shfl_sync(0xffffffffu, kn, 0);
-              while (kn < ccnt) {
-                const uint32_t da = sb + SO_SDESC + kn * 80;
-                if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);     // the next item: the atomic's latency hides behind this one
-                const float4 q0 = lds128<0>(da), q1 = lds128<16>(da), q2 = lds128<32>(da), q3 = lds128<48>(da), q4 = lds128<64>(da);
-                kn = __shfl_sync(0xffffffffu, kn, 0);
-                const int rect = __float_as_int(q3.y);
-                const int w = (rect >> 10) & 63;
-                if (w == 0) continue;                                     // binned conservatively: nothing of the face in this tile
-                const int c0 = rect & 31, r0 = (rect >> 5) & 31, h = (rect >> 16) & 63;
-                const int inner = __float_as_int(q3.z);
-                const int jc0 = inner & 31, jr0 = (inner >> 5) & 31;
-                const unsigned jw = (inner >> 10) & 63, jh = (inner >> 16) & 63;
-                const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y, z0 = q1.z, z1 = q1.w, z2 = q2.x;
-                const float inv_den = q2.y, il01 = q2.z, il02 = q2.w, il12 = q3.x;
-                const unsigned zbits = __float_as_uint(q3.w);
-                const int fcur = __float_as_int(q4.x);
-                const int magic = __float_as_int(q4.y);
-                if (lane == 0) { RS_ADD(0, 1); RS_ADD(1, w * h); }
-                const int npix = w * h;
-                const bool dpos = inv_den > 0.f;
-                // edge vectors exactly as the oracle rounds them
-                const float ex12 = MH_SUB(x2, x1), ey12 = MH_SUB(y2, y1);
-                const float ex20 = MH_SUB(x0, x2), ey20 = MH_SUB(y0, y2);
-                const float ex01 = MH_SUB(x1, x0), ey01 = MH_SUB(y1, y0);
-                for (int o = lane; o < npix; o += 32) {
+              bool more = true;
+              int npix = 0, ob = 0;                                       // current face: pixels of its rectangle, offset of the next pass
+              int c0 = 0, r0 = 0, w = 1, magic = 0, jc0 = 0, jr0 = 0, kd = 0;
+              unsigned jw = 0u, jh = 0u, zbits = 0u;
+              for (;;) {
+                while (qn < 32 && more) {
+                    if (ob >= npix) {                                     // next face of the chunk (dynamic hand-out, one index ahead)
+                        const int k = __shfl_sync(0xffffffffu, kn, 0);
+                        if (k >= ccnt) { more = false; break; }
+                        if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);
+                        const float4 q3 = lds128<48>(sb + SO_SDESC + k * 80);
+                        const int rect = __float_as_int(q3.x), inner = __float_as_int(q3.y);
+                        zbits = __float_as_uint(q3.z); magic = __float_as_int(q3.w);
+                        w = (rect >> 10) & 63;                            // 0: binned conservatively, nothing of the face in this tile
+                        c0 = rect & 31; r0 = (rect >> 5) & 31;
+                        npix = w * ((rect >> 16) & 63);
+                        jc0 = inner & 31; jr0 = (inner >> 5) & 31; jw = (inner >> 10) & 63; jh = (inner >> 16) & 63;
+                        kd = k; ob = 0;
+                        if (lane == 0 && npix) { RS_ADD(0, 1); RS_ADD(1, npix); }
+                        continue;
+                    }
                     RS_WARP(2);
+                    const int o = ob + lane;
+                    ob += 32;
+                    const bool valid = o < npix;
                     const int row = (o * magic) >> 16;
                     const int col = o - row * w;
                     const int lx = c0 + col, ly = r0 + row;
@@ -563,10 +570,32 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     // prune on the depth words of the keys alone (conservative on ties): no fragment of this face can be nearer
                     // than its nearest vertex; outside the inner rectangle it cannot be a silhouette fragment at all
                     const bool inner = ((unsigned)(lx - jc0) < jw) && ((unsigned)(ly - jr0) < jh);
-                    const bool pd = zbits <= lds32<SO_DKEY + 4>(ka);
-                    const bool ps = inner && (zbits <= lds32<SO_SKEY + 3 * SK_STRIDE + 4>(ka));
-                    if (!pd && !ps) continue;
-                    RS_ADD(3, 1); RS_WARP(4); if (inner) RS_ADD(10, 1);
+                    const bool pd = valid && (zbits <= lds32<SO_DKEY + 4>(ka));
+                    const bool ps = valid && inner && (zbits <= lds32<SO_SKEY + 3 * SK_STRIDE + 4>(ka));
+                    const bool surv = pd || ps;
+                    const unsigned bal = __ballot_sync(0xffffffffu, surv);
+                    if (surv) sts32<0>(qa + 4 * (qn + __popc(bal & ltmask)), (unsigned)kd | ((unsigned)lx << 10) | ((unsigned)ly << 15) | (pd ? 1u << 20 : 0u) | (ps ? 1u << 21 : 0u));
+                    qn += __popc(bal);
+                    if (surv) { RS_ADD(3, 1); if (inner) RS_ADD(10, 1); }
+                }
+                if (qn == 0) break;
+                __syncwarp();
+                const int nev = min(qn, 32);
+                qn -= nev;
+                if (lane < nev) {
+                    RS_WARP(4);
+                    const unsigned ent = lds32<0>(qa + 4 * (qn + lane));
+                    const uint32_t da = sb + SO_SDESC + (ent & 1023u) * 80;
+                    const int lx = (ent >> 10) & 31, ly = (ent >> 15) & 31;
+                    const bool pd = (ent >> 20) & 1u, ps = (ent >> 21) & 1u;
+                    const uint32_t ka = sb + 8 * (ly * TW + lx);
+                    const float4 q0 = lds128<0>(da), q1 = lds128<16>(da), q2 = lds128<32>(da);
+                    const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y, z0 = q1.z, z1 = q1.w, z2 = q2.x;
+                    const float inv_den = q2.y;
+                    // edge vectors exactly as the oracle rounds them
+                    const float ex12 = MH_SUB(x2, x1), ey12 = MH_SUB(y2, y1);
+                    const float ex20 = MH_SUB(x0, x2), ey20 = MH_SUB(y0, y2);
+                    const float ex01 = MH_SUB(x1, x0), ey01 = MH_SUB(y1, y0);
                     const float px = ldsf<SO_SPX>(sb + 4 * lx), py = ldsf<SO_SPY>(sb + 4 * ly);
                     const float dx0 = MH_SUB(px, x0), dy0 = MH_SUB(py, y0);
                     const float dx1 = MH_SUB(px, x1), dy1 = MH_SUB(py, y1);
@@ -578,35 +607,36 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     // depth first: a fragment that cannot displace a key needs no distance test
                     const float c0w = __saturatef(e0 * inv_den), c1w = __saturatef(e1 * inv_den), c2w = __saturatef(e2 * inv_den);
                     const float pz = __fdividef(c0w * z0 + c1w * z1 + c2w * z2, fmaxf(c0w + c1w + c2w, 1e-5f));
-                    if (!(pz >= 0.f)) continue;
+                    const float4 q4 = lds128<64>(da);                      // 1/|e12|^2, face
+                    const int fcur = __float_as_int(q4.y);
                     const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)fcur;
-                    const bool wd = pd && (key < lds64<SO_DKEY>(ka));
-                    const bool ws = ps && (key < lds64<SO_SKEY + 3 * SK_STRIDE>(ka));
-                    if (!wd && !ws) continue;
-                    RS_ADD(5, 1); RS_WARP(6);
-                    const bool inside = (e0 != 0.f) && (e1 != 0.f) && (e2 != 0.f) && ((e0 > 0.f) == dpos) && ((e1 > 0.f) == dpos) && ((e2 > 0.f) == dpos);
-                    bool vd = inside, vs = inside;
-                    if (!inside) {
-                        const float d01 = seg_dist_fast(dx0, dy0, ex01, ey01, il01, dx1, dy1);
-                        const float d02 = seg_dist_fast(dx0, dy0, -ex20, -ey20, il02, dx2, dy2);
-                        const float d12 = seg_dist_fast(dx1, dy1, ex12, ey12, il12, dx2, dy2);
-                        const float d = fminf(fminf(d01, d02), d12);
-                        if (d >= blur_d_hi) continue;
-                        vd = d < blur_d_lo; vs = d < blur_s_lo;
-                        if ((!vd) || (!vs && d < blur_s_hi)) {              // within 1e-5 of a threshold: decide on the exact distance
-                            MhFace fc; MhFrag fr;
-                            int iv[3];
-                            load_face(sv, P.faces, fcur, P.r_d, &fc, iv);
-                            mh_face_eval(fc, px, py, &fr);
-                            vd = fr.dist < P.blur_d; vs = fr.dist < P.blur_s;
+                    const bool wd = pd && (pz >= 0.f) && (key < lds64<SO_DKEY>(ka));
+                    const bool ws = ps && (pz >= 0.f) && (key < lds64<SO_SKEY + 3 * SK_STRIDE>(ka));
+                    if (wd || ws) {
+                        RS_ADD(5, 1); RS_WARP(6);
+                        const bool dpos = inv_den > 0.f;
+                        const bool inside = (e0 != 0.f) && (e1 != 0.f) && (e2 != 0.f) && ((e0 > 0.f) == dpos) && ((e1 > 0.f) == dpos) && ((e2 > 0.f) == dpos);
+                        bool vd = inside, vs = inside;
+                        if (!inside) {
+                            const float d01 = seg_dist_fast(dx0, dy0, ex01, ey01, q2.z, dx1, dy1);
+                            const float d02 = seg_dist_fast(dx0, dy0, -ex20, -ey20, q2.w, dx2, dy2);
+                            const float d12 = seg_dist_fast(dx1, dy1, ex12, ey12, q4.x, dx2, dy2);
+                            const float d = fminf(fminf(d01, d02), d12);
+                            vd = d < blur_d_lo; vs = d < blur_s_lo;
+                            if (d < blur_d_hi && ((!vd) || (!vs && d < blur_s_hi))) {   // within 1e-5 of a threshold: decide on the exact distance
+                                MhFace fc; MhFrag fr;
+                                int iv[3];
+                                load_face(sv, P.faces, fcur, P.r_d, &fc, iv);
+                                mh_face_eval(fc, px, py, &fr);
+                                vd = fr.dist < P.blur_d; vs = fr.dist < P.blur_s;
+                            }
+                            RS_ADD(9, 1);
                         }
+                        if (vd && wd) { RS_ADD(7, 1); atoms_min64<SO_DKEY>(ka, key); }
+                        if (vs && ws) { RS_ADD(8, 1); key_insert4(ka + SO_SKEY, key); }
                     }
-                    if (!inside) RS_ADD(9, 1);
-                    if (vd && wd) RS_ADD(7, 1);
-                    if (vs && ws) RS_ADD(8, 1);
-                    if (vd && wd) atoms_min64<SO_DKEY>(ka, key);
-                    if (vs && ws) key_insert4(ka + SO_SKEY, key);
                 }
+                __syncwarp();
               }
             }
             __syncthreads();
