@@ -535,60 +535,12 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
               // they are evaluated with all lanes busy, each lane loading its own face from the descriptor.
               const uint32_t qa = sb + SO_QUEUE + warp * (R_QUEUE * 4);
               const unsigned ltmask = (1u << lane) - 1u;
-              int qn = 0;                                                 // queued survivors (warp-uniform)
-              int kn = 0;
-              if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);
-              bool more = true;
-              int npix = 0, ob = 0;                                       // current face: pixels of its rectangle, offset of the next pass
-              int c0 = 0, r0 = 0, w = 1, magic = 0, jc0 = 0, jr0 = 0, kd = 0;
-              unsigned jw = 0u, jh = 0u, zbits = 0u;
-              for (;;) {
-                while (qn < 32 && more) {
-                    if (ob >= npix) {                                     // next face of the chunk (dynamic hand-out, one index ahead)
-                        const int k = __shfl_sync(0xffffffffu, kn, 0);
-                        if (k >= ccnt) { more = false; break; }
-                        if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);
-                        const float4 q3 = lds128<48>(sb + SO_SDESC + k * 80);
-                        const int rect = __float_as_int(q3.x), inner = __float_as_int(q3.y);
-                        zbits = __float_as_uint(q3.z); magic = __float_as_int(q3.w);
-                        w = (rect >> 10) & 63;                            // 0: binned conservatively, nothing of the face in this tile
-                        c0 = rect & 31; r0 = (rect >> 5) & 31;
-                        npix = w * ((rect >> 16) & 63);
-                        jc0 = inner & 31; jr0 = (inner >> 5) & 31; jw = (inner >> 10) & 63; jh = (inner >> 16) & 63;
-                        kd = k; ob = 0;
-                        if (lane == 0 && npix) { RS_ADD(0, 1); RS_ADD(1, npix); }
-                        continue;
-                    }
-                    RS_WARP(2);
-                    const int o = ob + lane;
-                    ob += 32;
-                    const bool valid = o < npix;
-                    const int row = (o * magic) >> 16;
-                    const int col = o - row * w;
-                    const int lx = c0 + col, ly = r0 + row;
-                    const uint32_t ka = sb + 8 * (ly * TW + lx);          // + SO_DKEY: depth key of the pixel, + SO_SKEY + s * SK_STRIDE: silhouette keys
-                    // prune on the depth words of the keys alone (conservative on ties): no fragment of this face can be nearer
-                    // than its nearest vertex; outside the inner rectangle it cannot be a silhouette fragment at all
-                    const bool inner = ((unsigned)(lx - jc0) < jw) && ((unsigned)(ly - jr0) < jh);
-                    const bool pd = valid && (zbits <= lds32<SO_DKEY + 4>(ka));
-                    const bool ps = valid && inner && (zbits <= lds32<SO_SKEY + 3 * SK_STRIDE + 4>(ka));
-                    const bool surv = pd || ps;
-                    const unsigned bal = __ballot_sync(0xffffffffu, surv);
-                    if (surv) sts32<0>(qa + 4 * (qn + __popc(bal & ltmask)), (unsigned)kd | ((unsigned)lx << 10) | ((unsigned)ly << 15) | (pd ? 1u << 20 : 0u) | (ps ? 1u << 21 : 0u));
-                    qn += __popc(bal);
-                    if (surv) { RS_ADD(3, 1); if (inner) RS_ADD(10, 1); }
-                }
-                if (qn == 0) break;
-                __syncwarp();
-                const int nev = min(qn, 32);
-                qn -= nev;
-                if (lane < nev) {
+              // EVALUATE one queued survivor: entry = pixel (10 bits) | descriptor << 10 | may displace the depth key << 20 | a silhouette key << 21
+              auto evaluate = [&](const unsigned ent) {
                     RS_WARP(4);
-                    const unsigned ent = lds32<0>(qa + 4 * (qn + lane));
-                    const uint32_t da = sb + SO_SDESC + (ent & 1023u) * 80;
-                    const int lx = (ent >> 10) & 31, ly = (ent >> 15) & 31;
+                    const uint32_t da = sb + SO_SDESC + ((ent >> 10) & 1023u) * 80;
+                    const uint32_t ka = sb + 8 * (ent & 1023u);           // + SO_DKEY: depth key of the pixel, + SO_SKEY + s * SK_STRIDE: silhouette keys
                     const bool pd = (ent >> 20) & 1u, ps = (ent >> 21) & 1u;
-                    const uint32_t ka = sb + 8 * (ly * TW + lx);
                     const float4 q0 = lds128<0>(da), q1 = lds128<16>(da), q2 = lds128<32>(da);
                     const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y, z0 = q1.z, z1 = q1.w, z2 = q2.x;
                     const float inv_den = q2.y;
@@ -596,7 +548,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const float ex12 = MH_SUB(x2, x1), ey12 = MH_SUB(y2, y1);
                     const float ex20 = MH_SUB(x0, x2), ey20 = MH_SUB(y0, y2);
                     const float ex01 = MH_SUB(x1, x0), ey01 = MH_SUB(y1, y0);
-                    const float px = ldsf<SO_SPX>(sb + 4 * lx), py = ldsf<SO_SPY>(sb + 4 * ly);
+                    const float px = ldsf<SO_SPX>(sb + 4 * (ent & 31u)), py = ldsf<SO_SPY>(sb + 4 * ((ent >> 5) & 31u));
                     const float dx0 = MH_SUB(px, x0), dy0 = MH_SUB(py, y0);
                     const float dx1 = MH_SUB(px, x1), dy1 = MH_SUB(py, y1);
                     const float dx2 = MH_SUB(px, x2), dy2 = MH_SUB(py, y2);
@@ -635,9 +587,60 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         if (vd && wd) { RS_ADD(7, 1); atoms_min64<SO_DKEY>(ka, key); }
                         if (vs && ws) { RS_ADD(8, 1); key_insert4(ka + SO_SKEY, key); }
                     }
+              };
+              int qn = 0;                                                 // queued survivors (warp-uniform)
+              int kn = 0;
+              if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);
+              for (;;) {
+                // next face of the chunk (dynamic hand-out, one index ahead)
+                const int k = __shfl_sync(0xffffffffu, kn, 0);
+                if (k >= ccnt) break;
+                if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);
+                const float4 q3 = lds128<48>(sb + SO_SDESC + k * 80);
+                const int rect = __float_as_int(q3.x), inner = __float_as_int(q3.y);
+                const unsigned zbits = __float_as_uint(q3.z);
+                const int magic = __float_as_int(q3.w);
+                const int w = (rect >> 10) & 63;                          // 0: binned conservatively, nothing of the face in this tile
+                const int c0 = rect & 31, r0 = (rect >> 5) & 31;
+                const int npix = w * ((rect >> 16) & 63);
+                const int jc0 = inner & 31, jr0 = (inner >> 5) & 31;
+                const unsigned jw = (inner >> 10) & 63, jh = (inner >> 16) & 63;
+                const unsigned ebase = (unsigned)k << 10;
+                if (lane == 0 && npix) { RS_ADD(0, 1); RS_ADD(1, npix); }
+                // PRUNE passes over the face's rectangle
+                for (int o = lane; o - lane < npix; o += 32) {
+                    RS_WARP(2);
+                    const bool valid = o < npix;
+                    const int row = (o * magic) >> 16;
+                    const int col = o - row * w;
+                    const int lx = c0 + col, ly = r0 + row;
+                    const int pix = ly * TW + lx;
+                    const uint32_t ka = sb + 8 * pix;
+                    // prune on the depth words of the keys alone (conservative on ties): no fragment of this face can be nearer
+                    // than its nearest vertex; outside the inner rectangle it cannot be a silhouette fragment at all
+                    const bool inner_px = ((unsigned)(lx - jc0) < jw) && ((unsigned)(ly - jr0) < jh);
+                    const bool pd = valid && (zbits <= lds32<SO_DKEY + 4>(ka));
+                    const bool ps = valid && inner_px && (zbits <= lds32<SO_SKEY + 3 * SK_STRIDE + 4>(ka));
+                    const unsigned bal = __ballot_sync(0xffffffffu, pd || ps);
+                    if (pd || ps) {
+                        unsigned ent = ebase | (unsigned)pix;
+                        if (pd) ent |= 1u << 20;
+                        if (ps) ent |= 1u << 21;
+                        sts32<0>(qa + 4 * (qn + __popc(bal & ltmask)), ent);
+                        RS_ADD(3, 1); if (inner_px) RS_ADD(10, 1);
+                    }
+                    qn += __popc(bal);
+                    if (qn >= 32) {                                       // a full batch
+                        __syncwarp();
+                        qn -= 32;
+                        evaluate(lds32<0>(qa + 4 * (qn + lane)));
+                        __syncwarp();
+                    }
                 }
-                __syncwarp();
               }
+              __syncwarp();
+              if (lane < qn) evaluate(lds32<0>(qa + 4 * lane));           // the rest
+              __syncwarp();
             }
             __syncthreads();
             PROF(3);
