@@ -167,6 +167,53 @@ __device__ __forceinline__ void key_insert4(uint32_t a /* slot 0 of the pixel */
     atoms_min64<3 * SK_STRIDE>(a, x);
 }
 
+// P3 on single-chunk tiles: the same fragment values / silhouette backward from the tile's (face, tile) descriptor that is still in
+// shared memory -- no index or vertex gathers, no reciprocals (the descriptor holds the ones P2 used)
+__device__ __forceinline__ void frag_values_desc(uint32_t da, float px, float py, float* pz, float* sd) {
+    const float4 q0 = lds128<0>(da), q1 = lds128<16>(da), q2 = lds128<32>(da);
+    const float x0 = q0.x, y0 = q0.y, x1 = q0.z, y1 = q0.w, x2 = q1.x, y2 = q1.y, z0 = q1.z, z1 = q1.w, z2 = q2.x;
+    const float inv_den = q2.y;
+    const float dx0 = px - x0, dy0 = py - y0, dx1 = px - x1, dy1 = py - y1, dx2 = px - x2, dy2 = py - y2;
+    const float ex12 = x2 - x1, ey12 = y2 - y1, ex20 = x0 - x2, ey20 = y0 - y2, ex01 = x1 - x0, ey01 = y1 - y0;
+    const float e0 = MH_SUB(MH_MUL(dx1, ey12), MH_MUL(dy1, ex12));
+    const float e1 = MH_SUB(MH_MUL(dx2, ey20), MH_MUL(dy2, ex20));
+    const float e2 = MH_SUB(MH_MUL(dx0, ey01), MH_MUL(dy0, ex01));
+    const bool dpos = inv_den > 0.f;
+    const bool inside = (e0 != 0.f) && (e1 != 0.f) && (e2 != 0.f) && ((e0 > 0.f) == dpos) && ((e1 > 0.f) == dpos) && ((e2 > 0.f) == dpos);
+    const float c0 = __saturatef(e0 * inv_den), c1 = __saturatef(e1 * inv_den), c2 = __saturatef(e2 * inv_den);
+    *pz = (c0 * z0 + c1 * z1 + c2 * z2) / fmaxf(c0 + c1 + c2, 1e-5f);
+    const float d01 = seg_dist_fast(dx0, dy0, ex01, ey01, q2.z, dx1, dy1);
+    const float d02 = seg_dist_fast(dx0, dy0, -ex20, -ey20, q2.w, dx2, dy2);
+    const float d12 = seg_dist_fast(dx1, dy1, ex12, ey12, ldsf<64>(da), dx2, dy2);
+    const float d = fminf(fminf(d01, d02), d12);
+    *sd = inside ? -d : d;
+}
+
+__device__ __forceinline__ void grad_add(float* p, float v);
+
+__device__ __forceinline__ void sil_grad_desc(float* sg, uint32_t da, float px, float py, float gd) {
+    const float4 q0 = lds128<0>(da), q1 = lds128<16>(da), q2 = lds128<32>(da), q4 = lds128<64>(da);
+    const float vx[3] = {q0.x, q0.z, q1.x}, vy[3] = {q0.y, q0.w, q1.y};
+    const float il[3] = {q2.z, q2.w, q4.x};                              // edges 01, 02, 12
+    const unsigned i01 = __float_as_uint(q4.z);
+    const int iv[3] = {(int)(i01 & 0xffffu), (int)(i01 >> 16), __float_as_int(q4.w)};
+    float best = INFINITY, bt = 0.f, bqx = 0.f, bqy = 0.f;
+    int ia = 0, ib = 1;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const int a = (e == 2) ? 1 : 0, b = (e == 0) ? 1 : 2;
+        const float bax = vx[b] - vx[a], bay = vy[b] - vy[a];
+        const float t = (il[e] == 0.f) ? 1.0f : __saturatef((bax * (px - vx[a]) + bay * (py - vy[a])) * il[e]);
+        const float qx = px - (vx[a] + t * bax), qy = py - (vy[a] + t * bay);
+        const float d = qx * qx + qy * qy;
+        if (d < best) { best = d; bt = t; bqx = qx; bqy = qy; ia = iv[a]; ib = iv[b]; }
+    }
+    const float g = -2.0f * gd;
+    const float ga = g * (1.0f - bt), gb = g * bt;
+    if (ga != 0.f) { grad_add(&sg[3 * ia], ga * bqx); grad_add(&sg[3 * ia + 1], ga * bqy); }
+    if (gb != 0.f) { grad_add(&sg[3 * ib], gb * bqx); grad_add(&sg[3 * ib + 1], gb * bqy); }
+}
+
 // -DMH_RSTATS: (face, pixel)-pair statistics of P2 in slots 8.. of the profile buffer (instrumented build only)
 #ifdef MH_RSTATS
 #define RS_DECL long long rs_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
@@ -218,7 +265,7 @@ __device__ __forceinline__ void grad_add(float* p, float v) {
 
 // Descriptor of one (face, tile) item -- everything P2 needs, computed ONCE by one thread (the tile's faces are spread over
 // the 1024 threads) instead of redundantly by the 32 lanes of the warp that rasterises the face:
-//   d0 = x0 y0 x1 y1 | d1 = x2 y2 z0 z1 | d2 = z2 1/den 1/|e01|^2 1/|e02|^2 | d3 = rect inner zbits magic | d4 = 1/|e12|^2 face - -
+//   d0 = x0 y0 x1 y1 | d1 = x2 y2 z0 z1 | d2 = z2 1/den 1/|e01|^2 1/|e02|^2 | d3 = rect inner zbits magic | d4 = 1/|e12|^2 face i0|i1<<16 i2
 // rect  = c0 | r0 << 5 | w << 10 | h << 16 : the face's pixel rectangle inside the tile, EXACT for the oracle's bbox test (bbox
 //         inflated by sqrt(blur) of the depth raster), so the pair loop needs no per-pixel bbox test; w = 0: nothing in this tile
 // inner = same packing: the only pixels where the face can be a SILHOUETTE fragment (bbox inflated by the silhouette radius x 1.001
@@ -253,7 +300,7 @@ __device__ __forceinline__ void make_desc(const RenderParams& P, const float* sv
     d[1] = make_float4(x2, y2, z0, z1);
     d[2] = make_float4(z2, __frcp_rn(den), l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), l02 <= MH_KEPS ? 0.f : __frcp_rn(l02));
     d[3] = make_float4(__int_as_float(rect), __int_as_float(inner), __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))), __int_as_float((65536 + w - 1) / w));
-    d[4] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), __int_as_float(f), 0.f, 0.f);
+    d[4] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), __int_as_float(f), __uint_as_float((unsigned)i0 | ((unsigned)i1 << 16)), __int_as_float(i2));
 }
 
 // Backward of the unsigned squared edge distance of one silhouette fragment: d = |p - a - t (b - a)|^2 on the nearest edge
@@ -561,7 +608,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                     const float pz = __fdividef(c0w * z0 + c1w * z1 + c2w * z2, fmaxf(c0w + c1w + c2w, 1e-5f));
                     const float4 q4 = lds128<64>(da);                      // 1/|e12|^2, face
                     const int fcur = __float_as_int(q4.y);
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)fcur;
+                    // key: depth | face | descriptor -- ordered by depth, then face (the oracle's tie-break); the descriptor index rides along for P3
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | ((unsigned)fcur << 10) | ((ent >> 10) & 1023u);
                     const bool wd = pd && (pz >= 0.f) && (key < lds64<SO_DKEY>(ka));
                     const bool ws = ps && (pz >= 0.f) && (key < lds64<SO_SKEY + 3 * SK_STRIDE>(ka));
                     if (wd || ws) {
@@ -649,10 +697,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             const int xi = ox + (tid & (TW - 1)), yi = oy + (tid >> 5);
             const float pxn = spx[tid & (TW - 1)], pyn = spy[tid >> 5];
             float dz = -1.0f; int df = -1;
+            const bool single = cnt <= R_DESC;                           // the tile's descriptors are all still in shared memory
             if ((pflags & 1u) && dkey[tid] != KEY_EMPTY) {
-                df = (int)(dkey[tid] & 0xffffffffull);
+                const unsigned lo = (unsigned)(dkey[tid] & 0xffffffffull);
+                df = (int)(lo >> 10);
                 float sdu;
-                frag_values(sv, P.faces, df, pxn, pyn, &dz, &sdu);
+                if (single) frag_values_desc(sb + SO_SDESC + (lo & 1023u) * 80, pxn, pyn, &dz, &sdu);
+                else frag_values(sv, P.faces, df, pxn, pyn, &dz, &sdu);
             }
             int sf[4]; float sd[4]; float pk[4];
             float prod = 1.0f;
@@ -661,9 +712,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const unsigned long long k = (pflags & 2u) ? skey[s * R_THREADS + tid] : KEY_EMPTY;
                 sf[s] = -1; sd[s] = 0.f; pk[s] = 0.f;
                 if (k != KEY_EMPTY) {
-                    sf[s] = (int)(k & 0xffffffffull);
+                    sf[s] = (int)(k & 0xffffffffull);                     // face << 10 | descriptor
                     float pzu;
-                    frag_values(sv, P.faces, sf[s], pxn, pyn, &pzu, &sd[s]);
+                    if (single) frag_values_desc(sb + SO_SDESC + (sf[s] & 1023) * 80, pxn, pyn, &pzu, &sd[s]);
+                    else frag_values(sv, P.faces, sf[s] >> 10, pxn, pyn, &pzu, &sd[s]);
                     pk[s] = 1.0f / (1.0f + expf(sd[s] / P.sigma));        // sigmoid(-signed / sigma)
                 }
                 prod = prod * (1.0f - pk[s]);
@@ -709,7 +761,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         const float gsd = ga * others * (-pk[s] * (1.0f - pk[s]) / P.sigma);
                         const float gdist = sd[s] < 0.f ? -gsd : gsd;     // signed = inside ? -dist : dist
                         if (gdist == 0.f) continue;
-                        sil_grad(sg, sv, P.faces, sf[s], pxn, pyn, gdist);
+                        if (single) sil_grad_desc(sg, sb + SO_SDESC + (sf[s] & 1023) * 80, pxn, pyn, gdist);
+                        else sil_grad(sg, sv, P.faces, sf[s] >> 10, pxn, pyn, gdist);
                     }
                 }
             }
