@@ -8,16 +8,23 @@
 // per-person-frame host sync (:450-475, losses.py:33-40) and PyTorch3D's atomic-add raster backward.
 // PyTorch3D semantics: SURVEY.md Appendix A / oracle/raster.py (parity unpinned upstream).
 //
-// One persistent CTA per SM walks the person-frames.  Per body:
+// One persistent CTA (1024 threads) per SM pulls person-frames from an atomic counter, largest first.  Per body:
 //   P0  the body's 6890 absolute vertices are staged into shared memory with one TMA bulk copy
 //       (cp.async.bulk + mbarrier) and converted in place to NDC;
-//   P1  faces are binned to 16x16-pixel tiles (count, scan, fill) - lists in a per-CTA global scratch;
-//   P2  every tile: each thread owns one pixel and walks the tile's faces (staged 128 at a time in shared
-//       memory), keeping the nearest depth fragment and the 4 nearest silhouette fragments; both rasters
-//       share one face evaluation;
-//   P3  per pixel: depth-loss sums, silhouette alpha, loss and its backward (shared-memory atomics into a
-//       per-body gradient array); depth winners go to a compact list because their gradient scale needs
-//       the whole-image sums;
+//   P1  faces are binned to 32x32-pixel tiles anchored at the body's bounding box; the tile lists (face ids in a
+//       per-CTA global scratch) are counting-sorted by (tile, depth slab) in one fill pass, near -> far;
+//   per tile:
+//   T0  every thread owns one pixel: the instance bit planes decide whether the loss needs a depth fragment / silhouette
+//       fragments there (keys of pixels that need nothing start at 0 and prune every face); one thread per face of the
+//       tile builds the (face, tile) descriptor in shared memory (exact pixel rectangle, reciprocals, depth bound);
+//   P2  PRUNE: a warp walks the pixel rectangle of one face, 32 pixels per pass, and appends the pixels where the face's
+//       nearest vertex is not behind the keys it could displace to a per-warp queue; EVALUATE: every 32 queued survivors
+//       -- from whichever faces -- are evaluated with all lanes busy (depth first, distance test only if a key would be
+//       displaced) and update the per-pixel keys (depth | face): one 64-bit min for the nearest depth fragment, a 4-slot
+//       concurrent sorted insertion for the four nearest silhouette fragments; both rasters share one evaluation;
+//   P3  per pixel: values of the <= 5 winning fragments from the descriptors, depth-loss sums, silhouette alpha, loss and
+//       its backward (fire-and-forget reductions into a per-CTA gradient row that stays in L2); depth winners go to a
+//       compact list because their gradient scale needs the whole-image sums;
 //   P4  block reduction of the sums, depth backward over the winner list;
 //   P5  NDC gradients are chained to camera space and added to dL/dV.
 // Everything outside the tiles a body touches contributes a mesh-independent constant that the prepass
@@ -28,9 +35,7 @@
 #define TH 32                 // tile height (pixels)
 #define R_THREADS 1024        // one thread per tile pixel in the per-pixel phases
 #define R_MAXBINS 1024
-#define R_CHUNK 256
 #define R_NSLAB 64            // depth slabs (at most): the tile lists are ordered near -> far so that later faces are pruned early
-#define R_ITEMS (R_CHUNK * (TW * TH / 32))   // 32-pixel groups of one staged chunk (a face covers at most the whole tile)
 #define KEY_EMPTY 0xffffffffffffffffull
 #define R_DESC 1024               // (face, tile) descriptors staged per chunk (5 float4 each)
 #define R_QUEUE 64                // survivor queue entries per warp (fewer than 32 wait, a pass adds at most 32)
@@ -71,20 +76,6 @@ struct RenderParams {
     int maxbins;
     long long* prof;              // optional: per-phase cycle counters (8 per CTA)
 };
-
-// face record staged per tile: everything the (face, pixel) pair evaluation needs
-struct FaceRec {
-    float x0, y0, x1, y1, x2, y2, z0, z1, z2;
-    float den, inv_den;
-    float il01, il02, il12;           // 1 / |edge|^2, 0 when degenerate
-    float bxmin, bxmax, bymin, bymax; // exact bbox inflated by sqrt(blur) (oracle's test)
-    int pxy;                          // pixel rectangle inside the tile: col0 | row0 << 5 | w << 9 | magic(w) << 15
-    int fid;
-    int npix;                         // pixels of the rectangle
-    unsigned zbits;                   // bits of a lower bound of every fragment depth of the face (its nearest vertex)
-};
-
-__constant__ int c_magic[TW + 1];      // ceil(65536 / w): row = (o * magic) >> 16 for o < 512
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -542,16 +533,18 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             // depth fragment (outside the eroded instance mask, optimizer.py:434-438) or no silhouette fragments (hidden by the
             // masks of nearer persons or gated off, :459-475) gets key 0 = "nothing can improve it": P2 prunes every face there
             unsigned pflags;                                              // bit 0 need depth, 1 need silhouette, 2 seg bit, 3 in image
-            {
-                const int xip = ox + (tid & (TW - 1)), yip = oy + (tid >> 5);
-                const bool inimg = (xip < P.W) && (yip < P.H);
-                pflags = inimg ? 0xbu : 0u;
-                if (MODE == 0 && inimg) {
-                    const size_t pidx = plane + (size_t)yip * P.W + xip;
-                    const uint32_t cb = P.cbits[pidx], eb = P.ebits[pidx];
-                    pflags = 8u | ((pvalid && ((eb >> n) & 1u)) ? 1u : 0u) | ((gate && ((cb & pre) == 0u)) ? 2u : 0u) | (((cb >> n) & 1u) << 2);
-                }
+            const int xip = ox + (tid & (TW - 1)), yip = oy + (tid >> 5);
+            const bool inimg = (xip < P.W) && (yip < P.H);
+            uint32_t cb = 0u, eb = 0u;
+            if (MODE == 0 && inimg) {                                     // issued first: the plane loads fly while the descriptors are built
+                const size_t pidx = plane + (size_t)yip * P.W + xip;
+                cb = P.cbits[pidx]; eb = P.ebits[pidx];
             }
+            const int txmax = min(TW, P.W - ox) - 1, tymax = min(TH, P.H - oy) - 1;     // last valid local column / row
+            // ---- descriptors of the first chunk of the tile's faces: one thread per face ----
+            if (tid < cnt) make_desc(P, sv, binlist[off + tid], ox, oy, txmax, tymax, sdesc + tid * 5);
+            pflags = inimg ? 0xbu : 0u;
+            if (MODE == 0 && inimg) pflags = 8u | ((pvalid && ((eb >> n) & 1u)) ? 1u : 0u) | ((gate && ((cb & pre) == 0u)) ? 2u : 0u) | (((cb >> n) & 1u) << 2);
             const bool need_d = pflags & 1u, need_s = pflags & 2u;
             dkey[tid] = need_d ? KEY_EMPTY : 0ull;
             if (tid == 0) sint[40] = 0;
@@ -560,9 +553,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             skey[3 * R_THREADS + tid] = need_s ? KEY_EMPTY : 0ull;
             if (tid < TW) spx[tid] = (ox + tid < P.W) ? P.pix_x[ox + tid] : 0.f;
             if (tid >= 64 && tid < 64 + TH) spy[tid - 64] = (oy + tid - 64 < P.H) ? P.pix_y[oy + tid - 64] : 0.f;
-            const int txmax = min(TW, P.W - ox) - 1, tymax = min(TH, P.H - oy) - 1;     // last valid local column / row
-            // ---- descriptors of the first chunk of the tile's faces: one thread per face ----
-            if (tid < cnt) make_desc(P, sv, binlist[off + tid], ox, oy, txmax, tymax, sdesc + tid * 5);
             const int tile_needed = __syncthreads_or(need_d || need_s);
             PROF(2);
             if (!tile_needed) continue;                                   // uniform: nothing the loss reads in this tile
@@ -856,12 +846,6 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(float));
     { const char* v = getenv("MH_RENDER_NSLAB"); rs->nslab = v ? std::min(std::max(atoi(v), 1), 256) : R_NSLAB; }     // development switch
     rs->prof = nullptr;
-    {
-        int magic[TW + 1];
-        magic[0] = 0;
-        for (int w = 1; w <= TW; ++w) magic[w] = (65536 + w - 1) / w;
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_magic, magic, sizeof(magic));
-    }
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
     rs->smem = (size_t)SO_END + 128;
     e = cudaFuncSetAttribute(k_render<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs->smem);

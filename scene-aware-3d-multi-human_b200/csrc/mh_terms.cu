@@ -165,74 +165,108 @@ __global__ void k_velocity(const float* __restrict__ trans_all, int T, int N, in
 
 // -------------------------------------------------------------------------------------------------
 // Contact term: streaming exact top-32 nearest scene points of the lowest vertex (optimizer.py:487-506).
-// One CTA per local person-frame.  Pass A: per-thread minima -> the 32nd smallest of them bounds the 32nd
-// nearest distance; pass B collects every point under the bound; the 32 nearest are ranked exactly by
-// (distance, index).  No distance matrix, no sort over M.
+// One CTA per KNN_Q consecutive local person-frames: every scene point is loaded once and tested against all of them (the
+// cloud is L2-resident; one CTA per person-frame is L2-bandwidth bound).  KNN_Q is chosen so that the grid still fills the GPU.  Pass A: per-thread minima -> the 32nd
+// smallest of them bounds the 32nd nearest distance; pass B collects every point under the bound; the 32 nearest are ranked
+// exactly by (distance, index).  No distance matrix, no sort over M.
 #define KNN_THREADS 256
-#define KNN_CAP 2048
-__device__ __forceinline__ float d2_point(const float* __restrict__ p, float x, float y, float z) {
+#define KNN_CAP 512
+__device__ __forceinline__ float d2_point(float p0, float p1, float p2, float x, float y, float z) {
     // sum(pow(pcd - low, 2), -1): three squares added in coordinate order
-    const float a = p[0] - x, b = p[1] - y, c = p[2] - z;
+    const float a = p0 - x, b = p1 - y, c = p2 - z;
     return (a * a + b * b) + c * c;
 }
 
+template <int KNN_Q>
 __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict__ verts, const int* __restrict__ lowidx,
-                                                         const float* __restrict__ scene, int64_t M, int N, float coef,
+                                                         const float* __restrict__ scene, int64_t M, int N, int TN, float coef,
                                                          float* __restrict__ contact, float* __restrict__ g_trans,
                                                          float* __restrict__ losses) {
-    __shared__ float smin[KNN_THREADS];
-    __shared__ float cd[KNN_CAP];
-    __shared__ int ci[KNN_CAP];
-    __shared__ int sel[MH_KNN];
-    __shared__ int scount;
-    __shared__ float stau, slo, shi;
-    const int i = blockIdx.x, tid = threadIdx.x;
-    const size_t b = (size_t)i + N;
-    const int li = lowidx[b];
-    const float x = verts[b * MH_LD3V + 3 * li], y = verts[b * MH_LD3V + 3 * li + 1], z = verts[b * MH_LD3V + 3 * li + 2];
-    float mn = INFINITY;
-    for (int64_t p = tid; p < M; p += KNN_THREADS) mn = fminf(mn, d2_point(scene + 3 * p, x, y, z));
-    smin[tid] = mn;
+    __shared__ float smin[KNN_Q][KNN_THREADS];
+    __shared__ float cd[KNN_Q][KNN_CAP];
+    __shared__ int ci[KNN_Q][KNN_CAP];
+    __shared__ int sel[KNN_Q][MH_KNN];
+    __shared__ int scount[KNN_Q];
+    __shared__ float stau[KNN_Q], slo[KNN_Q], shi[KNN_Q];
+    __shared__ int sdone[KNN_Q];
+    const int i0 = blockIdx.x * KNN_Q, tid = threadIdx.x;
+    const int nq = min(KNN_Q, TN - i0);
+    float x[KNN_Q], y[KNN_Q], z[KNN_Q], mn[KNN_Q];
+#pragma unroll
+    for (int q = 0; q < KNN_Q; ++q) {
+        const size_t b = (size_t)min(i0 + q, TN - 1) + N;
+        const int li = lowidx[b];
+        x[q] = verts[b * MH_LD3V + 3 * li]; y[q] = verts[b * MH_LD3V + 3 * li + 1]; z[q] = verts[b * MH_LD3V + 3 * li + 2];
+        mn[q] = INFINITY;
+    }
+    for (int64_t p = tid; p < M; p += KNN_THREADS) {
+        const float p0 = scene[3 * p], p1 = scene[3 * p + 1], p2 = scene[3 * p + 2];
+#pragma unroll
+        for (int q = 0; q < KNN_Q; ++q) mn[q] = fminf(mn[q], d2_point(p0, p1, p2, x[q], y[q], z[q]));
+    }
+#pragma unroll
+    for (int q = 0; q < KNN_Q; ++q) smin[q][tid] = mn[q];
+    if (tid < KNN_Q) { scount[tid] = 0; sdone[tid] = tid >= nq; }
     __syncthreads();
-    int rank = 0;
-    for (int j = 0; j < KNN_THREADS; ++j) rank += (smin[j] < mn) || (smin[j] == mn && j < tid);
-    if (rank == MH_KNN - 1) { stau = mn; slo = 0.f; shi = mn; }
-    if (tid == 0) scount = 0;
+#pragma unroll
+    for (int q = 0; q < KNN_Q; ++q) {
+        int rank = 0;
+        for (int j = 0; j < KNN_THREADS; ++j) rank += (smin[q][j] < mn[q]) || (smin[q][j] == mn[q] && j < tid);
+        if (rank == MH_KNN - 1) { stau[q] = mn[q]; slo[q] = 0.f; shi[q] = mn[q]; }
+    }
     __syncthreads();
     for (int iter = 0; iter < 64; ++iter) {
-        const float tau = stau;
+        float tau[KNN_Q];
+        bool act[KNN_Q];
+#pragma unroll
+        for (int q = 0; q < KNN_Q; ++q) { tau[q] = stau[q]; act[q] = !sdone[q]; }
         for (int64_t p = tid; p < M; p += KNN_THREADS) {
-            const float dd = d2_point(scene + 3 * p, x, y, z);
-            if (dd <= tau) {
-                const int q = atomicAdd(&scount, 1);
-                if (q < KNN_CAP) { cd[q] = dd; ci[q] = (int)p; }
+            const float p0 = scene[3 * p], p1 = scene[3 * p + 1], p2 = scene[3 * p + 2];
+#pragma unroll
+            for (int q = 0; q < KNN_Q; ++q) {
+                const float dd = d2_point(p0, p1, p2, x[q], y[q], z[q]);
+                if (act[q] && dd <= tau[q]) {
+                    const int k = atomicAdd(&scount[q], 1);
+                    if (k < KNN_CAP) { cd[q][k] = dd; ci[q][k] = (int)p; }
+                }
             }
         }
         __syncthreads();
-        const int cnt = scount;
-        if (cnt >= MH_KNN && cnt <= KNN_CAP) break;
-        __syncthreads();
-        if (tid == 0) {          // bisection on the bound (only reached with > KNN_CAP near-ties)
-            if (cnt > KNN_CAP) shi = tau; else slo = tau;
-            stau = 0.5f * (slo + shi);
-            scount = 0;
+        bool all = true;
+        if (tid < KNN_Q && !sdone[tid]) {
+            const int cnt = scount[tid];
+            if (cnt >= MH_KNN && cnt <= KNN_CAP) sdone[tid] = 1;
+            else {               // bisection on the bound (only reached with > KNN_CAP near-ties)
+                if (cnt > KNN_CAP) shi[tid] = stau[tid]; else slo[tid] = stau[tid];
+                stau[tid] = 0.5f * (slo[tid] + shi[tid]);
+                scount[tid] = 0;
+            }
         }
         __syncthreads();
+#pragma unroll
+        for (int q = 0; q < KNN_Q; ++q) all = all && sdone[q];
+        if (all) break;
     }
-    const int cnt = min(scount, KNN_CAP);
-    for (int a = tid; a < cnt; a += KNN_THREADS) {
-        const float da = cd[a];
-        const int ia = ci[a];
-        int r = 0;
-        for (int j = 0; j < cnt; ++j) r += (cd[j] < da) || (cd[j] == da && ci[j] < ia);
-        if (r < MH_KNN) sel[r] = ia;
+    for (int q = 0; q < nq; ++q) {
+        const int cnt = min(scount[q], KNN_CAP);
+        for (int a = tid; a < cnt; a += KNN_THREADS) {
+            const float da = cd[q][a];
+            const int ia = ci[q][a];
+            int r = 0;
+            for (int j = 0; j < cnt; ++j) r += (cd[q][j] < da) || (cd[q][j] == da && ci[q][j] < ia);
+            if (r < MH_KNN) sel[q][r] = ia;
+        }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < nq) {
+        const int q = tid, i = i0 + q;
         float my = 0.f;
-        for (int r = 0; r < MH_KNN; ++r) my += scene[3 * (size_t)sel[r] + 1];
+        for (int r = 0; r < MH_KNN; ++r) my += scene[3 * (size_t)sel[q][r] + 1];
         my *= (1.0f / MH_KNN);
-        const float cdv = my - y;                               // contact_dist_vertical (:501)
+        float yq = 0.f;
+#pragma unroll
+        for (int k = 0; k < KNN_Q; ++k) if (k == q) yq = y[k];
+        const float cdv = my - yq;                              // contact_dist_vertical (:501)
         const float r = cdv + 0.02f;                            // target.y = T.y + cdv + 0.02 (:502-503)
         atomicAdd(losses + MH_L_CONTACT, fabsf(r));
         g_trans[(size_t)i * 3 + 1] += coef * -signf(r);         // d|T - target|/dT.y with the target detached (:504-506)
@@ -303,7 +337,11 @@ int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) 
                                                      g_trans, losses);
     MH_LAUNCHED(c);
     if (c->M > 0) {
-        k_contact<<<TN, KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, c->c.reg_contact, c->contact, g_trans, losses);
+        const int waves2 = 2 * c->num_sms;                             // person-frames per CTA: as many as keep two waves of CTAs
+        if (TN >= 8 * waves2) k_contact<8><<<mh_cdiv(TN, 8), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses);
+        else if (TN >= 4 * waves2) k_contact<4><<<mh_cdiv(TN, 4), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses);
+        else if (TN >= 2 * waves2) k_contact<2><<<mh_cdiv(TN, 2), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses);
+        else k_contact<1><<<TN, KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses);
         MH_LAUNCHED(c);
         k_foot<<<mh_cdiv(d.T, d.B), 128, 0, st>>>(c->verts, c->lowidx, c->contact, d.T, d.N, d.B, c->c.reg_foot_sliding, c->dverts, losses);
         MH_LAUNCHED(c);
