@@ -230,6 +230,9 @@ int mh_render_profile(mh_ctx* ctx, int32_t on, long long* out32_host);
 /* testing aid: REDUCE the render capacities (0 keeps a value) so that small inputs reach the coarse-binning path (maxbins)
  * and the MH_E_CAPACITY paths (tile-list entries per body, depth-winner entries per body); clears the capacity flag */
 int mh_debug_set_render_caps(mh_ctx* ctx, int32_t maxbins, int32_t bincap, int32_t wcap);
+/* testing aid: the pose-corrective contraction alone, C (M, 20672) = A (M, 192) . posedirs, HOST pointers, blocking; use_tc = 1 runs
+ * the tcgen05 / TMEM kernel (3 x TF32), 0 the FP32 SIMT kernel (smpl.py:549-553 without the shape term) */
+int mh_debug_gemm_fwd(mh_ctx* ctx, const float* A_host, float* C_host, int32_t M, int32_t use_tc);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t mh_launch_count(const mh_ctx* ctx);
 

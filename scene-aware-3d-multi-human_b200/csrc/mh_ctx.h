@@ -142,6 +142,8 @@ struct MhSmplArgs {
     int* lowidx;               // (nbodies) or null
 };
 int mh_smpl_forward_run(mh_ctx* c, const MhSmplArgs& a, cudaStream_t st);
+int mh_gemm_fwd_tc(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape,
+                   cudaStream_t st);          // mh_gemm_tc.cu: tcgen05 / TMEM, 3 x TF32
 int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st);
 
 // mh_terms.cu

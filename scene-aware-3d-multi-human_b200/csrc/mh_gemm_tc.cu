@@ -1,0 +1,217 @@
+// Pose-corrective contraction on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-level accuracy by a 3 x TF32 split.
+//
+//   C[m][n] = sum_k A[m][k] B[k][n] + Vs[row(m)][n]        M = bodies, N = MH_LD3V (20672), K = MH_KPF (192)
+//
+// Reference path replaced: `v_posed = v_shaped + matmul(pose_feature, posedirs)` (mhmocap/smpl.py:549-553) -- one of the two
+// genuinely dense contractions of the hot path (hard part 2).
+//
+// One CTA per 128 x 256 output tile.  K is walked in chunks of 32 through two shared-memory stages: all threads load the
+// chunk of A and B (both staged K-major) from global memory, split every value into x_hi = tf32(x), x_lo = tf32(x - x_hi) and
+// store both halves in the canonical no-swizzle UMMA layouts (8 x 16-byte core matrices); ONE thread then issues, per K = 8
+// step, the three products hi*hi + hi*lo + lo*hi as `tcgen05.mma.cta_group::1.kind::tf32` into the same 128-lane x 256-column
+// fp32 accumulator in TMEM and commits the stage to an mbarrier, so the loads of the next chunk overlap the MMAs.  The epilogue
+// reads the accumulator with `tcgen05.ld` (one TMEM lane = one body row per thread), adds v_shaped and writes v_posed.
+// The dropped lo*lo term is 2^-22 relative: the result differs from the fp32 FMA chain by < 1e-8 m.
+#include "mh_ctx.h"
+
+#define TC_BM 128
+#define TC_BN 256
+#define TC_BK 32
+#define TC_THREADS 256
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                        // 16 KB: one half (hi or lo) of an A chunk
+constexpr int TC_B_BYTES = TC_BK * TC_BN * 4;                        // 32 KB: one half of a B chunk
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;      // A_hi A_lo B_hi B_lo
+constexpr int TC_SMEM_BYTES = 2 * TC_STAGE_BYTES;
+constexpr int TC_TMEM_COLS = 256;
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle: start address, leading / stride byte offsets (all >> 4), descriptor version 1
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+__device__ __forceinline__ void tc_split(float x, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+    lo = __uint_as_float(l);
+}
+
+__device__ __forceinline__ void tc_split4(const float4 v, float4& hi, float4& lo) {
+    tc_split(v.x, hi.x, lo.x); tc_split(v.y, hi.y, lo.y); tc_split(v.z, hi.z, lo.z); tc_split(v.w, hi.w, lo.w);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_fwd_tc(const float* __restrict__ Am, const float* __restrict__ Bm,
+                                                               const float* __restrict__ Vs, float* __restrict__ C, int M, int Npers,
+                                                               int per_body_shape) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ __align__(8) unsigned long long bars[3];                // stage 0 free, stage 1 free, accumulator complete
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
+    const int ncols = min(TC_BN, MH_LD3V - n0);                        // 256, 192 on the last column tile
+    const uint32_t sbase = tc_smem_u32(tc_smem);
+    const uint32_t bar0 = tc_smem_u32(&bars[0]);
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    // instruction descriptor: D = f32, A = B = tf32, both K-major, N, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    uint32_t phase[2] = {0u, 0u};
+    constexpr int NIT = MH_KPF / TC_BK;
+    for (int it = 0; it < NIT; ++it) {
+        const int s = it & 1;
+        unsigned char* st = tc_smem + s * TC_STAGE_BYTES;
+        if (it >= 2) { tc_wait(bar0 + 8 * s, phase[s]); phase[s] ^= 1u; }          // the MMAs that read this stage are done
+        // A chunk: 128 rows x 32 k, K-major: 16-byte unit (row, k4) at k4 * 128 + row
+        float4* Ah = reinterpret_cast<float4*>(st);
+        float4* Al = reinterpret_cast<float4*>(st + TC_A_BYTES);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = tid + TC_THREADS * i;
+            const int row = id & (TC_BM - 1), k4 = id >> 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + row < M) v = *reinterpret_cast<const float4*>(Am + (size_t)(m0 + row) * MH_KPF + it * TC_BK + k4 * 4);
+            float4 hi, lo;
+            tc_split4(v, hi, lo);
+            Ah[id] = hi; Al[id] = lo;
+        }
+        // B chunk: 32 k x 256 n, staged K-major as well (kind::tf32 with an N-major B and no swizzle returned zeros on the B200:
+        // tools/probe/tc_probe.cu): 16-byte unit (n, k4) = B[4 k4 .. 4 k4 + 3][n] at k4 * 256 + n.  One column per thread: the four
+        // scalar loads are coalesced across the warp, the 16-byte stores are consecutive
+        float4* Bh = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES);
+        float4* Bl = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES + TC_B_BYTES);
+        if (tid < ncols) {
+            const float* bp = Bm + (size_t)(it * TC_BK) * MH_LD3V + n0 + tid;
+#pragma unroll
+            for (int k4 = 0; k4 < TC_BK / 4; ++k4) {
+                const float4 v = make_float4(bp[(size_t)(4 * k4) * MH_LD3V], bp[(size_t)(4 * k4 + 1) * MH_LD3V], bp[(size_t)(4 * k4 + 2) * MH_LD3V],
+                                             bp[(size_t)(4 * k4 + 3) * MH_LD3V]);
+                float4 hi, lo;
+                tc_split4(v, hi, lo);
+                Bh[k4 * TC_BN + tid] = hi; Bl[k4 * TC_BN + tid] = lo;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_h = sbase + s * TC_STAGE_BYTES, a_l = a_h + TC_A_BYTES;
+            const uint32_t b_h = a_h + 2 * TC_A_BYTES, b_l = b_h + TC_B_BYTES;
+#pragma unroll
+            for (int j = 0; j < TC_BK / 8; ++j) {                               // K = 8 per instruction
+                const uint64_t dah = tc_desc(a_h + j * 2 * (TC_BM * 16), TC_BM * 16, 128), dal = tc_desc(a_l + j * 2 * (TC_BM * 16), TC_BM * 16, 128);
+                const uint64_t dbh = tc_desc(b_h + j * 2 * (TC_BN * 16), TC_BN * 16, 128), dbl = tc_desc(b_l + j * 2 * (TC_BN * 16), TC_BN * 16, 128);
+                tc_mma_tf32(tmem, dah, dbh, idesc, (it | j) != 0);
+                tc_mma_tf32(tmem, dah, dbl, idesc, 1u);
+                tc_mma_tf32(tmem, dal, dbh, idesc, 1u);
+            }
+            tc_commit(bar0 + 8 * s);
+            if (it == NIT - 1) tc_commit(bar0 + 16);
+        }
+    }
+    tc_wait(bar0 + 16, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31 (one body row per thread), columns 128 (w / 4) .. + 127
+    {
+        const int q = warp & 3, half = warp >> 2;
+        const int m = m0 + 32 * q + lane;
+        const int srow = per_body_shape ? m : (m % Npers);
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+            const int col = 128 * half + 32 * cb;
+            if (col >= ncols) break;                                            // warp-uniform
+            uint32_t r[32];
+            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)col;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (m < M) {
+                const float4* vs = reinterpret_cast<const float4*>(Vs + (size_t)srow * MH_LD3V + n0 + col);
+                float4* out = reinterpret_cast<float4*>(C + (size_t)m * MH_LD3V + n0 + col);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = vs[i];
+                    out[i] = make_float4(__uint_as_float(r[4 * i]) + v.x, __uint_as_float(r[4 * i + 1]) + v.y,
+                                         __uint_as_float(r[4 * i + 2]) + v.z, __uint_as_float(r[4 * i + 3]) + v.w);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+}
+
+int mh_gemm_fwd_tc(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape,
+                   cudaStream_t st) {
+    MH_CUDA(c, cudaFuncSetAttribute(k_gemm_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    k_gemm_fwd_tc<<<dim3(mh_cdiv(MH_LD3V, TC_BN), mh_cdiv(nbodies, TC_BM)), TC_THREADS, TC_SMEM_BYTES, st>>>(pf, c->pext, vshaped, vposed,
+                                                                                                         nbodies, Npers, per_body_shape);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+// Testing aid: the pose-corrective contraction alone, C = A (M x 192, host) . pext[0:192] (no shape term), with the tensor-core
+// kernel (use_tc = 1) or the FP32 SIMT kernel (0); C_host is (M, MH_LD3V).
+int mh_gemm_fwd_simt(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape, cudaStream_t st);
+extern "C" int mh_debug_gemm_fwd(mh_ctx* c, const float* A_host, float* C_host, int32_t M, int32_t use_tc) {
+    if (!c || !A_host || !C_host || M <= 0) return MH_E_ARG;
+    cudaSetDevice(c->d.device);
+    float *A = nullptr, *Z = nullptr, *C = nullptr;
+    MH_CUDA(c, cudaMalloc((void**)&A, sizeof(float) * (size_t)M * MH_KPF));
+    MH_CUDA(c, cudaMalloc((void**)&Z, sizeof(float) * MH_LD3V));
+    MH_CUDA(c, cudaMalloc((void**)&C, sizeof(float) * (size_t)M * MH_LD3V));
+    MH_CUDA(c, cudaMemcpy(A, A_host, sizeof(float) * (size_t)M * MH_KPF, cudaMemcpyHostToDevice));
+    MH_CUDA(c, cudaMemset(Z, 0, sizeof(float) * MH_LD3V));
+    MH_CUDA(c, cudaMemset(C, 0xff, sizeof(float) * (size_t)M * MH_LD3V));
+    int rc = use_tc ? mh_gemm_fwd_tc(c, A, Z, C, M, 1, 0, 0) : mh_gemm_fwd_simt(c, A, Z, C, M, 1, 0, 0);
+    if (rc == MH_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(C_host, C, sizeof(float) * (size_t)M * MH_LD3V, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "mh_debug_gemm_fwd: %s", cudaGetErrorString(e)); rc = MH_E_CUDA; }
+    }
+    cudaFree(A); cudaFree(Z); cudaFree(C);
+    return rc;
+}

@@ -200,6 +200,12 @@ __global__ void __launch_bounds__(256) k_skin_fwd(const float* __restrict__ vpos
     }
 }
 
+int mh_gemm_fwd_simt(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape, cudaStream_t st) {
+    k_gemm_fwd<<<dim3(MH_LD3V / GF_BN, mh_cdiv(nbodies, GF_BM)), 256, 0, st>>>(pf, c->pext, vshaped, vposed, nbodies, Npers, per_body_shape);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
 int mh_smpl_forward_run(mh_ctx* c, const MhSmplArgs& a, cudaStream_t st) {
     if (a.nbodies <= 0) return MH_OK;
     k_shape_prep<<<dim3(mh_cdiv(MH_LD3V, 256), a.shape_rows), 256, 0, st>>>(a.betas, a.shape_rows, c->vtemplate, c->pext, a.vshaped);
@@ -208,9 +214,14 @@ int mh_smpl_forward_run(mh_ctx* c, const MhSmplArgs& a, cudaStream_t st) {
     MH_LAUNCHED(c);
     k_pose_prep<<<mh_cdiv(a.nbodies, 64), 64, 0, st>>>(a.theta, a.Jrest, a.nbodies, a.N, a.per_body_shape, a.A, a.pf);
     MH_LAUNCHED(c);
-    k_gemm_fwd<<<dim3(MH_LD3V / GF_BN, mh_cdiv(a.nbodies, GF_BM)), 256, 0, st>>>(a.pf, c->pext, a.vshaped, a.vposed, a.nbodies,
-                                                                               a.N, a.per_body_shape);
-    MH_LAUNCHED(c);
+    static const int use_tc = [] { const char* v = getenv("MH_GEMM_TC"); return v ? atoi(v) : 0; }();     // development switch
+    if (use_tc) {
+        MH_TRY(mh_gemm_fwd_tc(c, a.pf, a.vshaped, a.vposed, a.nbodies, a.N, a.per_body_shape, st));
+    } else {
+        k_gemm_fwd<<<dim3(MH_LD3V / GF_BN, mh_cdiv(a.nbodies, GF_BM)), 256, 0, st>>>(a.pf, c->pext, a.vshaped, a.vposed, a.nbodies,
+                                                                                   a.N, a.per_body_shape);
+        MH_LAUNCHED(c);
+    }
     k_skin_fwd<<<a.nbodies, 256, 0, st>>>(a.vposed, a.A, c->wj, c->ww, c->KW, a.trans, a.xscale, a.N, c->rptr, c->rvert, c->rw,
                                           a.verts, a.j17, a.lowidx, 0);
     MH_LAUNCHED(c);
