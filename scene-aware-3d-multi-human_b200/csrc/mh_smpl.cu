@@ -214,7 +214,8 @@ int mh_smpl_forward_run(mh_ctx* c, const MhSmplArgs& a, cudaStream_t st) {
     MH_LAUNCHED(c);
     k_pose_prep<<<mh_cdiv(a.nbodies, 64), 64, 0, st>>>(a.theta, a.Jrest, a.nbodies, a.N, a.per_body_shape, a.A, a.pf);
     MH_LAUNCHED(c);
-    static const int use_tc = [] { const char* v = getenv("MH_GEMM_TC"); return v ? atoi(v) : 0; }();     // development switch
+    // tensor cores (mh_gemm_tc.cu); MH_GEMM_TC=0 selects the FP32 SIMT kernel for A/B measurements
+    static const int use_tc = [] { const char* v = getenv("MH_GEMM_TC"); return v ? atoi(v) : 1; }();
     if (use_tc) {
         MH_TRY(mh_gemm_fwd_tc(c, a.pf, a.vshaped, a.vposed, a.nbodies, a.N, a.per_body_shape, st));
     } else {

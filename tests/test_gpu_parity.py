@@ -62,6 +62,32 @@ def test_smpl_forward_kat(c1, kat):
     assert np.array_equal(v1, v[:1]) and np.array_equal(j1, j[:1])
 
 
+def test_pose_corrective_contraction_on_tensor_cores(c1, L):
+    """`v_posed - v_shaped = pose_feature . posedirs` (smpl.py:549-553): the tcgen05 / TMEM kernel (3 x TF32 split) against float64
+    and against the FP32 SIMT kernel, on a row count that is not a multiple of the 128-row tile (the last column tile is 192 wide)."""
+    ctx = c1[0].ctx
+    eye = np.eye(192, dtype=np.float32)
+    basis = np.zeros((192, L.LD3V), np.float32)
+    ctx.call('mh_debug_gemm_fwd', L.ptr(eye), L.ptr(basis), 192, 0)             # exact: one product per output
+    assert np.abs(basis).max() > 0
+    via_tc = np.zeros_like(basis)
+    ctx.call('mh_debug_gemm_fwd', L.ptr(eye), L.ptr(via_tc), 192, 1)
+    assert np.abs(via_tc - basis).max() <= 1e-6 * np.abs(basis).max()           # hi + lo reproduces every entry (lo . lo dropped)
+    rng = np.random.default_rng(11)
+    M = 300
+    A = rng.normal(0, 0.2, (M, 192)).astype(np.float32)
+    ref = A.astype(np.float64) @ basis.astype(np.float64)
+    out = {}
+    for use_tc in (0, 1):
+        C = np.full((M, L.LD3V), np.nan, np.float32)
+        ctx.call('mh_debug_gemm_fwd', L.ptr(A), L.ptr(C), M, use_tc)
+        out[use_tc] = C
+    scale = np.abs(ref).max()
+    assert np.abs(out[0] - ref).max() <= 1e-6 * scale                           # FP32 FMA chain
+    assert np.abs(out[1] - ref).max() <= 3e-6 * scale                           # tensor cores, fp32 accumulation in TMEM
+    assert np.array_equal(out[1][:, L.LD3V - 2:], out[0][:, L.LD3V - 2:])       # the padding columns stay exactly zero
+
+
 def test_one_euro_kat(c1, kat):
     opt = c1[0]
     assert np.array_equal(opt.one_euro_filter(kat['oef_in'], 0.01, 0.02).cpu().numpy(), kat['oef_out'])
@@ -72,7 +98,12 @@ def test_one_euro_kat(c1, kat):
 
 @pytest.mark.parametrize('which', ['c1', 'n2'])
 def test_render_planes_vs_oracle(which, c1, n2, L):
-    """zbuf[...,0] of the depth raster and the soft-silhouette alpha of every person-frame vs oracle.raster."""
+    """zbuf[...,0] of the depth raster and the soft-silhouette alpha of every person-frame vs oracle.raster.
+
+    The rasterisers are compared on IDENTICAL vertices (the device's own SMPL output, read back): coverage, the blur-radius
+    tests and the 4 nearest fragments are discrete in the vertex positions, so a 1e-8 m difference between two correct SMPL
+    evaluations (FP32 FMA chain vs tensor-core accumulation vs torch's CPU sgemm) can flip one fragment and move alpha by
+    1e-3.  The SMPL forward itself is pinned by `test_smpl_forward_kat` (1e-5 m) and checked here to 1e-6 m."""
     import torch
     from oracle import raster, refmath as rm, synth
     opt, g, data, meta = c1 if which == 'c1' else n2
@@ -90,11 +121,13 @@ def test_render_planes_vs_oracle(which, c1, n2, L):
         for n in range(N):
             zb = np.zeros((H, W), np.float32); al = np.zeros((H, W), np.float32)
             ctx.call('mh_debug_render', t, n, L.ptr(zb), L.ptr(al))
+            dev_verts = opt._view(L.BUF_VERTS).view(T + 2, N, L.LD3V)[1 + t, n, :3 * L.V].cpu().view(L.V, 3)
             with torch.no_grad():
                 out = rm.smpl_forward(mt, torch.from_numpy(g[f'c{c}_p_betas'][0, n:n + 1]), torch.from_numpy(g[f'c{c}_p_poses_smpl'][t, n:n + 1]))
                 s = np.float32(1.1) ** g[f'c{c}_p_xscale'].reshape(-1)[n]
                 va = float(s) * out['verts'][0] + torch.from_numpy(g[f'c{c}_p_poses_T'][t, n])
-                z0, a0 = raster.render_person(va, faces, Kndc, H, W)
+                assert float((dev_verts - va).abs().max()) < 1e-6             # metres: the two SMPL evaluations agree
+                z0, a0 = raster.render_person(dev_verts.clone(), faces, Kndc, H, W)
             z0, a0 = z0.numpy(), a0.numpy()
             assert (z0 > 0).sum() > 100
             assert np.array_equal(z0 > 0, zb > 0), (t, n)                     # identical coverage

@@ -22,7 +22,7 @@ A[np.arange(M), np.arange(M) % 192] = 1.0
 C0 = np.zeros((M, L.LD3V), np.float32); C1 = np.zeros_like(C0)
 ctx.call('mh_debug_gemm_fwd', L.ptr(A), L.ptr(C0), M, 0)
 ctx.call('mh_debug_gemm_fwd', L.ptr(A), L.ptr(C1), M, 1)
-B = C0[:192]                                             # rows of the basis
+B = C0[:192].copy()                                      # rows of the basis
 print('identity pattern: max abs diff', np.abs(C1 - C0).max(), 'max abs', np.abs(C0).max(), 'nan', int(np.isnan(C1).sum()))
 Bn = B / (np.linalg.norm(B, axis=1, keepdims=True) + 1e-30)
 for m in (0, 1, 2, 3, 4, 7, 8, 9, 31, 32, 127, 128, 200, 299):
