@@ -233,6 +233,9 @@ int mh_debug_set_render_caps(mh_ctx* ctx, int32_t maxbins, int32_t bincap, int32
 /* testing aid: the pose-corrective contraction alone, C (M, 20672) = A (M, 192) . posedirs, HOST pointers, blocking; use_tc = 1 runs
  * the tcgen05 / TMEM kernel (3 x TF32), 0 the FP32 SIMT kernel (smpl.py:549-553 without the shape term) */
 int mh_debug_gemm_fwd(mh_ctx* ctx, const float* A_host, float* C_host, int32_t M, int32_t use_tc);
+/* testing aid: the backward contraction alone, D (M, 208) = E (M, 20672) . extended_basis^T (dL/dpose_feature and the shape-blend
+ * part of dL/dbeta), split-K partials summed on the host; HOST pointers, blocking */
+int mh_debug_gemm_bwd(mh_ctx* ctx, const float* E_host, float* D_host, int32_t M, int32_t use_tc);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t mh_launch_count(const mh_ctx* ctx);
 

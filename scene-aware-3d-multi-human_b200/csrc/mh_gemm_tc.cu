@@ -193,9 +193,131 @@ int mh_gemm_fwd_tc(mh_ctx* c, const float* pf, const float* vshaped, float* vpos
     return MH_OK;
 }
 
+// -------------------------------------------------------------------------------------------------------------------------
+// Backward contraction: Dpart[ks][m][n] = sum_{k in split ks} E[m][k] Bext[n][k]      (dL/dpose_feature and the shape-blend part
+// of dL/dbeta, smpl.py:549-553 / :530 backward).  M = bodies, N = MH_NEXT (208 rows of the extended basis), K = MH_LD3V split in
+// MH_KSPLIT ranges of 1088.  Both operands are K-major in global memory already.  Same pipeline as the forward kernel.
+constexpr int TCB_B_BYTES = MH_NEXT * TC_BK * 4;                      // 26 KB: one half of a B chunk (208 rows x 32 k)
+constexpr int TCB_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TCB_B_BYTES;
+constexpr int TCB_SMEM_BYTES = 2 * TCB_STAGE_BYTES;
+constexpr int TCB_KLEN = MH_LD3V / MH_KSPLIT;
+static_assert(MH_LD3V % MH_KSPLIT == 0 && TCB_KLEN % TC_BK == 0 && MH_NEXT % 16 == 0, "split-K must tile the padded row");
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bwd_tc(const float* __restrict__ E, const float* __restrict__ Bext,
+                                                               float* __restrict__ Dpart, int M, int first_body, int nb_total) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ __align__(8) unsigned long long bars[3];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * TC_BM, ks = blockIdx.y;
+    const int kbeg = ks * TCB_KLEN;
+    const uint32_t sbase = tc_smem_u32(tc_smem);
+    const uint32_t bar0 = tc_smem_u32(&bars[0]);
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MH_NEXT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    uint32_t phase[2] = {0u, 0u};
+    constexpr int NIT = TCB_KLEN / TC_BK;
+    for (int it = 0; it < NIT; ++it) {
+        const int s = it & 1;
+        unsigned char* st = tc_smem + s * TCB_STAGE_BYTES;
+        const int k0 = kbeg + it * TC_BK;
+        if (it >= 2) { tc_wait(bar0 + 8 * s, phase[s]); phase[s] ^= 1u; }
+        float4* Ah = reinterpret_cast<float4*>(st);
+        float4* Al = reinterpret_cast<float4*>(st + TC_A_BYTES);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = tid + TC_THREADS * i;
+            const int row = id & (TC_BM - 1), k4 = id >> 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + row < M) v = *reinterpret_cast<const float4*>(E + (size_t)(first_body + m0 + row) * MH_LD3V + k0 + k4 * 4);
+            float4 hi, lo;
+            tc_split4(v, hi, lo);
+            Ah[id] = hi; Al[id] = lo;
+        }
+        // B chunk: 208 basis rows x 32 k: 16-byte unit (n, k4) at k4 * 208 + n
+        float4* Bh = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES);
+        float4* Bl = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES + TCB_B_BYTES);
+#pragma unroll
+        for (int i = 0; i < (MH_NEXT * 8 + TC_THREADS - 1) / TC_THREADS; ++i) {
+            const int id = tid + TC_THREADS * i;
+            if (id < MH_NEXT * 8) {
+                const int n = id % MH_NEXT, k4 = id / MH_NEXT;
+                const float4 v = *reinterpret_cast<const float4*>(Bext + (size_t)n * MH_LD3V + k0 + k4 * 4);
+                float4 hi, lo;
+                tc_split4(v, hi, lo);
+                Bh[id] = hi; Bl[id] = lo;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_h = sbase + s * TCB_STAGE_BYTES, a_l = a_h + TC_A_BYTES;
+            const uint32_t b_h = a_h + 2 * TC_A_BYTES, b_l = b_h + TCB_B_BYTES;
+#pragma unroll
+            for (int j = 0; j < TC_BK / 8; ++j) {
+                const uint64_t dah = tc_desc(a_h + j * 2 * (TC_BM * 16), TC_BM * 16, 128), dal = tc_desc(a_l + j * 2 * (TC_BM * 16), TC_BM * 16, 128);
+                const uint64_t dbh = tc_desc(b_h + j * 2 * (MH_NEXT * 16), MH_NEXT * 16, 128), dbl = tc_desc(b_l + j * 2 * (MH_NEXT * 16), MH_NEXT * 16, 128);
+                tc_mma_tf32(tmem, dah, dbh, idesc, (it | j) != 0);
+                tc_mma_tf32(tmem, dah, dbl, idesc, 1u);
+                tc_mma_tf32(tmem, dal, dbh, idesc, 1u);
+            }
+            tc_commit(bar0 + 8 * s);
+            if (it == NIT - 1) tc_commit(bar0 + 16);
+        }
+    }
+    tc_wait(bar0 + 16, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        // epilogue: 13 blocks of 16 columns; warps 0-3 take blocks 0-6, warps 4-7 blocks 7-12 of their 32 TMEM lanes
+        const int q = warp & 3, half = warp >> 2;
+        const int m = m0 + 32 * q + lane;
+        const int cb0 = half ? 7 : 0, cb1 = half ? MH_NEXT / 16 : 7;
+#pragma unroll 1
+        for (int cb = cb0; cb < cb1; ++cb) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * cb);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (m < M) {
+                float4* out = reinterpret_cast<float4*>(Dpart + ((size_t)ks * nb_total + first_body + m) * MH_NEXT + 16 * cb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    out[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+}
+
+int mh_gemm_bwd_tc(mh_ctx* c, const float* E, float* dpf_part, int M, int first_body, int nb_total, cudaStream_t st) {
+    MH_CUDA(c, cudaFuncSetAttribute(k_gemm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_BYTES));
+    k_gemm_bwd_tc<<<dim3(mh_cdiv(M, TC_BM), MH_KSPLIT), TC_THREADS, TCB_SMEM_BYTES, st>>>(E, c->pext, dpf_part, M, first_body, nb_total);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
 // Testing aid: the pose-corrective contraction alone, C = A (M x 192, host) . pext[0:192] (no shape term), with the tensor-core
 // kernel (use_tc = 1) or the FP32 SIMT kernel (0); C_host is (M, MH_LD3V).
-int mh_gemm_fwd_simt(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape, cudaStream_t st);
+
 extern "C" int mh_debug_gemm_fwd(mh_ctx* c, const float* A_host, float* C_host, int32_t M, int32_t use_tc) {
     if (!c || !A_host || !C_host || M <= 0) return MH_E_ARG;
     cudaSetDevice(c->d.device);
@@ -213,5 +335,33 @@ extern "C" int mh_debug_gemm_fwd(mh_ctx* c, const float* A_host, float* C_host, 
         if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "mh_debug_gemm_fwd: %s", cudaGetErrorString(e)); rc = MH_E_CUDA; }
     }
     cudaFree(A); cudaFree(Z); cudaFree(C);
+    return rc;
+}
+
+// Testing aid: the backward contraction alone, D (M, 208) = E (M, 20672, host) . pext^T, split-K partials reduced on the host.
+
+extern "C" int mh_debug_gemm_bwd(mh_ctx* c, const float* E_host, float* D_host, int32_t M, int32_t use_tc) {
+    if (!c || !E_host || !D_host || M <= 0) return MH_E_ARG;
+    cudaSetDevice(c->d.device);
+    float *E = nullptr, *P = nullptr;
+    const size_t np = (size_t)MH_KSPLIT * M * MH_NEXT;
+    MH_CUDA(c, cudaMalloc((void**)&E, sizeof(float) * (size_t)M * MH_LD3V));
+    MH_CUDA(c, cudaMalloc((void**)&P, sizeof(float) * np));
+    MH_CUDA(c, cudaMemcpy(E, E_host, sizeof(float) * (size_t)M * MH_LD3V, cudaMemcpyHostToDevice));
+    MH_CUDA(c, cudaMemset(P, 0xff, sizeof(float) * np));
+    int rc = use_tc ? mh_gemm_bwd_tc(c, E, P, M, 0, M, 0) : mh_gemm_bwd_simt(c, E, P, M, 0, M, 0);
+    if (rc == MH_OK) {
+        std::vector<float> h(np);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(h.data(), P, sizeof(float) * np, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "mh_debug_gemm_bwd: %s", cudaGetErrorString(e)); rc = MH_E_CUDA; }
+        else
+            for (size_t i = 0; i < (size_t)M * MH_NEXT; ++i) {
+                float a = 0.f;
+                for (int ks = 0; ks < MH_KSPLIT; ++ks) a += h[(size_t)ks * M * MH_NEXT + i];
+                D_host[i] = a;
+            }
+    }
+    cudaFree(E); cudaFree(P);
     return rc;
 }

@@ -400,6 +400,12 @@ __global__ void k_pose_bwd(const float* __restrict__ theta_all, const float* __r
     atomicAdd(g_xscale + n, 0.09531017980432493f * s * gT[(size_t)b * 4 + 3]);     // d(1.1^x)/dx = ln(1.1) 1.1^x
 }
 
+int mh_gemm_bwd_simt(mh_ctx* c, const float* E, float* dpf_part, int M, int first_body, int nb_total, cudaStream_t st) {
+    k_gemm_bwd<<<dim3(mh_cdiv(M, GB_BM), MH_KSPLIT), 256, 0, st>>>(E, c->pext, dpf_part, M, first_body, nb_total);
+    MH_LAUNCHED(c);
+    return MH_OK;
+}
+
 int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st) {
     const int N = c->d.N, T = c->d.T;
     const int M = T * N, first = N;
@@ -407,8 +413,9 @@ int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st) {
     k_skin_bwd<<<M, 256, 0, st>>>(c->dverts, c->vposed, c->A, c->wj, c->ww, c->KW, c->jptr, c->jvert, c->jw, xs, N, c->dA,
                                   c->gT, first);
     MH_LAUNCHED(c);
-    k_gemm_bwd<<<dim3(mh_cdiv(M, GB_BM), MH_KSPLIT), 256, 0, st>>>(c->dverts, c->pext, c->dpf_part, M, first, c->nb);
-    MH_LAUNCHED(c);
+    static const int use_tc = [] { const char* v = getenv("MH_GEMM_TC"); return v ? atoi(v) : 1; }();     // as in the forward pass
+    if (use_tc) MH_TRY(mh_gemm_bwd_tc(c, c->dverts, c->dpf_part, M, first, c->nb, st));
+    else MH_TRY(mh_gemm_bwd_simt(c, c->dverts, c->dpf_part, M, first, c->nb, st));
     float* dpf = c->dpf_part + (size_t)MH_KSPLIT * c->nb * MH_NEXT;       // reduced copy lives after the partials
     k_reduce_partials<<<mh_cdiv((int64_t)M * MH_NEXT, 256), 256, 0, st>>>(c->dpf_part, dpf, first, M, c->nb);
     MH_LAUNCHED(c);

@@ -88,6 +88,32 @@ def test_pose_corrective_contraction_on_tensor_cores(c1, L):
     assert np.array_equal(out[1][:, L.LD3V - 2:], out[0][:, L.LD3V - 2:])       # the padding columns stay exactly zero
 
 
+def test_backward_contraction_on_tensor_cores(c1, L):
+    """`dL/dpose_feature = dL/dv_posed . posedirs^T` plus the shape-blend rows (K = 20672 in 19 split-K ranges): tcgen05 / TMEM kernel
+    against float64 and against the FP32 SIMT kernel."""
+    ctx = c1[0].ctx
+    eye = np.eye(192, dtype=np.float32)
+    basis = np.zeros((192, L.LD3V), np.float32)
+    ctx.call('mh_debug_gemm_fwd', L.ptr(eye), L.ptr(basis), 192, 0)
+    rng = np.random.default_rng(12)
+    M = 200                                                                     # not a multiple of the 128-row tile
+    E = rng.normal(0, 1e-3, (M, L.LD3V)).astype(np.float32)
+    E[:, 3 * L.V:] = 0
+    ref = E.astype(np.float64) @ basis.astype(np.float64).T                     # (M, 192)
+    out = {}
+    for use_tc in (0, 1):
+        D = np.full((M, 208), np.nan, np.float32)
+        ctx.call('mh_debug_gemm_bwd', L.ptr(E), L.ptr(D), M, use_tc)
+        out[use_tc] = D
+    scale = np.abs(ref).max()
+    e0, e1 = np.abs(out[0][:, :192] - ref).max() / scale, np.abs(out[1][:, :192] - ref).max() / scale
+    assert e0 <= 2e-5, ('simt', e0)                                             # 1088 sequential FP32 additions per split
+    assert e1 <= 2e-5, ('tensor cores', e1)
+    s2 = np.abs(out[0][:, 192:]).max()
+    e2 = np.abs(out[1][:, 192:] - out[0][:, 192:]).max() / s2
+    assert s2 > 0 and e2 <= 4e-5, ('shape-blend rows', e2)                      # shape-blend rows (+ zero padding)
+
+
 def test_one_euro_kat(c1, kat):
     opt = c1[0]
     assert np.array_equal(opt.one_euro_filter(kat['oef_in'], 0.01, 0.02).cpu().numpy(), kat['oef_out'])
