@@ -156,6 +156,9 @@ int mh_reset_optimizer(mh_ctx* ctx, void* stream);
  * either output may be NULL. */
 int mh_smpl_forward(mh_ctx* ctx, const float* betas_host, const float* theta_host, int64_t nb,
                     float* verts_host, float* joints17_host);
+/* evaluation (mhmocap/evaluate.py:222-229, smpl.py:376-389): SMPL forward of nbodies (betas (nb,10), theta (nb,72)), then
+ * joints (nb,J,3) = regressor (J,6890, dense, HOST) . local vertices (no scale, no translation).  HOST pointers, blocking. */
+int mh_smpl_regress(mh_ctx* ctx, const float* betas, const float* theta, int64_t nbodies, const float* regressor, int32_t J, float* joints);
 
 /* ---- hot loop A: __init_global_poses (optimizer.py:710-770) ------------------------------------ */
 /* pose2d (T,N,17,3), per-frame ROMP theta (T,N,72) / betas (T,N,10): evaluates the (constant) regressed

@@ -6,6 +6,7 @@ C ABI of ``include/mhopt.h``).  Importing the package loads the library and fail
 """
 from . import _lib                                         # noqa: F401  (raises when libmhopt.so is absent)
 from .optimizer import SMPLDepthSequenceOptimizer, SMPLOptimizerBase       # noqa: F401
+from . import evaluation                                   # noqa: F401  (mhmocap/evaluate.py mirror; SMPL joints on the device)
 
 
 
@@ -28,4 +29,4 @@ def install_as_mhmocap_optimizer():
     return optimizer
 
 
-__all__ = ['SMPLDepthSequenceOptimizer', 'SMPLOptimizerBase', 'install_as_mhmocap_optimizer']
+__all__ = ['SMPLDepthSequenceOptimizer', 'SMPLOptimizerBase', 'install_as_mhmocap_optimizer', 'evaluation']

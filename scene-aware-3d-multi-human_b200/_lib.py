@@ -74,6 +74,7 @@ def _load():
         'mh_device_view': (c_int32, [ctx, c_int32, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64)]),
         'mh_reset_optimizer': (c_int32, [ctx, c_void_p]),
         'mh_smpl_forward': (c_int32, [ctx, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+        'mh_smpl_regress': (c_int32, [ctx, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
         'mh_init_begin': (c_int32, [ctx, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
         'mh_init_grads': (c_int32, [ctx, c_int32, c_int32, c_void_p]),
         'mh_init_update': (c_int32, [ctx, c_float, c_int32, c_void_p]),

@@ -531,6 +531,76 @@ extern "C" int mh_smpl_forward(mh_ctx* c, const float* betas, const float* theta
     return r;
 }
 
+// ---- evaluation: SMPL forward + an arbitrary sparse joint regressor ---------------------------------
+// joints[b][j] = sum_v R[j][v] verts_local[b][v]   (smpl.py:376-389: vertices2joints with J_regressor_mupots / _h36m17 / _extra9;
+// evaluate.py:222-229).  One warp per (body, joint) walks the joint's non-zeros.
+__global__ void k_regress_joints(const float* __restrict__ verts, const int* __restrict__ rptr, const int* __restrict__ rvert,
+                                 const float* __restrict__ rw, int nbodies, int J, float* __restrict__ out) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nbodies * J) return;
+    const int b = w / J, j = w % J;
+    const float* v = verts + (size_t)b * MH_LD3V;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int e = rptr[j] + lane; e < rptr[j + 1]; e += 32) {
+        const float wt = rw[e];
+        const int vi = rvert[e];
+        ax = fmaf(wt, v[3 * vi], ax); ay = fmaf(wt, v[3 * vi + 1], ay); az = fmaf(wt, v[3 * vi + 2], az);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_down_sync(0xffffffffu, ax, o); ay += __shfl_down_sync(0xffffffffu, ay, o); az += __shfl_down_sync(0xffffffffu, az, o);
+    }
+    if (lane == 0) { float* o = out + ((size_t)b * J + j) * 3; o[0] = ax; o[1] = ay; o[2] = az; }
+}
+
+extern "C" int mh_smpl_regress(mh_ctx* c, const float* betas, const float* theta, int64_t nbodies, const float* regressor, int32_t J,
+                               float* joints) {
+    API_BEGIN(c);
+    if (!c->model_set) MH_FAIL(c, MH_E_STATE, "mh_smpl_regress: mh_set_model first");
+    if (!betas || !theta || !regressor || !joints || nbodies < 1 || J < 1 || J > 64) MH_FAIL(c, MH_E_ARG, "mh_smpl_regress: bad arguments");
+    cudaStream_t st = 0;
+    // CSR of the (J, V) regressor: zero weights dropped (exact)
+    std::vector<int> rptr(J + 1, 0), rvert;
+    std::vector<float> rw;
+    for (int j = 0; j < J; ++j) {
+        for (int v = 0; v < MH_V; ++v) {
+            const float w = regressor[(size_t)j * MH_V + v];
+            if (w != 0.f) { rvert.push_back(v); rw.push_back(w); }
+        }
+        rptr[j + 1] = (int)rvert.size();
+    }
+    if (rvert.empty()) { rvert.push_back(0); rw.push_back(0.f); }
+    const int64_t chunk = c->nb;
+    int *d_rptr = nullptr, *d_rvert = nullptr;
+    float *d_rw = nullptr, *dbetas = nullptr, *dj = nullptr;
+    int r = MH_OK;
+    if (cudaMalloc((void**)&d_rptr, sizeof(int) * rptr.size()) != cudaSuccess || cudaMalloc((void**)&d_rvert, sizeof(int) * rvert.size()) != cudaSuccess ||
+        cudaMalloc((void**)&d_rw, sizeof(float) * rw.size()) != cudaSuccess || cudaMalloc((void**)&dbetas, sizeof(float) * chunk * 10) != cudaSuccess ||
+        cudaMalloc((void**)&dj, sizeof(float) * chunk * J * 3) != cudaSuccess)
+        r = MH_E_CUDA;
+    if (r == MH_OK) {
+        cudaMemcpyAsync(d_rptr, rptr.data(), sizeof(int) * rptr.size(), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_rvert, rvert.data(), sizeof(int) * rvert.size(), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_rw, rw.data(), sizeof(float) * rw.size(), cudaMemcpyHostToDevice, st);
+    }
+    for (int64_t s = 0; s < nbodies && r == MH_OK; s += chunk) {
+        const int n = (int)std::min<int64_t>(chunk, nbodies - s);
+        cudaMemcpyAsync(dbetas, betas + s * 10, sizeof(float) * n * 10, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(c->theta_all, theta + s * 72, sizeof(float) * n * 72, cudaMemcpyHostToDevice, st);
+        // scale 1, translation 0 (null pointers): local vertices, per-body shapes in `dverts` as in mh_smpl_forward
+        MhSmplArgs a = {dbetas, n, 1, c->theta_all, nullptr, nullptr, n, c->d.N, c->dverts, c->Jrest, c->A, c->pf, c->vposed,
+                        c->verts, c->j17, nullptr};
+        r = mh_smpl_forward_run(c, a, st);
+        if (r != MH_OK) break;
+        k_regress_joints<<<mh_cdiv((int64_t)n * J * 32, 256), 256, 0, st>>>(c->verts, d_rptr, d_rvert, d_rw, n, J, dj);
+        c->launches++;
+        if (cudaMemcpyAsync(joints + s * J * 3, dj, sizeof(float) * n * J * 3, cudaMemcpyDeviceToHost, st) != cudaSuccess) r = MH_E_CUDA;
+        if (cudaStreamSynchronize(st) != cudaSuccess) r = MH_E_CUDA;
+    }
+    cudaFree(d_rptr); cudaFree(d_rvert); cudaFree(d_rw); cudaFree(dbetas); cudaFree(dj);
+    if (r == MH_E_CUDA && !c->err[0]) snprintf(c->err, sizeof(c->err), "mh_smpl_regress: %s", cudaGetErrorString(cudaGetLastError()));
+    return r;
+}
+
 // ---- hot loop A ---------------------------------------------------------------------------------
 __global__ void k_init_fill(float* __restrict__ poses_T, int64_t n, const float* __restrict__ pose2d, float* __restrict__ vis, int64_t nj,
                             float thr) {

@@ -444,3 +444,17 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         j17 = np.empty((b.shape[0], 17, 3), np.float32)
         self.ctx.call('mh_smpl_forward', L.ptr(b), L.ptr(p), b.shape[0], L.ptr(verts), L.ptr(j17))
         return verts, j17
+
+    def smpl_regress(self, betas, poses, regressor):
+        """SMPL forward + ``regressor (J, 6890) . verts`` on the device (``smpl.py:376-389`` with any of the reference's regressors:
+        ``joints_mupots``, ``joints_h36m17``, ``joints_extra9``); local joints (nb, J, 3), used by ``evaluation.SMPLJoints``."""
+        b, p = L.f32(betas).reshape(-1, 10), L.f32(poses).reshape(-1, 72)
+        R = np.asarray(regressor, np.float32)
+        if R.ndim == 2 and R.shape[0] == L.V and R.shape[1] != L.V:            # the reference's .npy files are stored (6890, J)
+            R = R.T
+        R = L.f32(np.ascontiguousarray(R))
+        if R.ndim != 2 or R.shape[1] != L.V:
+            raise ValueError(f'regressor must be (J, {L.V}) or ({L.V}, J), got {R.shape}')
+        out = np.empty((b.shape[0], R.shape[0], 3), np.float32)
+        self.ctx.call('mh_smpl_regress', L.ptr(b), L.ptr(p), b.shape[0], L.ptr(R), R.shape[0], L.ptr(out))
+        return out
