@@ -34,6 +34,8 @@ static int upload(mh_ctx* c, T** p, const std::vector<T>& h) {
     return MH_OK;
 }
 
+int mh_upload_floats(mh_ctx* c, float** p, const std::vector<float>& h) { return upload(c, p, h); }
+
 extern "C" const char* mh_version(void) { return "mhopt-b200 0.1 (sm_100a)"; }
 
 extern "C" const char* mh_last_error(const mh_ctx* c) { return c ? c->err : "null context"; }
@@ -242,6 +244,7 @@ extern "C" int mh_set_model(mh_ctx* c, const mh_model* m) {
     std::vector<int32_t> faces(m->faces, m->faces + (size_t)MH_F * 3);
     c->KW = KW; c->jnnz = (int)jvert.size(); c->rnnz = (int)rvert.size();
     MH_TRY(upload(c, &c->pext, pext));
+    MH_TRY(mh_gemm_tc_prepare(c, pext));
     MH_TRY(upload(c, &c->vtemplate, vt));
     MH_TRY(upload(c, &c->Jt, Jt));
     MH_TRY(upload(c, &c->Js, Js));

@@ -39,6 +39,8 @@ struct mh_ctx {
     std::vector<void*> allocs;
     // ---- model ----
     float* pext;               // (MH_NEXT, MH_LD3V) extended basis
+    float* pextF;              // the basis pre-split (hi | lo TF32) in the UMMA tile layout of the forward contraction (mh_gemm_tc.cu)
+    float* pextB;              // ... of the backward contraction
     float* vtemplate;          // (MH_LD3V)
     float* Jt;                 // (24,3)   J_regressor . v_template
     float* Js;                 // (24,3,10) J_regressor . shapedirs
@@ -145,6 +147,8 @@ int mh_smpl_forward_run(mh_ctx* c, const MhSmplArgs& a, cudaStream_t st);
 int mh_gemm_fwd_tc(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape,
                    cudaStream_t st);          // mh_gemm_tc.cu: tcgen05 / TMEM, 3 x TF32
 int mh_gemm_bwd_tc(mh_ctx* c, const float* E, float* dpf_part, int M, int first_body, int nb_total, cudaStream_t st);
+int mh_gemm_tc_prepare(mh_ctx* c, const std::vector<float>& pext);      // builds pextF / pextB at mh_set_model
+int mh_upload_floats(mh_ctx* c, float** p, const std::vector<float>& h);    // allocation owned by the context + H2D copy
 int mh_gemm_bwd_simt(mh_ctx* c, const float* E, float* dpf_part, int M, int first_body, int nb_total, cudaStream_t st);
 int mh_gemm_fwd_simt(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape, cudaStream_t st);
 int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st);

@@ -5,12 +5,14 @@
 // Reference path replaced: `v_posed = v_shaped + matmul(pose_feature, posedirs)` (mhmocap/smpl.py:549-553) -- one of the two
 // genuinely dense contractions of the hot path (hard part 2).
 //
-// One CTA per 128 x 256 output tile.  K is walked in chunks of 32 through two shared-memory stages: all threads load the
-// chunk of A and B (both staged K-major) from global memory, split every value into x_hi = tf32(x), x_lo = tf32(x - x_hi) and
-// store both halves in the canonical no-swizzle UMMA layouts (8 x 16-byte core matrices); ONE thread then issues, per K = 8
-// step, the three products hi*hi + hi*lo + lo*hi as `tcgen05.mma.cta_group::1.kind::tf32` into the same 128-lane x 256-column
-// fp32 accumulator in TMEM and commits the stage to an mbarrier, so the loads of the next chunk overlap the MMAs.  The epilogue
-// reads the accumulator with `tcgen05.ld` (one TMEM lane = one body row per thread), adds v_shaped and writes v_posed.
+// One CTA per 128 x 256 output tile.  K is walked in chunks of 32 through two shared-memory stages.  Every value is split into
+// x_hi = tf32(x), x_lo = tf32(x - x_hi); both halves sit in the canonical no-swizzle K-major UMMA layout (8 x 16-byte core
+// matrices).  The BASIS operand is constant: it is split and laid out per (tile, chunk) once at mh_set_model (`pextF` / `pextB`),
+// so a chunk of it is ONE contiguous block that a single TMA bulk copy (`cp.async.bulk`, mbarrier complete_tx) brings in; the
+// per-cycle operand (pose features / vertex gradients) is loaded and split by the threads.  ONE thread then issues, per K = 8 step,
+// the three products hi*hi + hi*lo + lo*hi as `tcgen05.mma.cta_group::1.kind::tf32` into the same 128-lane fp32 accumulator in
+// TMEM and commits the stage to an mbarrier, so the loads of the next chunk overlap the MMAs.  The epilogue reads the accumulator
+// with `tcgen05.ld` (one TMEM lane = one body row per thread), adds v_shaped and writes v_posed.
 // The dropped lo*lo term is 2^-22 relative: the result differs from the fp32 FMA chain by < 1e-8 m.
 #include "mh_ctx.h"
 
@@ -53,6 +55,13 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// one TMA bulk copy global -> shared, completion (bytes) on an mbarrier that expects them
+__device__ __forceinline__ void tc_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_split(float x, float& hi, float& lo) {
     uint32_t h, l;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
@@ -65,11 +74,11 @@ __device__ __forceinline__ void tc_split4(const float4 v, float4& hi, float4& lo
     tc_split(v.x, hi.x, lo.x); tc_split(v.y, hi.y, lo.y); tc_split(v.z, hi.z, lo.z); tc_split(v.w, hi.w, lo.w);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_fwd_tc(const float* __restrict__ Am, const float* __restrict__ Bm,
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_fwd_tc(const float* __restrict__ Am, const float* __restrict__ Bsplit,
                                                                const float* __restrict__ Vs, float* __restrict__ C, int M, int Npers,
                                                                int per_body_shape) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    __shared__ __align__(8) unsigned long long bars[3];                // stage 0 free, stage 1 free, accumulator complete
+    __shared__ __align__(8) unsigned long long bars[5];                // stage 0 / 1 free, accumulator complete, stage 0 / 1 basis landed
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
@@ -77,7 +86,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_fwd_tc(const float* __re
     const uint32_t sbase = tc_smem_u32(tc_smem);
     const uint32_t bar0 = tc_smem_u32(&bars[0]);
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+        for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -96,6 +105,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_fwd_tc(const float* __re
         const int s = it & 1;
         unsigned char* st = tc_smem + s * TC_STAGE_BYTES;
         if (it >= 2) { tc_wait(bar0 + 8 * s, phase[s]); phase[s] ^= 1u; }          // the MMAs that read this stage are done
+        // B chunk (hi | lo, 64 KB, already split and in the UMMA layout: 16-byte unit (n, k4) at k4 * 256 + n): one TMA bulk copy
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_bulk_load(sbase + s * TC_STAGE_BYTES + 2 * TC_A_BYTES, Bsplit + ((size_t)blockIdx.x * NIT + it) * (2 * TC_B_BYTES / 4), 2 * TC_B_BYTES,
+                         bar0 + 24 + 8 * s);
+        }
         // A chunk: 128 rows x 32 k, K-major: 16-byte unit (row, k4) at k4 * 128 + row
         float4* Ah = reinterpret_cast<float4*>(st);
         float4* Al = reinterpret_cast<float4*>(st + TC_A_BYTES);
@@ -109,25 +124,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_fwd_tc(const float* __re
             tc_split4(v, hi, lo);
             Ah[id] = hi; Al[id] = lo;
         }
-        // B chunk: 32 k x 256 n, staged K-major as well (kind::tf32 with an N-major B and no swizzle returned zeros on the B200:
-        // tools/probe/tc_probe.cu): 16-byte unit (n, k4) = B[4 k4 .. 4 k4 + 3][n] at k4 * 256 + n.  One column per thread: the four
-        // scalar loads are coalesced across the warp, the 16-byte stores are consecutive
-        float4* Bh = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES);
-        float4* Bl = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES + TC_B_BYTES);
-        if (tid < ncols) {
-            const float* bp = Bm + (size_t)(it * TC_BK) * MH_LD3V + n0 + tid;
-#pragma unroll
-            for (int k4 = 0; k4 < TC_BK / 4; ++k4) {
-                const float4 v = make_float4(bp[(size_t)(4 * k4) * MH_LD3V], bp[(size_t)(4 * k4 + 1) * MH_LD3V], bp[(size_t)(4 * k4 + 2) * MH_LD3V],
-                                             bp[(size_t)(4 * k4 + 3) * MH_LD3V]);
-                float4 hi, lo;
-                tc_split4(v, hi, lo);
-                Bh[k4 * TC_BN + tid] = hi; Bl[k4 * TC_BN + tid] = lo;
-            }
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
+            tc_wait(bar0 + 24 + 8 * s, (uint32_t)(it >> 1) & 1u);               // the basis chunk has landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_h = sbase + s * TC_STAGE_BYTES, a_l = a_h + TC_A_BYTES;
             const uint32_t b_h = a_h + 2 * TC_A_BYTES, b_l = b_h + TC_B_BYTES;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_fwd_tc(const float* __re
 int mh_gemm_fwd_tc(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape,
                    cudaStream_t st) {
     MH_CUDA(c, cudaFuncSetAttribute(k_gemm_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    k_gemm_fwd_tc<<<dim3(mh_cdiv(MH_LD3V, TC_BN), mh_cdiv(nbodies, TC_BM)), TC_THREADS, TC_SMEM_BYTES, st>>>(pf, c->pext, vshaped, vposed,
+    k_gemm_fwd_tc<<<dim3(mh_cdiv(MH_LD3V, TC_BN), mh_cdiv(nbodies, TC_BM)), TC_THREADS, TC_SMEM_BYTES, st>>>(pf, c->pextF, vshaped, vposed,
                                                                                                          nbodies, Npers, per_body_shape);
     MH_LAUNCHED(c);
     return MH_OK;
@@ -203,10 +203,10 @@ constexpr int TCB_SMEM_BYTES = 2 * TCB_STAGE_BYTES;
 constexpr int TCB_KLEN = MH_LD3V / MH_KSPLIT;
 static_assert(MH_LD3V % MH_KSPLIT == 0 && TCB_KLEN % TC_BK == 0 && MH_NEXT % 16 == 0, "split-K must tile the padded row");
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bwd_tc(const float* __restrict__ E, const float* __restrict__ Bext,
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bwd_tc(const float* __restrict__ E, const float* __restrict__ Bsplit,
                                                                float* __restrict__ Dpart, int M, int first_body, int nb_total) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    __shared__ __align__(8) unsigned long long bars[3];
+    __shared__ __align__(8) unsigned long long bars[5];                // stage 0 / 1 free, accumulator complete, stage 0 / 1 basis landed
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * TC_BM, ks = blockIdx.y;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bwd_tc(const float* __re
     const uint32_t sbase = tc_smem_u32(tc_smem);
     const uint32_t bar0 = tc_smem_u32(&bars[0]);
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+        for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -233,6 +233,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bwd_tc(const float* __re
         unsigned char* st = tc_smem + s * TCB_STAGE_BYTES;
         const int k0 = kbeg + it * TC_BK;
         if (it >= 2) { tc_wait(bar0 + 8 * s, phase[s]); phase[s] ^= 1u; }
+        // B chunk (hi | lo of 208 basis rows x 32 k, already split, 16-byte unit (n, k4) at k4 * 208 + n): one TMA bulk copy
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_bulk_load(sbase + s * TCB_STAGE_BYTES + 2 * TC_A_BYTES, Bsplit + ((size_t)ks * NIT + it) * (2 * TCB_B_BYTES / 4), 2 * TCB_B_BYTES,
+                         bar0 + 24 + 8 * s);
+        }
         float4* Ah = reinterpret_cast<float4*>(st);
         float4* Al = reinterpret_cast<float4*>(st + TC_A_BYTES);
 #pragma unroll
@@ -245,23 +251,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bwd_tc(const float* __re
             tc_split4(v, hi, lo);
             Ah[id] = hi; Al[id] = lo;
         }
-        // B chunk: 208 basis rows x 32 k: 16-byte unit (n, k4) at k4 * 208 + n
-        float4* Bh = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES);
-        float4* Bl = reinterpret_cast<float4*>(st + 2 * TC_A_BYTES + TCB_B_BYTES);
-#pragma unroll
-        for (int i = 0; i < (MH_NEXT * 8 + TC_THREADS - 1) / TC_THREADS; ++i) {
-            const int id = tid + TC_THREADS * i;
-            if (id < MH_NEXT * 8) {
-                const int n = id % MH_NEXT, k4 = id / MH_NEXT;
-                const float4 v = *reinterpret_cast<const float4*>(Bext + (size_t)n * MH_LD3V + k0 + k4 * 4);
-                float4 hi, lo;
-                tc_split4(v, hi, lo);
-                Bh[id] = hi; Bl[id] = lo;
-            }
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
+            tc_wait(bar0 + 24 + 8 * s, (uint32_t)(it >> 1) & 1u);               // the basis chunk has landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_h = sbase + s * TCB_STAGE_BYTES, a_l = a_h + TC_A_BYTES;
             const uint32_t b_h = a_h + 2 * TC_A_BYTES, b_l = b_h + TCB_B_BYTES;
@@ -310,8 +303,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bwd_tc(const float* __re
 
 int mh_gemm_bwd_tc(mh_ctx* c, const float* E, float* dpf_part, int M, int first_body, int nb_total, cudaStream_t st) {
     MH_CUDA(c, cudaFuncSetAttribute(k_gemm_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_BYTES));
-    k_gemm_bwd_tc<<<dim3(mh_cdiv(M, TC_BM), MH_KSPLIT), TC_THREADS, TCB_SMEM_BYTES, st>>>(E, c->pext, dpf_part, M, first_body, nb_total);
+    k_gemm_bwd_tc<<<dim3(mh_cdiv(M, TC_BM), MH_KSPLIT), TC_THREADS, TCB_SMEM_BYTES, st>>>(E, c->pextB, dpf_part, M, first_body, nb_total);
     MH_LAUNCHED(c);
+    return MH_OK;
+}
+
+// The constant operand of both contractions, split into TF32 hi | lo halves and laid out per (tile, chunk) exactly as the kernels
+// stage it in shared memory, so that one chunk is one contiguous block (one TMA bulk copy).
+static inline float tc_tf32_rna_host(float x) {             // cvt.rna.tf32.f32: nearest, ties away from zero, 10 mantissa bits kept
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+int mh_gemm_tc_prepare(mh_ctx* c, const std::vector<float>& pext) {
+    auto split = [](float x, float& hi, float& lo) { hi = tc_tf32_rna_host(x); lo = tc_tf32_rna_host(x - hi); };
+    // forward: block (column tile nt, chunk it) = [hi: 8 k4 x 256 n units of 4 k | lo: same]
+    const int ntile = mh_cdiv(MH_LD3V, TC_BN), nit = MH_KPF / TC_BK;
+    std::vector<float> F((size_t)ntile * nit * (2 * TC_B_BYTES / 4), 0.f);
+    for (int nt = 0; nt < ntile; ++nt)
+        for (int it = 0; it < nit; ++it) {
+            float* hi = &F[((size_t)nt * nit + it) * (2 * TC_B_BYTES / 4)];
+            float* lo = hi + TC_B_BYTES / 4;
+            for (int k4 = 0; k4 < TC_BK / 4; ++k4)
+                for (int n = 0; n < TC_BN; ++n) {
+                    const int col = nt * TC_BN + n;
+                    if (col >= MH_LD3V) continue;
+                    for (int j = 0; j < 4; ++j)
+                        split(pext[(size_t)(it * TC_BK + 4 * k4 + j) * MH_LD3V + col], hi[(size_t)(k4 * TC_BN + n) * 4 + j], lo[(size_t)(k4 * TC_BN + n) * 4 + j]);
+                }
+        }
+    MH_TRY(mh_upload_floats(c, &c->pextF, F));
+    // backward: block (split ks, chunk it) = [hi: 8 k4 x 208 basis rows units of 4 k | lo: same]
+    const int nitb = TCB_KLEN / TC_BK;
+    std::vector<float> B((size_t)MH_KSPLIT * nitb * (2 * TCB_B_BYTES / 4), 0.f);
+    for (int ks = 0; ks < MH_KSPLIT; ++ks)
+        for (int it = 0; it < nitb; ++it) {
+            float* hi = &B[((size_t)ks * nitb + it) * (2 * TCB_B_BYTES / 4)];
+            float* lo = hi + TCB_B_BYTES / 4;
+            const int k0 = ks * TCB_KLEN + it * TC_BK;
+            for (int k4 = 0; k4 < TC_BK / 4; ++k4)
+                for (int n = 0; n < MH_NEXT; ++n)
+                    for (int j = 0; j < 4; ++j)
+                        split(pext[(size_t)n * MH_LD3V + k0 + 4 * k4 + j], hi[(size_t)(k4 * MH_NEXT + n) * 4 + j], lo[(size_t)(k4 * MH_NEXT + n) * 4 + j]);
+        }
+    MH_TRY(mh_upload_floats(c, &c->pextB, B));
     return MH_OK;
 }
 

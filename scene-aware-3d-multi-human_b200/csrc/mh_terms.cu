@@ -166,7 +166,7 @@ __global__ void k_velocity(const float* __restrict__ trans_all, int T, int N, in
 // -------------------------------------------------------------------------------------------------
 // Contact term: streaming exact top-32 nearest scene points of the lowest vertex (optimizer.py:487-506).
 // One CTA per KNN_Q consecutive local person-frames: every scene point is loaded once and tested against all of them (the
-// cloud is L2-resident; one CTA per person-frame is L2-bandwidth bound).  KNN_Q is chosen so that the grid still fills the GPU.  Pass A: per-thread minima -> the 32nd
+// cloud is L2-resident; one CTA per person-frame is L2-bandwidth bound).  KNN_Q is chosen so that the grid still fills the GPU twice.  Pass A: per-thread minima -> the 32nd
 // smallest of them bounds the 32nd nearest distance; pass B collects every point under the bound; the 32 nearest are ranked
 // exactly by (distance, index).  No distance matrix, no sort over M.
 #define KNN_THREADS 256
@@ -337,11 +337,14 @@ int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) 
                                                      g_trans, losses);
     MH_LAUNCHED(c);
     if (c->M > 0) {
-        const int waves2 = 2 * c->num_sms;                             // person-frames per CTA: as many as keep two waves of CTAs
-        if (TN >= 8 * waves2) k_contact<8><<<mh_cdiv(TN, 8), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses);
-        else if (TN >= 4 * waves2) k_contact<4><<<mh_cdiv(TN, 4), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses);
-        else if (TN >= 2 * waves2) k_contact<2><<<mh_cdiv(TN, 2), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses);
-        else k_contact<1><<<TN, KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses);
+        // person-frames per CTA: as many as keep two waves of CTAs -- measured: 256 CTAs of 2 are slower than 512 CTAs of 1 on 148 SMs
+        // (MH_KNN_Q forces a value: testing aid)
+        const int w2 = 2 * c->num_sms;
+        int Q = TN >= 8 * w2 ? 8 : TN >= 4 * w2 ? 4 : TN >= 2 * w2 ? 2 : 1;
+        if (const char* v = getenv("MH_KNN_Q")) { const int q = atoi(v); if (q == 1 || q == 2 || q == 4 || q == 8) Q = q; }
+#define MH_CONTACT(QQ) k_contact<QQ><<<mh_cdiv(TN, QQ), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses)
+        if (Q == 8) MH_CONTACT(8); else if (Q == 4) MH_CONTACT(4); else if (Q == 2) MH_CONTACT(2); else MH_CONTACT(1);
+#undef MH_CONTACT
         MH_LAUNCHED(c);
         k_foot<<<mh_cdiv(d.T, d.B), 128, 0, st>>>(c->verts, c->lowidx, c->contact, d.T, d.N, d.B, c->c.reg_foot_sliding, c->dverts, losses);
         MH_LAUNCHED(c);

@@ -263,8 +263,11 @@ def test_optimizer_updates_match_torch(c1, L):
         assert np.abs(ours - tt.detach().numpy()).max() <= 2e-6 * np.abs(tt.detach().numpy()).max()
 
 
-def test_contact_knn_against_brute_force(pkg, L):
-    """Streaming exact top-32 (no distance matrix) vs numpy on a 50k-point cloud with duplicated points (ties)."""
+@pytest.mark.parametrize('knn_q', [1, 2, 8])
+def test_contact_knn_against_brute_force(pkg, L, knn_q, monkeypatch):
+    """Streaming exact top-32 (no distance matrix) vs numpy on a 50k-point cloud with duplicated points (ties); 1, 2 and 8
+    person-frames per CTA (the grid-filling rule picks 8 only at benchmark sizes: MH_KNN_Q forces it here)."""
+    monkeypatch.setenv('MH_KNN_Q', str(knn_q))
     g, data, meta = gh.load_fit('fit_n2.npz')
     N, T, W, H, batch = meta[:5]
     opt = gh.make_optimizer(pkg, g, data, meta, coefs=dict(gh.COEFS, depth=0.0, silhouette=0.0), max_scene_points=60000)
