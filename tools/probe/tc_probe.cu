@@ -1,4 +1,5 @@
-// Development probe (standalone, nvcc -gencode arch=compute_100a,code=sm_100a): one tcgen05.mma kind::tf32 M=128 N=256 K=8 with
+// Development probe, standalone:  nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/probe/tc_probe tools/probe/tc_probe.cu
+// then  gpurun -- ./tools/probe/tc_probe .  One tcgen05.mma kind::tf32 M=128 N=256 K=8 with
 // operands laid out by hand, under several descriptor hypotheses.  Prints which hypothesis reproduces A.B.
 #include <cstdio>
 #include <cstdint>
