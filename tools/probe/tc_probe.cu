@@ -119,7 +119,6 @@ int main() {
         {2048, 128, 128, 8192, 1, 0},    // B swapped only
         {128, 2048, 8192, 128, 1, 0},    // A swapped only
         {2048, 128, 4096, 128, 0, 1},    // B K-major (n rows): lbo = K-chunk stride (256 * 16), sbo = 8-row stride
-        {2048, 128, 128, 4096, 0, 1},
     };
     for (size_t i = 0; i < sizeof(hyps) / sizeof(hyps[0]); ++i) {
         cudaMemset(dC, 0xff, C.size() * 4); cudaMemset(dF, 0, 16);
