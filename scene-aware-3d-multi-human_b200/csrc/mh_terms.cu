@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict
         }
         __syncthreads();
         bool all = true;
-        if (tid < KNN_Q && !sdone[tid]) {
+        // volatile: without it the compiler loads sdone[0] in EVERY thread before testing tid (harmless, but a read / write hazard for racecheck)
+        if (tid < KNN_Q && !reinterpret_cast<volatile int*>(sdone)[tid]) {
             const int cnt = scount[tid];
             if (cnt >= MH_KNN && cnt <= KNN_CAP) sdone[tid] = 1;
             else {               // bisection on the bound (only reached with > KNN_CAP near-ties)
