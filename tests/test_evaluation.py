@@ -95,3 +95,38 @@ def test_device_joints_and_metrics():
     r = ev.compute_mm_pck_results(_optvar(g), g['gt17'], g['vis17'], joints, g['cam_K'])
     got = np.array([r[k] for k in ('mm_abs_error', 'mm_rel_error', 'mm_mrpe', 'pck_rel', 'ap25_root', 'abs_jitter')], np.float64)
     assert np.abs(got - g['mm']).max() <= 0.02, (got, g['mm'])                   # mm / percent: 1e-5 m of joint noise
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/mhmocap'), reason='differential check against the reference needs /root/reference (build container only)')
+@pytest.mark.parametrize('seed,T,N,K,J', [(0, 3, 2, 2, 17), (1, 4, 3, 2, 17), (2, 2, 1, 3, 19), (3, 5, 4, 4, 17), (4, 3, 2, 5, 19)])
+def test_differential_against_the_reference(seed, T, N, K, J):
+    """Random sequences (more / fewer predictions than annotations, invisible joints and roots, both joint layouts): the mirror and the
+    UNMODIFIED reference, fed the same joints, agree bit for bit."""
+    sys.path.insert(0, '/root/reference')
+    argv, sys.argv = sys.argv, sys.argv[:1]
+    try:
+        import mhmocap.evaluate as rev
+    finally:
+        sys.argv = argv
+        sys.path.remove('/root/reference')
+    import torch
+    ev = _load_eval_module()
+    rng = np.random.default_rng(100 + seed)
+    jm = rng.normal(0, 0.3, (T * N, 17, 3)).astype(np.float32)
+    ja = rng.normal(0, 0.3, (T * N, 17, 3)).astype(np.float32)
+    optvar = {'poses_T': (rng.normal(0, 0.5, (T, N, 1, 3)) + [0, 0, 4]).astype(np.float32), 'poses_smpl': rng.normal(0, 0.2, (T, N, 72)).astype(np.float32),
+              'betas_smpl': rng.normal(0, 0.5, (T, N, 10)).astype(np.float32), 'scale_factor': (1 + 0.1 * rng.normal(0, 1, (1, N, 1, 1))).astype(np.float32),
+              'valid_smpl': np.ones((T, N, 1), np.float32)}
+    gt = (rng.normal(0, 0.5, (T, K, J, 3)) + [0, 0, 4]).astype(np.float32)
+    vis = (rng.random((T, K, J, 1)) > 0.3).astype(np.float32)
+    cam_K = np.array([[900, 0, 500], [0, 950, 300], [0, 0, 1]], np.float32)
+
+    def SMPLPY(betas, poses):
+        return {'joints_mupots': torch.from_numpy(jm), 'joints_alphapose': torch.from_numpy(ja)}
+
+    ref = rev.compute_smpl_pred_error_3dproj(optvar, gt.copy(), vis.copy(), SMPLPY, cam_K)
+    got = ev.compute_smpl_pred_error_3dproj(optvar, gt, vis, lambda b, p, which: jm if which == 'mupots' else ja, cam_K)
+    for k in KEYS:
+        assert np.array_equal(np.asarray(ref[k]), got[k]), (k, seed)
+    assert ev.masked_average_error(got['abs_dist'], got['valid_joints']) == rev.masked_average_error(ref['abs_dist'], ref['valid_joints'])
+    assert ev.masked_average_pck(got['rel_dist'], got['valid_joints'], 0.15) == rev.masked_average_pck(ref['rel_dist'], ref['valid_joints'], 0.15)
