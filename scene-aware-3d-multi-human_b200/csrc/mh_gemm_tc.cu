@@ -101,6 +101,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_fwd_tc(const float* __re
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     uint32_t phase[2] = {0u, 0u};
     constexpr int NIT = MH_KPF / TC_BK;
+    float4 av[4];
+    auto load_a = [&](int chunk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = tid + TC_THREADS * i;
+            const int row = id & (TC_BM - 1), k4 = id >> 7;
+            av[i] = (m0 + row < M) ? *reinterpret_cast<const float4*>(Am + (size_t)(m0 + row) * MH_KPF + chunk * TC_BK + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_a(0);
     for (int it = 0; it < NIT; ++it) {
         const int s = it & 1;
         unsigned char* st = tc_smem + s * TC_STAGE_BYTES;
@@ -111,19 +121,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_fwd_tc(const float* __re
             tc_bulk_load(sbase + s * TC_STAGE_BYTES + 2 * TC_A_BYTES, Bsplit + ((size_t)blockIdx.x * NIT + it) * (2 * TC_B_BYTES / 4), 2 * TC_B_BYTES,
                          bar0 + 24 + 8 * s);
         }
-        // A chunk: 128 rows x 32 k, K-major: 16-byte unit (row, k4) at k4 * 128 + row
+        // A chunk: 128 rows x 32 k, K-major: 16-byte unit (row, k4) at k4 * 128 + row; the values were loaded one iteration ahead
         float4* Ah = reinterpret_cast<float4*>(st);
         float4* Al = reinterpret_cast<float4*>(st + TC_A_BYTES);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int id = tid + TC_THREADS * i;
-            const int row = id & (TC_BM - 1), k4 = id >> 7;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + row < M) v = *reinterpret_cast<const float4*>(Am + (size_t)(m0 + row) * MH_KPF + it * TC_BK + k4 * 4);
             float4 hi, lo;
-            tc_split4(v, hi, lo);
-            Ah[id] = hi; Al[id] = lo;
+            tc_split4(av[i], hi, lo);
+            Ah[tid + TC_THREADS * i] = hi; Al[tid + TC_THREADS * i] = lo;
         }
+        if (it + 1 < NIT) load_a(it + 1);                                     // in flight across the barrier and the MMA issue
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
@@ -228,6 +235,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bwd_tc(const float* __re
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MH_NEXT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     uint32_t phase[2] = {0u, 0u};
     constexpr int NIT = TCB_KLEN / TC_BK;
+    float4 av[4];
+    auto load_a = [&](int kk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = tid + TC_THREADS * i;
+            const int row = id & (TC_BM - 1), k4 = id >> 7;
+            av[i] = (m0 + row < M) ? *reinterpret_cast<const float4*>(E + (size_t)(first_body + m0 + row) * MH_LD3V + kk + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_a(kbeg);
     for (int it = 0; it < NIT; ++it) {
         const int s = it & 1;
         unsigned char* st = tc_smem + s * TCB_STAGE_BYTES;
@@ -243,14 +260,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_bwd_tc(const float* __re
         float4* Al = reinterpret_cast<float4*>(st + TC_A_BYTES);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int id = tid + TC_THREADS * i;
-            const int row = id & (TC_BM - 1), k4 = id >> 7;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + row < M) v = *reinterpret_cast<const float4*>(E + (size_t)(first_body + m0 + row) * MH_LD3V + k0 + k4 * 4);
             float4 hi, lo;
-            tc_split4(v, hi, lo);
-            Ah[id] = hi; Al[id] = lo;
+            tc_split4(av[i], hi, lo);
+            Ah[tid + TC_THREADS * i] = hi; Al[tid + TC_THREADS * i] = lo;
         }
+        if (it + 1 < NIT) load_a(k0 + TC_BK);                                  // in flight across the barrier and the MMA issue
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
