@@ -226,9 +226,10 @@ int mh_read_planes(mh_ctx* ctx, int32_t t_local0, int32_t count, float* depths_h
  * oldest first; *n_cycles is the capacity in and the number of cycles written out.  Blocking. */
 int mh_set_timing(mh_ctx* ctx, int32_t on);
 int mh_read_timing(mh_ctx* ctx, float* out_ms, int32_t* n_cycles);
-/* development aid: per-phase cycle counters of the render kernel summed over its CTAs (8 int64: load+NDC | binning |
- * tile staging | pair scatter | per-pixel + silhouette backward | sums + depth backward | chain rule | unused);
- * `on` (re)starts / stops counting, out8_host (may be NULL) receives the counters accumulated so far. */
+/* development aid: counters of the render kernel summed over its CTAs, 32 int64: [0..7] cycles per phase (load+NDC | binning |
+ * tile set-up + descriptors | prune + evaluate | per-pixel + silhouette backward | sums + depth backward | chain rule | unused),
+ * [8..19] (face, pixel)-pair statistics when the library was built with -DMH_RSTATS (else 0), rest unused;
+ * `on` (re)starts / stops counting, out32_host (may be NULL) receives the counters accumulated so far. */
 int mh_render_profile(mh_ctx* ctx, int32_t on, long long* out32_host);
 /* testing aid: REDUCE the render capacities (0 keeps a value) so that small inputs reach the coarse-binning path (maxbins)
  * and the MH_E_CAPACITY paths (tile-list entries per body, depth-winner entries per body); clears the capacity flag */

@@ -920,17 +920,18 @@ int mh_render_debug(mh_ctx* c, int t, int n, float* zbuf_dev, float* alpha_dev, 
 }
 
 // Development aid: per-phase cycle counters of the render kernel, summed over the CTAs (8 slots:
-// load+ndc | binning | tile staging | pair scatter | per-pixel + silhouette backward | sums + depth backward | chain rule | -).
-extern "C" int mh_render_profile(mh_ctx* c, int32_t on, long long* out8_host /* 32 values */) {
+// load+ndc | binning | tile set-up + descriptors | prune + evaluate | per-pixel + silhouette backward | sums + depth backward | chain rule | -),
+// then the pair statistics of an -DMH_RSTATS build.
+extern "C" int mh_render_profile(mh_ctx* c, int32_t on, long long* out32_host) {
     if (!c || !c->rs) return MH_E_ARG;
     cudaSetDevice(c->d.device);
     MhRenderScratch* rs = c->rs;
     const size_t n = (size_t)rs->nctas * MH_NPROF;
-    if (out8_host && rs->prof) {
+    if (out32_host && rs->prof) {
         std::vector<long long> h(n);
         MH_CUDA(c, cudaDeviceSynchronize());
         MH_CUDA(c, cudaMemcpy(h.data(), rs->prof, n * sizeof(long long), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < MH_NPROF; ++k) { out8_host[k] = 0; for (int b = 0; b < rs->nctas; ++b) out8_host[k] += h[(size_t)b * MH_NPROF + k]; }
+        for (int k = 0; k < MH_NPROF; ++k) { out32_host[k] = 0; for (int b = 0; b < rs->nctas; ++b) out32_host[k] += h[(size_t)b * MH_NPROF + k]; }
     }
     if (on && !rs->prof) MH_CUDA(c, cudaMalloc((void**)&rs->prof, n * sizeof(long long)));
     if (on) MH_CUDA(c, cudaMemset(rs->prof, 0, n * sizeof(long long)));
