@@ -15,6 +15,7 @@ Differences from the reference that a caller can observe (all documented in DESI
     (``optimizer.py:595``);
   * with ``torch.distributed`` initialised, frames are sharded over the ranks (``sharding.py``).
 """
+import math
 import os
 
 import numpy as np
@@ -44,6 +45,30 @@ class _DevView(object):
     """Exposes a raw device pointer of the library as a ``__cuda_array_interface__`` object."""
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+
+
+def one_euro_over_time(x, min_cutoff, beta, frame_rate=25, d_cutoff=1.0):
+    """One-Euro filter of ``x (T, ...)`` along axis 0 with time stamps ``i / frame_rate`` (``one_euro_filter.py:16-53`` driven as in
+    ``optimizer.py:643-648``: first sample passes through, ``dx0 = 0``).  Host numpy: the arrays are T x N x 75 floats."""
+    x = np.array(x, copy=True)
+    x_prev, dx_prev, t_prev = x[0].copy(), np.zeros_like(x[0]), 0.0
+
+    def alpha(t_e, cutoff):
+        r = 2 * math.pi * cutoff * t_e
+        return r / (r + 1)
+
+    for i in range(1, len(x)):
+        t = i / frame_rate
+        t_e = t - t_prev
+        dx = (x[i] - x_prev) / t_e
+        a_d = alpha(t_e, d_cutoff)
+        dx_hat = a_d * dx + (1 - a_d) * dx_prev
+        a = alpha(t_e, min_cutoff + beta * np.abs(dx_hat))
+        x_hat = a * x[i] + (1 - a) * x_prev
+        # the reference stores the time stamp through its mask, i.e. as an array of x's dtype: from the second step on t_e is float32
+        x_prev, dx_prev, t_prev = x_hat, dx_hat, np.full_like(x_hat, t)
+        x[i] = x_hat
+    return x
 
 
 class SMPLOptimizerBase(object):
@@ -444,6 +469,28 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         j17 = np.empty((b.shape[0], 17, 3), np.float32)
         self.ctx.call('mh_smpl_forward', L.ptr(b), L.ptr(p), b.shape[0], L.ptr(verts), L.ptr(j17))
         return verts, j17
+
+    def predict(self, poses_T, poses_smpl, betas_smpl, scale_factor):
+        """``SMPLOptimizerBase.predict`` (``optimizer.py:133-143``; not called by the reference's drivers): absolute vertices and
+        sparse joints of the given bodies, ``scale_factor * SMPL(betas, poses) + poses_T`` with numpy broadcasting as there."""
+        if self.ctx is None:
+            raise RuntimeError('predict needs the device context: call init_optimized_variables first')
+        verts, joints = self.smpl_forward(betas_smpl, poses_smpl)
+        return scale_factor * verts + poses_T, scale_factor * joints + poses_T
+
+    def get_filtered_vertices_by_smpl(self, min_cutoff_T=0.004, min_cutoff_angles=0.1, beta_T=0.7, beta_angles=0.1, frame_rate=25):
+        """``optimizer.py:639-661`` (not called by the reference's drivers): One-Euro filter of the optimised translations and pose
+        angles over time (here with the proper time stamps ``i / frame_rate``, unlike ``one_euro_filter``), then SMPL on the
+        filtered poses; absolute vertices (T, N, 6890, 3) as a float32 tensor on ``self.device``.  Single-rank only."""
+        if self.world != 1:
+            raise NotImplementedError('get_filtered_vertices_by_smpl: gather the variables with get_optimized_variables() first')
+        ctx, N, T = self.ctx, self.num_people, self.T_local
+        pT = one_euro_over_time(ctx.get_param(L.P_POSES_T, (T, N, 1, 3)), min_cutoff_T, beta_T, frame_rate)
+        th = one_euro_over_time(ctx.get_param(L.P_POSES_SMPL, (T, N, 72)), min_cutoff_angles, beta_angles, frame_rate)
+        betas = np.tile(ctx.get_param(L.P_BETAS, (1, N, 10)), (T, 1, 1))
+        verts, _ = self.smpl_forward(betas.reshape(-1, 10), th.reshape(-1, 72))
+        scale = np.power(np.float32(1.1), ctx.get_param(L.P_XSCALE, (1, N, 1, 1))).astype(np.float32)
+        return torch.from_numpy((scale * verts.reshape(T, N, -1, 3) + pT).astype(np.float32)).to(self.device)
 
     def smpl_regress(self, betas, poses, regressor):
         """SMPL forward + ``regressor (J, 6890) . verts`` on the device (``smpl.py:376-389`` with any of the reference's regressors:

@@ -98,3 +98,27 @@ def test_frame_ranges(pkg):
     assert sh.neighbours(0, 2, ranges) == (None, None)              # rank 1 owns nothing -> no neighbour
     ranges = [sh.frame_range(512, 8, r, 8) for r in range(8)]
     assert sh.neighbours(3, 8, ranges) == (2, 4) and sh.neighbours(0, 8, ranges) == (None, 1) and sh.neighbours(7, 8, ranges) == (6, None)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/mhmocap'), reason='differential check against the reference needs /root/reference (build container only)')
+def test_one_euro_over_time_matches_the_reference_filter(pkg):
+    """`get_filtered_vertices_by_smpl` drives the reference's OneEuroFilter with time stamps i / frame_rate (optimizer.py:643-648);
+    the host mirror reproduces the class bit for bit (dx0 = zeros: the reference passes the int 0, which its own assert rejects)."""
+    sys.path.insert(0, '/root/reference')
+    try:
+        from mhmocap.one_euro_filter import OneEuroFilter
+    finally:
+        sys.path.remove('/root/reference')
+    opt = _mod(pkg, 'optimizer')
+    rng = np.random.default_rng(4)
+    for shape, mc, beta in (((9, 3, 1, 3), 0.004, 0.7), ((6, 2, 72), 0.1, 0.1)):
+        x = (rng.normal(0, 0.3, shape).cumsum(0)).astype(np.float32)
+        ref = x.copy()
+        f = OneEuroFilter(0, ref[0], dx0=np.zeros_like(ref[0]), min_cutoff=mc, beta=beta, d_cutoff=1.0)
+        for i in range(1, len(ref)):
+            ref[i] = f(i / 25, ref[i])
+        got = opt.one_euro_over_time(x, mc, beta, 25)
+        assert got.dtype == np.float32 and np.array_equal(got, ref)
+        assert np.array_equal(got[0], x[0]) and not np.array_equal(got[1:], x[1:])
+    one = opt.one_euro_over_time(x[:1], 0.1, 0.1)
+    assert np.array_equal(one, x[:1])                                             # a single frame passes through
