@@ -82,3 +82,29 @@ traffic = num('dram__bytes_read.sum') + num('dram__bytes_write.sum')
 json.dump({'workload': 'c3s', 'n_gpus': 1, 'dram_bytes_per_launch': traffic, 'person_frames_per_launch': units, 'dram_bytes_per_person_frame': traffic / units,
            'source': f'profiles/{tag}_render_ncu.md'}, open(os.path.join(Pd, 'render_traffic.json'), 'w'), indent=1)
 print('wrote profiles for', tag, 'traffic per person-frame', traffic / units)
+
+
+# ---- the tensor-core contractions (optional capture)
+rep2 = os.path.join(G, f'{tag}_gemm_tc.ncu-rep')
+if os.path.exists(rep2):
+    raw = subprocess.run(['ncu', '-i', rep2, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h, u, rows2 = rr[0], rr[1], rr[2:]
+    keep2 = ('Kernel Name', 'Block Size', 'Grid Size', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__registers_per_thread',
+             'launch__shared_mem_per_block_dynamic', 'sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+             'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+             'smsp__mem_tensor_reads_op_utcmma_matrix_c.sum.pct_of_peak_sustained_elapsed', 'smsp__mem_tensor_writes_op_utcmma.sum.pct_of_peak_sustained_elapsed',
+             'smsp__mem_tensor_reads_op_ldt.sum.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+             'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+             'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+             'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+             'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum')
+    ki = h.index('Kernel Name')
+    with open(os.path.join(Pd, f'{tag}_gemm_tc_ncu.md'), 'w') as f:
+        f.write('# `k_gemm_fwd_tc` / `k_gemm_bwd_tc`: one launch each, `ncu --set full --clock-control none` (workload c3s: 528 bodies incl. halo slots, 1280x720)\n\n')
+        f.write('Tensor-core contractions of `mh_gemm_tc.cu` (tcgen05.mma kind::tf32, 3 x TF32 split, accumulator in TMEM, basis by TMA bulk copies).\n\n')
+        f.write('| metric | unit | ' + ' | '.join(r[ki].split('(')[0] for r in rows2) + ' |\n|---|---|' + '---|' * len(rows2) + '\n')
+        for i, (k, uu) in enumerate(zip(h, u)):
+            if k in keep2:
+                f.write(f'| {k} | {uu} | ' + ' | '.join(r[i] for r in rows2) + ' |\n')
+    print('wrote', f'{tag}_gemm_tc_ncu.md')
