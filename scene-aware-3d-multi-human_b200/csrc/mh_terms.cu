@@ -452,7 +452,7 @@ __global__ void k_init_2d(const float* __restrict__ j17, const float* __restrict
         const float P[3] = {s * J[0] + trans[(size_t)i * 3], s * J[1] + trans[(size_t)i * 3 + 1], s * J[2] + trans[(size_t)i * 3 + 2]};
         float uv[2];
         mh_project(P, cam.K, cam.has_kd ? cam.Kd : nullptr, uv);
-        const float v = vis[(size_t)i * MH_NJR + lane];
+        const float v = vis[(size_t)i * MH_NJR + lane] * cam.w17[lane];            // pose_weights * vis_pose2d (optimizer.py:754-756)
         const float* q = pose2d + ((size_t)i * MH_NJR + lane) * 3;
         const float du = v * uv[0] - v * q[0], dv = v * uv[1] - v * q[1];
         l = du * du + dv * dv;

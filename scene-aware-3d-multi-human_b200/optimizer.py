@@ -13,7 +13,10 @@ Differences from the reference that a caller can observe (all documented in DESI
     inside batches of ``batch_size`` consecutive frames;
   * ``fit(num_iter <= 30)`` returns (scene outputs ``None``) instead of raising ``UnboundLocalError``
     (``optimizer.py:595``);
-  * with ``torch.distributed`` initialised, frames are sharded over the ranks (``sharding.py``).
+  * with ``torch.distributed`` initialised, frames are sharded over the ranks (``sharding.py``).  Shard edges must be
+    multiples of the dataloader's batch size, which the reference API only reveals in ``fit``: without the
+    ``batch_size=`` extension of ``init_optimized_variables`` every rank runs the (cheap) translation init on the WHOLE
+    sequence and the frames are sharded when ``fit`` sees the first batch.
 """
 import math
 import os
@@ -148,18 +151,30 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _make_context(self, T_total, N, B=None):
+        """Device context of this rank.  With several ranks and the batch size still unknown (the reference API passes it
+        only through the dataloader of ``fit``) the context covers the WHOLE sequence, replicated, and ``_reshard`` replaces
+        it when the first batch arrives; ``self._dist`` says whether the per-cycle exchanges run."""
         self.num_people = N
         self.T_total = T_total
         Bq = B if B else T_total
-        self.ranges = [sharding.frame_range(T_total, Bq, r, self.world) for r in range(self.world)]
-        self.t0, self.t1 = self.ranges[self.rank]
-        if self.t1 <= self.t0:
-            raise RuntimeError(f'rank {self.rank} owns no frames: {T_total} frames in batches of {Bq} over {self.world} ranks')
-        self.prev, self.next = sharding.neighbours(self.rank, self.world, self.ranges)
+        self._dist = self.world > 1 and bool(B)
+        if self._dist:
+            self.ranges = [sharding.frame_range(T_total, Bq, r, self.world) for r in range(self.world)]
+            self.t0, self.t1 = self.ranges[self.rank]
+            empty = [r for r, (a, b) in enumerate(self.ranges) if b <= a]
+            if empty:
+                # raised identically on EVERY rank (it only depends on T, B, world): nobody is left waiting in a collective
+                raise RuntimeError(f'ranks {empty} own no frames: {T_total} frames in batches of {Bq} over {self.world} ranks; '
+                                   f'use at most {(T_total + Bq - 1) // Bq} ranks')
+            self.prev, self.next = sharding.neighbours(self.rank, self.world, self.ranges)
+        else:
+            self.ranges = [(0, T_total)]
+            self.t0, self.t1 = 0, T_total
+            self.prev = self.next = None
         self.T_local = self.t1 - self.t0
         torch.cuda.set_device(self.device)
-        self.ctx = L.Context(self.T_local, N, self.img_h, self.img_w, B=Bq, device=self.device_ordinal, rank=self.rank,
-                             world=self.world, t0=self.t0, T_total=T_total,
+        self.ctx = L.Context(self.T_local, N, self.img_h, self.img_w, B=Bq, device=self.device_ordinal,
+                             rank=self.rank if self._dist else 0, world=self.world if self._dist else 1, t0=self.t0, T_total=T_total,
                              M_max=self.max_scene_points if self.max_scene_points else self.img_h * self.img_w)
         self.ctx.set_model(self.model)
         self.ctx.set_camera(self.cam_K, self.K_ndc, self.cam_dist_coef)
@@ -176,15 +191,46 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         return self._views[which]
 
     def _set_batch(self, B):
-        ranges = [sharding.frame_range(self.T_total, B, r, self.world) for r in range(self.world)]
-        if ranges != self.ranges:
-            raise RuntimeError(f'the dataloader batch size {B} changes the frame sharding chosen at init; pass '
-                               f'batch_size={B} to init_optimized_variables')
+        if self.world > 1:
+            if not self._dist:
+                self._reshard(B)
+            elif [sharding.frame_range(self.T_total, B, r, self.world) for r in range(self.world)] != self.ranges:
+                raise RuntimeError(f'the dataloader batch size {B} changes the frame sharding chosen at init; pass '
+                                   f'batch_size={B} to init_optimized_variables (or none at all)')
         self.ctx.call('mh_set_batch', B)
         self.batch_size = B
 
+    def _leaves_to_host(self):
+        """All six leaves of the local context as host arrays (whole-sequence shapes when the context is replicated)."""
+        ctx, N, T = self.ctx, self.num_people, self.T_local
+        return dict(poses_T=ctx.get_param(L.P_POSES_T, (T, N, 3)), poses_smpl=ctx.get_param(L.P_POSES_SMPL, (T, N, 72)),
+                    betas=ctx.get_param(L.P_BETAS, (1, N, 10)), betas_ref=ctx.get_param(L.P_BETAS_REF, (1, N, 10)),
+                    zmin_lin=ctx.get_param(L.P_ZMIN_LIN, (T,)), zmax_lin=ctx.get_param(L.P_ZMAX_LIN, (T,)),
+                    xscale=ctx.get_param(L.P_XSCALE, (N,)))
+
+    def _reshard(self, B):
+        """Replace the replicated whole-sequence context of the init stage by this rank's frame shard (batch size ``B`` is
+        known now); the leaves move over, frame-indexed ones sliced to the shard."""
+        s = self._leaves_to_host()
+        N = self.num_people
+        self.ctx.close()
+        self._make_context(self.T_total, N, B)
+        ctx, st = self.ctx, self._stream()
+        sl = slice(self.t0, self.t1)
+        ctx.call('mh_set_optimize_scale', int(self.optim_scale_factor))
+        ctx.set_param(L.P_XSCALE, s['xscale'], st)
+        ctx.set_param(L.P_POSES_T, s['poses_T'][sl], st)
+        ctx.set_param(L.P_POSES_SMPL, s['poses_smpl'][sl], st)
+        ctx.set_param(L.P_BETAS, s['betas'], st)
+        ctx.set_param(L.P_BETAS_REF, s['betas_ref'], st)
+        ctx.set_param(L.P_ZMIN_LIN, s['zmin_lin'][sl], st)
+        ctx.set_param(L.P_ZMAX_LIN, s['zmax_lin'][sl], st)
+        ctx.call('mh_clear_filters')
+        ctx.call('mh_set_scene', None, 0, st)
+        torch.cuda.current_stream(self.device).synchronize()
+
     def _exchange_halo(self):
-        if self.world == 1:
+        if not self._dist:
             return 0, 0
         self.ctx.call('mh_halo_pack', self._stream())
         n = self.num_people * 75
@@ -201,6 +247,8 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         assert (pose2d.shape[:2] == poses_smpl.shape[:2] == betas_smpl.shape[:2] == valid_smpl.shape[:2]), (
             f'Error: invalid inputs {pose2d.shape}, {poses_smpl.shape}, {betas_smpl.shape}, {valid_smpl.shape}')
         T, N = pose2d.shape[0:2]
+        assert tuple(pose2d.shape[2:]) == (17, 3), f'pose2d must be (T, N, 17, 3) AlphaPose joints, got {pose2d.shape}'
+        assert tuple(poses_smpl.shape[2:]) == (72,) and tuple(betas_smpl.shape[2:]) == (10,), (poses_smpl.shape, betas_smpl.shape)
         if self.ctx is not None:
             self.ctx.close()
         self._make_context(T, N, batch_size)
@@ -243,7 +291,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         for it in range(num_iter):
             hp, hn = self._exchange_halo()
             ctx.call('mh_init_grads', hp, hn, st)
-            if self.world > 1:
+            if self._dist:
                 sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
             ctx.call('mh_init_update', lr, it + 1, st)
             lr *= 0.95
@@ -280,6 +328,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
                 while e < len(idxs) and int(idxs[e]) == int(idxs[e - 1]) + 1 and int(idxs[e]) < self.t1:
                     e += 1
                 tl, cnt = t - self.t0, e - j
+                assert tuple(arr['pose2d'].shape[2:]) == (17, 3), f"pose2d must be (B, N, 17, 3), got {arr['pose2d'].shape}"
                 dep = L.f32(arr['depths'][j:e]); seg = L.f32(arr['seg_mask'][j:e]); p2d = L.f32(arr['pose2d'][j:e])
                 th = L.f32(arr['poses_smpl'][j:e]); vl = L.f32(self.valid_smpl[t:t + cnt].reshape(cnt, N))
                 assert dep.shape == (cnt, H, W) and seg.shape == (cnt, N, H, W), (dep.shape, seg.shape)
@@ -325,7 +374,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
                 self._refresh_filters(min_cutoff1, beta1, min_cutoff2, beta2)
             hp, hn = self._exchange_halo()
             ctx.call('mh_fit_grads', hp, hn, st)
-            if self.world > 1:
+            if self._dist:
                 sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
             if cycle >= 30 and self.scene_update:
                 ma = self._update_scene_geometry()
@@ -348,7 +397,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         hp, hn = self._exchange_halo()
         st = self._stream()
         self.ctx.call('mh_fit_grads', hp, hn, st)
-        if self.world > 1:
+        if self._dist:
             sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
         self.ctx.call('mh_fit_update', lr, st)
 
@@ -356,10 +405,10 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         """``optimizer.py:383-392``: the One-Euro scan is sequential in time, so the ranks run it one after the other,
         handing the filter state over; then the filtered boundary frames are exchanged for the halo slots."""
         ctx, st = self.ctx, self._stream()
-        if self.world > 1:
+        if self._dist:
             sharding.pass_carry(None, self._view(L.BUF_CARRY_IN), self.prev, self.next, self.group)
         ctx.call('mh_refresh_filters', mc1, b1, mc2, b2, float(frame_rate), int(self.prev is None), st)
-        if self.world > 1:
+        if self._dist:
             sharding.send_carry(self._view(L.BUF_CARRY_OUT), self.next, self.group)
             row = self.num_people * L.LD3V
             F = self._view(L.BUF_FILTERED).view(self.T_local + 2, row)
@@ -382,7 +431,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         planes = 1 if which == 0 else 3
         for p in range(npass):
             ctx.call('mh_scene_median_pass', which, p, st)
-            if self.world > 1:
+            if self._dist:
                 if p < npass - 1:
                     hist = self._view(L.BUF_MEDIAN_HIST)[:(1 if p == 0 else 16 * planes) * HW]
                     torch.distributed.all_reduce(hist, op=torch.distributed.ReduceOp.SUM, group=self.group)
@@ -427,7 +476,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
 
     # ------------------------------------------------------------------------------------------ outputs
     def _gather_frames(self, local):
-        if self.world == 1:
+        if not self._dist:
             return local
         parts = [None] * self.world
         torch.distributed.all_gather_object(parts, local, group=self.group)
@@ -482,7 +531,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         """``optimizer.py:639-661`` (not called by the reference's drivers): One-Euro filter of the optimised translations and pose
         angles over time (here with the proper time stamps ``i / frame_rate``, unlike ``one_euro_filter``), then SMPL on the
         filtered poses; absolute vertices (T, N, 6890, 3) as a float32 tensor on ``self.device``.  Single-rank only."""
-        if self.world != 1:
+        if self._dist:
             raise NotImplementedError('get_filtered_vertices_by_smpl: gather the variables with get_optimized_variables() first')
         ctx, N, T = self.ctx, self.num_people, self.T_local
         pT = one_euro_over_time(ctx.get_param(L.P_POSES_T, (T, N, 1, 3)), min_cutoff_T, beta_T, frame_rate)

@@ -36,16 +36,24 @@ def neighbours(rank, world, ranges):
     return prev, nxt
 
 
+def _peer(group, r):
+    """``prev`` / ``next`` are ranks WITHIN ``group`` (they index ``ranges``); point-to-point calls address GLOBAL ranks."""
+    if r is None or group is None:
+        return r
+    return dist.get_global_rank(group, r)
+
+
 def exchange_halo(send, recv, prev, nxt, group=None):
     """send / recv: (2, n) tensors -- row 0 = this rank's FIRST frame, row 1 = its LAST frame; after the call
     recv[0] = prev rank's last frame, recv[1] = next rank's first frame.  Returns (has_prev, has_next)."""
     ops = []
+    gp, gn = _peer(group, prev), _peer(group, nxt)
     if prev is not None:
-        ops.append(dist.P2POp(dist.isend, send[0], prev, group=group))
-        ops.append(dist.P2POp(dist.irecv, recv[0], prev, group=group))
+        ops.append(dist.P2POp(dist.isend, send[0], gp, group=group))
+        ops.append(dist.P2POp(dist.irecv, recv[0], gp, group=group))
     if nxt is not None:
-        ops.append(dist.P2POp(dist.isend, send[1], nxt, group=group))
-        ops.append(dist.P2POp(dist.irecv, recv[1], nxt, group=group))
+        ops.append(dist.P2POp(dist.isend, send[1], gn, group=group))
+        ops.append(dist.P2POp(dist.irecv, recv[1], gn, group=group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
@@ -62,12 +70,12 @@ def pass_carry(carry_out, carry_in, prev, nxt, group=None):
     """Sequential One-Euro hand-over: receive the filter state from ``prev`` (blocking), to be called BEFORE this
     rank's scan; ``send_carry`` is called after it."""
     if prev is not None:
-        dist.recv(carry_in, src=prev, group=group)
+        dist.recv(carry_in, src=_peer(group, prev), group=group)
 
 
 def send_carry(carry_out, nxt, group=None):
     if nxt is not None:
-        dist.send(carry_out, dst=nxt, group=group)
+        dist.send(carry_out, dst=_peer(group, nxt), group=group)
 
 
 def log_from_loss_block(L, n_batches_total):
