@@ -30,13 +30,18 @@ WORKLOADS = {
     'c3': dict(name='8 persons x 512 frames x 1280x720, 200k-pt scene cloud, batch 8', N=8, T=512, W=1280, H=720, M=200000, B=8),
     'c2': dict(name='3 persons x 200 frames x 512x512, batch 10', N=3, T=200, W=512, H=512, M=200000, B=10),
     'c4': dict(name='4 persons x 1000 frames x 1920x1080, batch 8', N=4, T=1000, W=1920, H=1080, M=200000, B=8),
+    # BASELINE.json configs[4]: the scene-contact KNN sweep (512x512 planes as SURVEY.md 8d sizes it); 8 GPUs in BASELINE, fits one
+    'c5': dict(name='6 persons x 2000 frames x 512x512, 1M-pt scene cloud, batch 8', N=6, T=2000, W=512, H=512, M=1000000, B=8),
     'c3s': dict(name='profiling slice of c3: 8 persons x 64 frames x 1280x720, batch 8', N=8, T=64, W=1280, H=720, M=200000, B=8),
+    # accuracy leg (both arms, outside the timed region): small enough for 30 cycles of the CPU port
+    'acc': dict(name='accuracy slice: 2 persons x 4 frames x 256x192, 20k-pt cloud, batch 2', N=2, T=4, W=256, H=192, M=20000, B=2),
     'small': dict(name='2 persons x 16 frames x 320x240 (plumbing)', N=2, T=16, W=320, H=240, M=20000, B=4),
 }
 COEFS = dict(proj2d_loss_coef=1.0, depth_loss_coef=0.05, silhouette_loss_coef=0.1, reg_velocity_coef=0.05,
              reg_verts_filter_coef=0.002, reg_poses_coef=0.002, reg_scales_coef=1e-4, reg_contact_coef=0.001,
              reg_foot_sliding_coef=0.01)          # configs/predict_mupots.yml:17-25
 CPU_SAMPLE_T = 2                                   # frames of the CPU sample (all N persons, full resolution, full cloud)
+ACC_CYCLES = 30                                    # cycles of the accuracy leg
 
 
 def algorithmic_bytes_per_pf(w):
@@ -81,7 +86,12 @@ def build_problem(pkg, w, device, scene_update=False):
     sl = slice(opt.t0, opt.t1)
     Tl = opt.T_local
     motion = synthdata.make_motion(N, T, seed=1)
-    rng = np.random.default_rng(101 + opt.rank)
+    # the noise is drawn for the WHOLE sequence and sliced: a frame gets the same inputs whatever rank owns it, so the losses of a
+    # sharded run are comparable with the single-GPU run (`loss_check`)
+    rng = np.random.default_rng(101)
+    low_conf = rng.random((T, N, 17, 1)) < 0.05
+    uv_noise = rng.normal(0, 0.3, (T, N, 17, 2))
+    theta_noise = rng.normal(0, 0.05, (T, N, 72))
     # ground truth on the device -> planes
     ctx.set_param(L.P_XSCALE, np.zeros(N, np.float32), st)
     ctx.set_param(L.P_POSES_T, motion['trans'][sl], st)
@@ -92,9 +102,9 @@ def build_problem(pkg, w, device, scene_update=False):
     _, j17 = opt.smpl_forward(np.tile(motion['beta'], (Tl, 1, 1)), motion['theta'][sl], want_verts=False)
     j3d = j17.reshape(Tl, N, 17, 3) + motion['trans'][sl][:, :, None, :]
     uv = project(cam_K, j3d)
-    conf = np.where(rng.random((Tl, N, 17, 1)) < 0.05, 0.1, 0.9)
-    pose2d = np.concatenate([uv + rng.normal(0, 0.3, uv.shape), conf], -1).astype(np.float32)
-    theta_ref = (motion['theta'][sl] + rng.normal(0, 0.05, (Tl, N, 72))).astype(np.float32)
+    conf = np.where(low_conf[sl], 0.1, 0.9)
+    pose2d = np.concatenate([uv + uv_noise[sl], conf], -1).astype(np.float32)
+    theta_ref = (motion['theta'][sl] + theta_noise[sl]).astype(np.float32)
     theta_ref[..., 66:] = 0
     valid = np.ones((Tl, N), np.float32)
     ctx.call('mh_ingest_frames', 0, Tl, None, None, L.ptr(pose2d), L.ptr(theta_ref), L.ptr(valid), st)
@@ -171,14 +181,14 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
-def cpu_problem(w, extra=None):
-    """Bounded CPU sample of the workload: the first CPU_SAMPLE_T frames, all N persons, full resolution, full scene cloud.
-    The planes come from the oracle's own rasteriser so that this leg needs no GPU."""
+def cpu_problem(w, Ts=None):
+    """Bounded CPU sample of the workload: the first Ts (default CPU_SAMPLE_T) frames, all N persons, full resolution, full scene
+    cloud.  The planes come from the oracle's own rasteriser so that this leg needs no GPU."""
     import torch
     import synthdata
     from oracle import fit_ref, raster, refmath as rm
     N, W, H, M = w['N'], w['W'], w['H'], w['M']
-    Ts = CPU_SAMPLE_T
+    Ts = CPU_SAMPLE_T if Ts is None else Ts
     md = model_dir()
     model = synthdata.load_model_tensors(md)
     cam_K = synthdata.camera_for(W, H)
@@ -207,12 +217,16 @@ def cpu_problem(w, extra=None):
     fr.set_scene_pcd(synthdata.scene_cloud(M, seed=2))
     fr.refresh_filters()
     opt = torch.optim.RMSprop(fr.leaves(), lr=0.01, alpha=0.5, momentum=0.9)
-    batches = [np.arange(0, Ts)]
+    B = min(w['B'], Ts)
+    batches = [np.arange(b, min(b + B, Ts)) for b in range(0, Ts, B)]
 
-    def step():
+    def step(lr=0.01):
+        for grp in opt.param_groups:
+            grp['lr'] = lr
         fr.cycle_grads(data, batches)
         opt.step()
     step.fit_ref, step.data, step.batches, step.cam_K, step.start = fr, data, batches, cam_K, s      # for tests/test_gpu_fullsize.py
+    step.motion, step.cloud = motion, fr.scene_pcd[0, 0].numpy()
     return step, Ts * N
 
 
@@ -247,6 +261,116 @@ def reference_arm(args, w, rank):
     }), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------- accuracy
+def run_accuracy(pkg, device='cuda:0', cycles=ACC_CYCLES, wname='acc'):
+    """"MPJPE vs ref" half of the BASELINE metric, outside every timed region: ACC_CYCLES steady-state cycles (all terms, frozen
+    cloud, filters refreshed once at the start) from IDENTICAL starts and IDENTICAL host inputs on both arms -- the CUDA path and
+    the CPU port of the reference optimiser -- then the reference's own evaluation (evaluate.py:180-296, eval_mupots.py:18-42:
+    MPJPE over the first 14 MuPoTS joints, absolute, in mm) of each arm against the synthetic ground truth and of one against the
+    other.  Part of the CPU-baseline leg (the only place bench.py may execute oracle/)."""
+    import torch
+    L = sys.modules[pkg.__name__ + '._lib']
+    ev = sys.modules.get(pkg.__name__ + '.evaluation')
+    if ev is None:
+        import importlib
+        ev = importlib.import_module(pkg.__name__ + '.evaluation')
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import gpu_harness as gh
+    w = WORKLOADS[wname]
+    N, T, W, H, M, B = w['N'], w['T'], w['W'], w['H'], w['M'], w['B']
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, _ = cpu_problem(w, Ts=T)
+    fr, data, cam_K, start, motion = step.fit_ref, step.data, step.cam_K, step.start, step.motion
+    # ---- CUDA arm (first: the port's leaves still hold the start state, the filters are refreshed from it on both arms)
+    opt = pkg.SMPLDepthSequenceOptimizer(image_size=(W, H), num_frames=T, cam_K=cam_K, device=device, smpl_model_parameters_path=model_dir(),
+                                         scene_update=False, max_scene_points=M, **COEFS)
+    opt.init_optimized_variables(data['pose2d'], data['poses_smpl'], data['betas_smpl'], data['valid_smpl'], num_iter=0, batch_size=B)
+    opt._ingest(gh.ListLoader(data, B))
+    set_start(opt, L, start)
+    opt.set_scene_pcd(step.cloud)
+    opt._refresh_filters(0.01, 0.02, 0.001, 0.5)
+    lr = 0.01
+    for _ in range(cycles):
+        opt.step_device_only(lr); lr *= 0.99
+    ours = opt.get_optimized_variables()
+    # ---- CPU port
+    t0 = time.time()
+    lr = 0.01
+    for _ in range(cycles):
+        step(lr); lr *= 0.99
+    port_s = time.time() - t0
+    port = {'poses_T': fr.poses_T.detach().numpy(), 'poses_smpl': fr.poses_smpl.detach().numpy(), 'betas_smpl': fr.betas.detach().numpy(),
+            'scale_factor': np.power(np.float32(1.1), fr.xscale.detach().numpy()).astype(np.float32)}
+    first = {'poses_T': start['poses_T'].reshape(T, N, 1, 3), 'poses_smpl': start['poses_smpl'], 'betas_smpl': start['betas'],
+             'scale_factor': np.ones((1, N, 1, 1), np.float32)}
+    # ---- evaluation (SMPL + MuPoTS joint regression on the device, matching / averages on the host)
+    sj = ev.SMPLJoints(opt, {'mupots': np.load(os.path.join(model_dir(), 'SMPL_MuPoTs_Regressor_v1.npy'))})
+    vis = np.ones((T, N, 17, 1), np.float32)
+
+    def joints_of(v):
+        be = np.tile(np.asarray(v['betas_smpl']).reshape(1, N, 10), (T, 1, 1))
+        j = sj(be.reshape(-1, 10), np.asarray(v['poses_smpl']).reshape(-1, 72), 'mupots').reshape(T, N, 17, 3)
+        sc = np.asarray(v['scale_factor']).reshape(1, N, 1, 1)
+        return sc * j + np.asarray(v['poses_T']).reshape(T, N, 1, 3)
+
+    def mpjpe(v, ref):
+        vv = dict(v)
+        vv['betas_smpl'] = np.tile(np.asarray(v['betas_smpl']).reshape(1, N, 10), (T, 1, 1))
+        return float(ev.compute_mm_pck_results(vv, ref, vis, sj, cam_K)['mm_abs_error'])
+
+    gt = joints_of({'poses_T': motion['trans'][:T], 'poses_smpl': motion['theta'][:T], 'betas_smpl': motion['beta'],
+                    'scale_factor': np.ones((1, N, 1, 1), np.float32)})
+    res = {'cycles': cycles, 'slice': w['name'], 'metric': 'MPJPE over the first 14 MuPoTS joints, absolute, mm (eval_mupots.py:18-42)',
+           'start_vs_gt_mm': mpjpe(first, gt),
+           'ours': {'mpjpe_vs_gt_mm': mpjpe(ours, gt), 'mpjpe_vs_port_mm': mpjpe(ours, joints_of(port))},
+           'port': {'mpjpe_vs_gt_mm': mpjpe(port, gt), 'seconds': port_s},
+           'max_abs_diff_ours_vs_port': {'poses_T_m': float(np.abs(np.asarray(ours['poses_T']) - port['poses_T']).max()),
+                                         'poses_smpl_rad': float(np.abs(np.asarray(ours['poses_smpl']) - port['poses_smpl']).max()),
+                                         'betas': float(np.abs(np.asarray(ours['betas_smpl']) - port['betas_smpl']).max())}}
+    opt.ctx.close()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------- hot loop A
+def run_init_loop(opt, aux, w, L, iters=50, warmup=5):
+    """Hot loop A (optimizer.py:740-761, Adam on the translations) on the bench workload, CUDA-event timed: person-frame
+    iterations per second of `mh_init_grads` + exchange + `mh_init_update` after the one-time SMPL evaluation of `mh_init_begin`."""
+    import torch
+    import torch.distributed as dist
+    ctx, st = opt.ctx, opt._stream()
+    Tl, N = opt.T_local, w['N']
+    betas = np.ascontiguousarray(np.tile(aux['motion']['beta'].reshape(1, N, 10), (Tl, 1, 1)), np.float32)
+    ctx.call('mh_init_begin', L.ptr(aux['pose2d']), L.ptr(aux['theta_ref']), L.ptr(betas), 0.15, st)
+    sh = sys.modules[type(opt).__module__.rsplit('.', 1)[0] + '.sharding']
+
+    def it(k, lr):
+        hp, hn = opt._exchange_halo()
+        ctx.call('mh_init_grads', hp, hn, st)
+        if opt._dist:
+            sh.allreduce_shared(opt._view(L.BUF_SHARED), opt.group)
+        ctx.call('mh_init_update', lr, k + 1, st)
+
+    lr = 0.5
+    for k in range(warmup):
+        it(k, lr); lr *= 0.95
+    torch.cuda.synchronize()
+    if opt._dist:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(warmup, warmup + iters):
+        it(k, lr); lr *= 0.95
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if opt._dist:
+        tt = torch.tensor([ms], device=opt.device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return {'value': w['N'] * w['T'] * iters / (ms * 1e-3), 'unit': 'person-frame-iters/s', 'ms_per_iter': ms / iters, 'iters': iters,
+            'what': 'hot loop A: 2-D reprojection + velocity gradients of the translations, fused Adam step (SMPL joints cached once)'}
+
+
 # ------------------------------------------------------------------------------------------------- e2e
 class HostLoader(object):
     """Re-iterable over pinned HOST tensors with the keys of the reference dataset (datautils.py:630-641)."""
@@ -279,23 +403,27 @@ def run_e2e(pkg, w, device, opt_dev, aux, steps):
               'pose2d': torch.from_numpy(aux['pose2d']).pin_memory(), 'poses_smpl': torch.from_numpy(aux['theta_ref']).pin_memory(),
               'idxs': torch.arange(t0, t0 + Tl, dtype=torch.int64)}
     del depths, seg
-    opt = pkg.SMPLDepthSequenceOptimizer(image_size=(W, H), num_frames=T, cam_K=aux['cam_K'], device=device,
-                                         smpl_model_parameters_path=model_dir(), scene_update=False, max_scene_points=M, **COEFS)
-    opt._make_context(T, N, B)
-    opt.optim_scale_factor = True
-    opt.valid_smpl = np.ones((T, N, 1), np.float32)
-    opt.partial_loader_ok = True
-    set_start(opt, L, aux['start'])
-    opt.set_scene_pcd(aux['cloud'])
+    # whole-sequence arrays of init_optimized_variables (optimizer.py:262): every rank passes the full shapes, only its own frames
+    # are read (the 2-D poses of the other ranks' frames are left zero here instead of being recomputed on every rank)
+    pose2d = np.zeros((T, N, 17, 3), np.float32); pose2d[t0:t0 + Tl] = aux['pose2d']
+    theta_ref = np.zeros((T, N, 72), np.float32); theta_ref[t0:t0 + Tl] = aux['theta_ref']
+    betas = np.ascontiguousarray(np.tile(aux['motion']['beta'].reshape(1, N, 10), (T, 1, 1)), np.float32)
+    valid = np.ones((T, N, 1), np.float32)
     loader = HostLoader(arrays, B)
-    world = opt.world
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.synchronize(device)
     if world > 1:
         dist.barrier()
     t_begin = time.perf_counter()
-    opt._ingest(loader)
-    opt._refresh_filters(0.01, 0.02, 0.001, 0.5)
-    log = opt.fit(loader, num_iter=steps)
+    # the calls a user of the reference makes (predict.py:290-344): construct, init (hot loop A, 100 iterations), fit, read back.
+    # `set_scene_pcd` freezes the scene cloud and `start_cycle=50` resumes the schedule in the steady-state regime (filters
+    # refreshed at the first cycle, every term on) -- the regime `value` is measured in
+    opt = pkg.SMPLDepthSequenceOptimizer(image_size=(W, H), num_frames=T, cam_K=aux['cam_K'], device=device,
+                                         smpl_model_parameters_path=model_dir(), scene_update=False, max_scene_points=M,
+                                         allow_partial_loader=True, **COEFS)
+    opt.init_optimized_variables(pose2d, theta_ref, betas, valid, num_iter=100, batch_size=B)
+    opt.set_scene_pcd(aux['cloud'])
+    log = opt.fit(loader, num_iter=50 + steps, start_cycle=50)
     out = opt.get_optimized_variables()
     torch.cuda.synchronize(device)
     dt = time.perf_counter() - t_begin
@@ -303,8 +431,8 @@ def run_e2e(pkg, w, device, opt_dev, aux, steps):
         tt = torch.tensor([dt], device=device, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-    d2h = sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray)) + steps * 16 * 4
-    h2d = opt.h2d_bytes
+    d2h = sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray)) + (steps + 100) * 16 * 4
+    h2d = opt.h2d_bytes + pose2d.nbytes + theta_ref.nbytes + betas.nbytes + aux['cloud'].nbytes
     opt.ctx.close()
     return N * T * steps / dt, h2d / steps, d2h / steps, float(log[-1]['loss_silhouette'])
 
@@ -421,15 +549,28 @@ def main():
         'loss_check': {'silhouette_first': float(losses0[L.L_SILHOUETTE]), 'silhouette_last': float(losses1[L.L_SILHOUETTE]),
                        'pose2d_first': float(losses0[L.L_POSE2D]), 'pose2d_last': float(losses1[L.L_POSE2D])},
     }
+    # sharded == single: the first-cycle losses of this run against the committed single-GPU values of the same workload
+    ref_path = os.path.join(ROOT, 'profiles', 'loss_check_n1.json')
+    if os.path.exists(ref_path):
+        n1 = json.load(open(ref_path)).get(args.workload)
+        if n1:
+            rel = max(abs(line['loss_check'][k] - n1[k]) / max(abs(n1[k]), 1e-12) for k in ('silhouette_first', 'pose2d_first'))
+            line['loss_check']['n1_reference'] = {k: n1[k] for k in ('silhouette_first', 'pose2d_first')}
+            line['loss_check']['max_rel_diff_vs_n1'] = rel
+            if rel > 1e-3:
+                raise SystemExit(f'loss_check: the {world}-GPU losses differ from the single-GPU reference by {rel:.2e} (> 1e-3): {line["loss_check"]}')
+    line['init_loop'] = run_init_loop(opt, aux, w, L)
     if not args.no_e2e:
         e2e, h2d, d2h, _ = run_e2e(pkg, w, device, opt, aux, args.steps)
         line['e2e'] = {'value': e2e, 'unit': 'person-frame-iters/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                       'what': f'fit() of {args.steps} cycles from pinned host buffers incl. one-time ingest, filter refresh and result readback'}
+                       'what': f'public API from pinned host buffers (reference dtypes): init_optimized_variables (100 iterations) + fit() of {args.steps} '
+                               f'steady-state cycles incl. one-time ingest, filter refresh, per-cycle loss readback and get_optimized_variables()'}
     opt.ctx.close()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, sec, cores, pf = run_cpu(w, 1, 1)
         line['cpu_baseline'] = {'value': v, 'unit': 'person-frame-iters/s', 'cores': cores, 'kind': 'port',
                                 'sample': f'{CPU_SAMPLE_T} frames x {w["N"]} persons x {w["W"]}x{w["H"]}, {w["M"]}-pt cloud, all terms; 1 warm + 1 timed cycle ({sec:.1f} s)'}
+        line['accuracy'] = run_accuracy(pkg, device)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

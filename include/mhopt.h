@@ -133,6 +133,11 @@ int mh_set_optimize_scale(mh_ctx* ctx, int32_t on);
 int mh_ingest_frames(mh_ctx* ctx, int32_t t_local0, int32_t count, const float* depths_host,
                      const float* seg_host, const float* pose2d_host, const float* theta_ref_host,
                      const float* valid_host, void* stream);
+/* The same with the instance masks as uint8 / bool {0,1} (count,N,H,W): a quarter of the host->device bytes of the reference
+ * dataset's float32 masks (utils.py:329-331 delivers {0.,1.}); extension for callers that can hand the masks over compactly. */
+int mh_ingest_frames_u8(mh_ctx* ctx, int32_t t_local0, int32_t count, const float* depths_host,
+                        const uint8_t* seg_host, const float* pose2d_host, const float* theta_ref_host,
+                        const float* valid_host, void* stream);
 /* Derived constants after the last ingest: eroded masks (optimizer.py:306-309, 434-435), mask areas and
  * validity flags (optimizer.py:404-409). */
 int mh_finalize_ingest(mh_ctx* ctx, void* stream);

@@ -79,7 +79,7 @@ class FitRef(object):
             scale = torch.pow(1.1, self.xscale)
             g3d = scale * j17.view(T, N, -1, 3) + poses_T
             p2d = rm.camera_projection(g3d.view(T * N, -1, 3), Kt, self.Kd).view(T, N, -1, 2)
-            loss_2d = torch.mean(torch.square(vis * p2d - vis * gt))              # MSELoss(mean) :740,754
+            loss_2d = torch.mean(torch.square(self.pose_weights * vis * p2d - self.pose_weights * vis * gt))   # MSELoss(mean) :740, 754-756
             speed = torch.sum(torch.square(poses_T[1:] - poses_T[:-1]))
             loss = self.coefs['proj2d'] * loss_2d + self.coefs['reg_velocity'] * speed
             log.append({'loss_2d': loss_2d.detach().numpy()})

@@ -65,6 +65,7 @@ def _load():
         'mh_set_joint_weights': (c_int32, [ctx, FP]),
         'mh_set_optimize_scale': (c_int32, [ctx, c_int32]),
         'mh_ingest_frames': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+        'mh_ingest_frames_u8': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         'mh_finalize_ingest': (c_int32, [ctx, c_void_p]),
         'mh_set_scene': (c_int32, [ctx, c_void_p, c_int64, c_void_p]),
         'mh_set_scene_from_depth': (c_int32, [ctx, c_void_p, c_void_p, c_void_p]),

@@ -308,14 +308,27 @@ extern "C" int mh_set_coefs(mh_ctx* c, const mh_coefs* k) {
 }
 
 // ---- frames -------------------------------------------------------------------------------------
+static int ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* depths, const void* seg, int seg_is_u8, const float* pose2d,
+                         const float* theta_ref, const float* valid, void* stream);
+
 extern "C" int mh_ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* depths, const float* seg, const float* pose2d,
                                 const float* theta_ref, const float* valid, void* stream) {
+    return ingest_frames(c, t0, count, depths, seg, 0, pose2d, theta_ref, valid, stream);
+}
+
+extern "C" int mh_ingest_frames_u8(mh_ctx* c, int32_t t0, int32_t count, const float* depths, const uint8_t* seg, const float* pose2d,
+                                   const float* theta_ref, const float* valid, void* stream) {
+    return ingest_frames(c, t0, count, depths, seg, 1, pose2d, theta_ref, valid, stream);
+}
+
+static int ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* depths, const void* seg, int seg_is_u8, const float* pose2d,
+                         const float* theta_ref, const float* valid, void* stream) {
     API_BEGIN(c);
     cudaStream_t st = (cudaStream_t)stream;
     const mh_dims& d = c->d;
     if (t0 < 0 || count < 1 || t0 + count > d.T) MH_FAIL(c, MH_E_ARG, "mh_ingest_frames: frames [%d, %d) outside [0, %d)", t0, t0 + count, d.T);
     if (!pose2d || !theta_ref || !valid) MH_FAIL(c, MH_E_ARG, "mh_ingest_frames: null buffer");
-    const int64_t HW = (int64_t)d.H * d.W, need = (int64_t)count * d.N * HW;
+    const int64_t HW = (int64_t)d.H * d.W, nseg = (int64_t)count * d.N * HW, need = seg_is_u8 ? (nseg + 3) / 4 : nseg;
     if (seg && need > c->stage_floats) {
         MH_CUDA(c, cudaStreamSynchronize(st));
         if (c->stage) cudaFree(c->stage);
@@ -324,11 +337,11 @@ extern "C" int mh_ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const floa
         c->stage_floats = need;
     }
     if (depths) MH_CUDA(c, cudaMemcpyAsync(c->depth + (int64_t)t0 * HW, depths, sizeof(float) * count * HW, cudaMemcpyHostToDevice, st));
-    if (seg) MH_CUDA(c, cudaMemcpyAsync(c->stage, seg, sizeof(float) * need, cudaMemcpyHostToDevice, st));
+    if (seg) MH_CUDA(c, cudaMemcpyAsync(c->stage, seg, seg_is_u8 ? (size_t)nseg : sizeof(float) * (size_t)nseg, cudaMemcpyHostToDevice, st));
     MH_CUDA(c, cudaMemcpyAsync(c->pose2d + (int64_t)t0 * d.N * 51, pose2d, sizeof(float) * count * d.N * 51, cudaMemcpyHostToDevice, st));
     MH_CUDA(c, cudaMemcpyAsync(c->theta_ref + (int64_t)t0 * d.N * 72, theta_ref, sizeof(float) * count * d.N * 72, cudaMemcpyHostToDevice, st));
     MH_CUDA(c, cudaMemcpyAsync(c->valid + (int64_t)t0 * d.N, valid, sizeof(float) * count * d.N, cudaMemcpyHostToDevice, st));
-    if (seg) MH_TRY(mh_ingest_compact(c, t0, count, st));
+    if (seg) MH_TRY(mh_ingest_compact(c, t0, count, seg_is_u8, st));
     return MH_OK;
 }
 

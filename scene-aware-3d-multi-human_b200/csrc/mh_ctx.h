@@ -169,7 +169,7 @@ int mh_render_synth(mh_ctx* c, float y_ground, float z_wall, cudaStream_t st);
 // mh_filter.cu
 int mh_filter_run(mh_ctx* c, float mc1, float b1, float mc2, float b2, float frame_rate, int first, cudaStream_t st);
 int mh_scene_from_depth(mh_ctx* c, const float* depth_dev, const uint8_t* mask_dev, cudaStream_t st);
-int mh_ingest_compact(mh_ctx* c, int t0, int count, cudaStream_t st);
+int mh_ingest_compact(mh_ctx* c, int t0, int count, int seg_is_u8, cudaStream_t st);
 int mh_ingest_derive(mh_ctx* c, cudaStream_t st);
 int mh_expand_planes(mh_ctx* c, int t, float* seg_dev, cudaStream_t st);
 // mh_scene.cu

@@ -7,24 +7,28 @@
 // occlusion accumulator (:458, 475) reduced to per-frame pixel counts.
 #include "mh_ctx.h"
 
-// seg (count, N, HW) f32 {0,1} -> one 32-bit plane per frame, bit n = person n covers the pixel
-__global__ void k_compact(const float* __restrict__ seg, int N, int64_t HW, uint32_t* __restrict__ cbits, int* __restrict__ flags) {
+// seg (count, N, HW) f32 {0,1} (as the reference dataset delivers it, utils.py:329-331) or u8 / bool {0,1} -> one 32-bit plane
+// per frame, bit n = person n covers the pixel
+template <typename T>
+__global__ void k_compact(const T* __restrict__ seg, int N, int64_t HW, uint32_t* __restrict__ cbits, int* __restrict__ flags) {
     const int t = blockIdx.y;
     bool bad = false;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
         uint32_t bits = 0;
         for (int n = 0; n < N; ++n) {
-            const float v = seg[((int64_t)t * N + n) * HW + p];
-            if (v != 0.f) { bits |= 1u << n; bad |= (v != 1.0f); }
+            const T v = seg[((int64_t)t * N + n) * HW + p];
+            if (v != (T)0) { bits |= 1u << n; bad |= (v != (T)1); }
         }
         cbits[(int64_t)t * HW + p] = bits;
     }
     if (bad) atomicOr(flags, 1);
 }
 
-int mh_ingest_compact(mh_ctx* c, int t0, int count, cudaStream_t st) {
+int mh_ingest_compact(mh_ctx* c, int t0, int count, int seg_is_u8, cudaStream_t st) {
     const int64_t HW = (int64_t)c->d.H * c->d.W;
-    k_compact<<<dim3(std::min(mh_cdiv(HW, 256), 1024), count), 256, 0, st>>>(c->stage, c->d.N, HW, c->cbits + (int64_t)t0 * HW, c->devflags);
+    const dim3 grid(std::min(mh_cdiv(HW, 256), 1024), count);
+    if (seg_is_u8) k_compact<uint8_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(c->stage), c->d.N, HW, c->cbits + (int64_t)t0 * HW, c->devflags);
+    else k_compact<float><<<grid, 256, 0, st>>>(c->stage, c->d.N, HW, c->cbits + (int64_t)t0 * HW, c->devflags);
     MH_LAUNCHED(c);
     return MH_OK;
 }

@@ -81,7 +81,7 @@ class SMPLOptimizerBase(object):
                  smpl_J_reg_extra_path='J_regressor_extra.npy', smpl_J_reg_h37m_path='J_regressor_h36m.npy',
                  smpl_J_reg_alphapose_path='SMPL_AlphaPose_Regressor_RMSprop_6.npy',
                  smpl_sparse_joints_key='joints_alphapose', pose24j_weights=None, pose17j_weights=None,
-                 process_group=None, scene_update=True, max_scene_points=None):
+                 process_group=None, scene_update=True, max_scene_points=None, allow_partial_loader=False):
         self.device_ordinal = _device_ordinal(device)
         self.device = torch.device('cuda', self.device_ordinal)
         if smpl_sparse_joints_key != 'joints_alphapose':
@@ -103,6 +103,9 @@ class SMPLOptimizerBase(object):
             self.rank, self.world = 0, 1
         self.scene_update = scene_update
         self.max_scene_points = max_scene_points
+        # extension: with several ranks the dataloader of a rank may deliver only that rank's frames (the reference API iterates the
+        # whole sequence on every process)
+        self.partial_loader_ok = bool(allow_partial_loader)
 
 
 class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
@@ -307,6 +310,8 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         seen = np.zeros(self.T_total, bool)
         self.h2d_bytes = 0
         B = None
+        stream = torch.cuda.current_stream(self.device)
+        inflight = []                                  # (event, host buffers): the copies are asynchronous, the buffers may be temporaries
         keep_scene = self.scene_update
         self._have_images = False
         for data in dataloader:
@@ -329,11 +334,18 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
                     e += 1
                 tl, cnt = t - self.t0, e - j
                 assert tuple(arr['pose2d'].shape[2:]) == (17, 3), f"pose2d must be (B, N, 17, 3), got {arr['pose2d'].shape}"
-                dep = L.f32(arr['depths'][j:e]); seg = L.f32(arr['seg_mask'][j:e]); p2d = L.f32(arr['pose2d'][j:e])
+                dep = L.f32(arr['depths'][j:e]); p2d = L.f32(arr['pose2d'][j:e])
                 th = L.f32(arr['poses_smpl'][j:e]); vl = L.f32(self.valid_smpl[t:t + cnt].reshape(cnt, N))
+                seg = arr['seg_mask'][j:e]
+                if seg.dtype in (np.uint8, np.bool_):                      # compact masks: a quarter of the bytes (extension)
+                    seg = np.ascontiguousarray(seg).view(np.uint8)
+                    entry = 'mh_ingest_frames_u8'
+                else:                                                      # float32 {0., 1.} as the reference dataset delivers them
+                    seg = L.f32(seg)
+                    entry = 'mh_ingest_frames'
                 assert dep.shape == (cnt, H, W) and seg.shape == (cnt, N, H, W), (dep.shape, seg.shape)
-                ctx.call('mh_ingest_frames', tl, cnt, L.ptr(dep), L.ptr(seg), L.ptr(p2d), L.ptr(th), L.ptr(vl), st)
-                torch.cuda.current_stream(self.device).synchronize()       # the host buffers may be temporaries
+                ctx.call(entry, tl, cnt, L.ptr(dep), L.ptr(seg), L.ptr(p2d), L.ptr(th), L.ptr(vl), st)
+                held = [dep, seg, p2d, th, vl]
                 self.h2d_bytes += dep.nbytes + seg.nbytes + p2d.nbytes + th.nbytes + vl.nbytes
                 if keep_scene:
                     # backmasks / images stay on the device for the scene median (optimizer.py:399-400, 579-582)
@@ -341,20 +353,30 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
                     im = np.ascontiguousarray(arr['images'][j:e], dtype=np.uint8) if 'images' in arr else None
                     assert bk.shape == (cnt, H, W) and (im is None or im.shape == (cnt, H, W, 3))
                     ctx.call('mh_scene_set_back', tl, cnt, L.ptr(bk), L.ptr(im), st)
-                    torch.cuda.current_stream(self.device).synchronize()
+                    held += [bk, im]
                     self._have_images = im is not None
                     self.h2d_bytes += bk.nbytes + (im.nbytes if im is not None else 0)
+                # keep the host buffers of the last two calls alive instead of synchronising after every call: the next batch is
+                # fetched / converted on the host while this one is still being copied
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                inflight.append((ev, held))
+                while len(inflight) > 2:
+                    inflight.pop(0)[0].synchronize()
                 j = e
-        if not seen[self.t0:self.t1].all() or not (seen.all() or getattr(self, 'partial_loader_ok', False)):
+        stream.synchronize()
+        inflight.clear()
+        if not seen[self.t0:self.t1].all() or not (seen.all() or self.partial_loader_ok):
             raise RuntimeError(f'the dataloader did not deliver frames {np.nonzero(~seen)[0][:8]}...')
         ctx.call('mh_finalize_ingest', st)
         self._ingested = True
 
     # ------------------------------------------------------------------------------------------ fit
     def fit(self, dataloader, num_iter=250, min_cutoff1=0.01, min_cutoff2=0.001, beta1=0.02, beta2=0.5,
-            update_filters_every=25, verbose=False):
+            update_filters_every=25, verbose=False, start_cycle=0):
         """Hot loop B (``optimizer.py:324-602``): RMSprop(lr .01, alpha .5, momentum .9) + ExponentialLR(.99), one
-        step per pass over the video.  Returns the reference's ``optim_log``."""
+        step per pass over the video.  Returns the reference's ``optim_log``.  ``start_cycle`` (extension) resumes the cycle
+        schedule -- learning rate, filter refreshes, scene updates -- at that cycle: cycles ``start_cycle .. num_iter - 1`` run."""
         ctx, st = self.ctx, self._stream()
         if not self._ingested:
             self._ingest(dataloader)
@@ -362,9 +384,9 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
             print('WARNING!!! Not optimizing scale_factor!')
         ctx.call('mh_reset_optimizer', st)
         n_batches = (self.T_total + self.batch_size - 1) // self.batch_size
-        lr = 0.01
+        lr = 0.01 * 0.99 ** start_cycle
         optim_log = []
-        cycles = range(num_iter)
+        cycles = range(start_cycle, num_iter)
         if verbose:
             from tqdm import tqdm
             cycles = tqdm(cycles)

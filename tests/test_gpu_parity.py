@@ -214,6 +214,22 @@ def test_init_stage(pkg, L, name):
     assert np.allclose(opt.ctx.get_param(L.P_BETAS, (1, N, 10)), g['init_betas'], atol=1e-7)
 
 
+def test_init_stage_with_joint_weights(pkg, L):
+    """``pose17j_weights`` in hot loop A (``optimizer.py:754-756``) vs the unmodified reference (``tests/golden/init_w17.npz``)."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch, num_iter, init_iter = meta
+    k = np.load(os.path.join(gh.GOLDEN, 'init_w17.npz'))
+    opt = gh.make_optimizer(pkg, g, data, meta, pose17j_weights=[float(v) for v in k['w17']])
+    log = opt.init_optimized_variables(data['pose2d'], data['poses_smpl'], data['betas_smpl'], data['valid_smpl'], num_iter=int(k['init_iter']),
+                                       batch_size=batch)
+    pT = opt.ctx.get_param(L.P_POSES_T, (T, N, 1, 3))
+    assert np.abs(pT - k['init_poses_T']).max() < 1e-4                        # metres
+    l2d = np.array([float(l['loss_2d']) for l in log])
+    assert np.abs(l2d - k['init_loss_2d']).max() <= 1e-4 * k['init_loss_2d'].max()
+    assert np.allclose(opt.ctx.get_param(L.P_ZMAX_LIN, (T, 1, 1)), k['init_zmax_lin'], atol=1e-4)
+    opt.ctx.close()
+
+
 def test_optimizer_updates_match_torch(c1, L):
     """Fused RMSprop / Adam steps vs torch.optim with identical gradients."""
     import torch

@@ -101,6 +101,19 @@ def test_synthetic_sequence_regenerates(model_dir, name):
         assert np.allclose(inputs[k], data[k], atol=1e-6), k
 
 
+def test_init_stage_with_joint_weights(model):
+    """Non-uniform ``pose17j_weights`` weigh the 2-D residual of hot loop A too (``optimizer.py:754-756``): golden vector of the
+    unmodified reference (``tests/golden/make_init_w17_golden.py``)."""
+    g, data, (N, T, W, H, batch, num_iter, init_iter) = _load_fit('fit_n2.npz')
+    k = np.load(os.path.join(GOLDEN, 'init_w17.npz'))
+    fr = fit_ref.FitRef(model, (W, H), T, g['cam_K'], COEFS, pose17j_weights=k['w17'])
+    log = fr.init_optimized_variables(data['pose2d'], data['poses_smpl'], data['betas_smpl'], data['valid_smpl'], num_iter=int(k['init_iter']))
+    assert np.abs(fr.poses_T.detach().numpy() - k['init_poses_T']).max() < 1e-4          # metres
+    l2d = np.array([float(l['loss_2d']) for l in log])
+    assert np.abs(l2d - k['init_loss_2d']).max() <= 1e-5 * k['init_loss_2d'].max()
+    assert np.abs(k['init_poses_T'] - g['init_poses_T']).max() > 1e-2                    # the weights do change the answer
+
+
 @pytest.mark.parametrize('name', ['fit_c1.npz', 'fit_n2.npz'])
 def test_init_stage(model, name):
     g, data, (N, T, W, H, batch, num_iter, init_iter) = _load_fit(name)
