@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict
     __shared__ int ci[KNN_Q][KNN_CAP];
     __shared__ int sel[KNN_Q][MH_KNN];
     __shared__ int scount[KNN_Q];
-    __shared__ float stau[KNN_Q], slo[KNN_Q], shi[KNN_Q];
+    // the bound is a (distance, point index) KEY: with more than KNN_CAP points at exactly the bounding distance (duplicated scene
+    // points) a bound on the distance alone cannot be bisected; on the key it always can (all keys are distinct)
+    __shared__ unsigned long long stau[KNN_Q], slo[KNN_Q], shi[KNN_Q];
     __shared__ int sdone[KNN_Q];
     const int i0 = blockIdx.x * KNN_Q, tid = threadIdx.x;
     const int nq = min(KNN_Q, TN - i0);
@@ -212,11 +214,11 @@ __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict
     for (int q = 0; q < KNN_Q; ++q) {
         int rank = 0;
         for (int j = 0; j < KNN_THREADS; ++j) rank += (smin[q][j] < mn[q]) || (smin[q][j] == mn[q] && j < tid);
-        if (rank == MH_KNN - 1) { stau[q] = mn[q]; slo[q] = 0.f; shi[q] = mn[q]; }
+        if (rank == MH_KNN - 1) { stau[q] = ((unsigned long long)__float_as_uint(mn[q]) << 32) | 0xffffffffull; slo[q] = 0ull; shi[q] = stau[q]; }
     }
     __syncthreads();
     for (int iter = 0; iter < 64; ++iter) {
-        float tau[KNN_Q];
+        unsigned long long tau[KNN_Q];
         bool act[KNN_Q];
 #pragma unroll
         for (int q = 0; q < KNN_Q; ++q) { tau[q] = stau[q]; act[q] = !sdone[q]; }
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict
 #pragma unroll
             for (int q = 0; q < KNN_Q; ++q) {
                 const float dd = d2_point(p0, p1, p2, x[q], y[q], z[q]);
-                if (act[q] && dd <= tau[q]) {
+                if (act[q] && ((((unsigned long long)__float_as_uint(dd)) << 32) | (unsigned)p) <= tau[q]) {
                     const int k = atomicAdd(&scount[q], 1);
                     if (k < KNN_CAP) { cd[q][k] = dd; ci[q][k] = (int)p; }
                 }
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict
             if (cnt >= MH_KNN && cnt <= KNN_CAP) sdone[tid] = 1;
             else {               // bisection on the bound (only reached with > KNN_CAP near-ties)
                 if (cnt > KNN_CAP) shi[tid] = stau[tid]; else slo[tid] = stau[tid];
-                stau[tid] = 0.5f * (slo[tid] + shi[tid]);
+                stau[tid] = slo[tid] + (shi[tid] - slo[tid]) / 2;
                 scount[tid] = 0;
             }
         }

@@ -311,6 +311,46 @@ def test_contact_knn_against_brute_force(pkg, L, knn_q, monkeypatch):
     assert abs(float(losses[L.L_CONTACT]) - ref) <= 1e-5 * ref
 
 
+def test_contact_knn_one_million_points_with_ties(pkg, L):
+    """BASELINE config C5's cloud size: 1 000 000 scene points, with MORE duplicates than the candidate list holds (700 > KNN_CAP = 512)
+    planted exactly at the 32-nearest boundary of one body -- the bound must then be bisected on (distance, index) -- and 10 duplicates
+    nearer than them; vs numpy brute force with the reference's arithmetic (``optimizer.py:492-500``)."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch = meta[:5]
+    M = 1000000
+    opt = gh.make_optimizer(pkg, g, data, meta, coefs=dict(gh.COEFS, depth=0.0, silhouette=0.0), max_scene_points=M)
+    gh.prepare(opt, g, data, meta)
+    c = 31
+    ctx, st = opt.ctx, opt._stream()
+    for which, key in ((L.P_POSES_T, 'poses_T'), (L.P_POSES_SMPL, 'poses_smpl'), (L.P_BETAS, 'betas'), (L.P_XSCALE, 'xscale')):
+        ctx.set_param(which, g[f'c{c}_p_{key}'], st)
+    ctx.set_param(L.P_ZMIN_LIN, g[f'c{c}_p_zmin_lin'], st); ctx.set_param(L.P_ZMAX_LIN, g[f'c{c}_p_zmax_lin'], st)
+    rng = np.random.default_rng(11)
+    cloud = np.stack([rng.uniform(-6, 6, M), rng.uniform(0.8, 1.2, M), rng.uniform(1, 10, M)], -1).astype(np.float32)
+    opt.set_scene_pcd(cloud)
+    ctx.call('mh_fit_grads', 0, 0, st)                                            # first: where the lowest vertices are
+    verts = opt._view(L.BUF_VERTS).view(T + 2, N, L.LD3V)[1:T + 1, :, :3 * L.V].cpu().numpy().reshape(T, N, L.V, 3)
+    low = verts[np.arange(T)[:, None], np.arange(N)[None], np.argmax(verts[..., 1], axis=2)]           # (T, N, 3)
+    q = low[1, 0]
+    idx = rng.permutation(M)
+    cloud[idx[:10]] = q + np.array([0.0005, 0.0030, 0.0], np.float32)             # 10 copies, nearer than every random point
+    cloud[idx[10:710]] = q + np.array([0.0, -0.0040, 0.0010], np.float32)         # 700 copies at the 32-nearest boundary (different y)
+    opt.set_scene_pcd(cloud)
+    ctx.call('mh_fit_grads', 0, 0, st)
+    losses = ctx.read_losses(st)
+    ref = 0.0
+    for t in range(T):
+        for n in range(N):
+            d2 = ((cloud - low[t, n]) ** 2).sum(1)
+            nn = np.argsort(d2, kind='stable')[:32]
+            if t == 1 and n == 0:
+                assert np.isin(nn, idx[:710]).all() and np.isin(nn, idx[:10]).sum() == 10                # the planted points are the neighbours
+            cdv = cloud[nn, 1].mean() - low[t, n, 1]
+            ref += abs(cdv + 0.02)
+    assert abs(float(losses[L.L_CONTACT]) - ref) <= 1e-5 * ref
+    opt.ctx.close()
+
+
 def _two_shard_cycle(pkg, L, g, data, meta, cycle):
     """World-size-2 frame sharding emulated on ONE GPU: two contexts (rank 0 / 1), halo frames and the shared gradient block
     exchanged through the host exactly as sharding.exchange_halo / allreduce_shared do over NCCL."""
