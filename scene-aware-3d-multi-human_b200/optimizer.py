@@ -319,6 +319,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
             if B is None:
                 B = len(idxs)
                 self._set_batch(B)
+                ctx = self.ctx                         # _set_batch may have replaced the replicated init context by this rank's shard
             arr = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in data.items()
                    if k in ('depths', 'seg_mask', 'pose2d', 'poses_smpl', 'images', 'backmasks')}
             seen[idxs] = True

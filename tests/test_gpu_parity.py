@@ -351,9 +351,11 @@ def test_contact_knn_one_million_points_with_ties(pkg, L):
     opt.ctx.close()
 
 
-def _two_shard_cycle(pkg, L, g, data, meta, cycle):
+def _two_shard_cycle(pkg, L, g, data, meta, cycle, refresh=False):
     """World-size-2 frame sharding emulated on ONE GPU: two contexts (rank 0 / 1), halo frames and the shared gradient block
-    exchanged through the host exactly as sharding.exchange_halo / allreduce_shared do over NCCL."""
+    exchanged through the host exactly as sharding.exchange_halo / allreduce_shared do over NCCL.  ``refresh``: the filtered
+    vertices come from the sharded One-Euro refresh itself (``optimizer._refresh_filters``: rank 0 scans first, hands its filter
+    state to rank 1, then the filtered boundary frames are swapped) instead of being injected; returns them as a third value."""
     import torch
     N, T, W, H, batch = meta[:5]
     sh = sys.modules[pkg.__name__ + '.sharding']
@@ -374,10 +376,23 @@ def _two_shard_cycle(pkg, L, g, data, meta, cycle):
         ctx.set_param(L.P_XSCALE, g[f'c{c}_p_xscale'], st)
         if len(g[f'c{c}_scene_pcd']):
             o.set_scene_pcd(g[f'c{c}_scene_pcd'])
-        if c >= 50:
+        if c >= 50 and not refresh:
             gh.set_filtered(o, g['verts_filtered'])
         ctx.call('mh_halo_pack', st)
         halos.append(o._view(L.BUF_HALO_SEND).view(2, -1).clone())
+    filtered = None
+    if refresh:
+        a, b = opts
+        a.ctx.call('mh_refresh_filters', 0.01, 0.02, 0.001, 0.5, 25.0, 1, a._stream())                   # rank 0: first = 1
+        torch.cuda.synchronize()
+        b._view(L.BUF_CARRY_IN).copy_(a._view(L.BUF_CARRY_OUT))                                          # sharding.send_carry / pass_carry
+        b.ctx.call('mh_refresh_filters', 0.01, 0.02, 0.001, 0.5, 25.0, 0, b._stream())                   # rank 1 continues the scan
+        torch.cuda.synchronize()
+        Fa = a._view(L.BUF_FILTERED).view(a.T_local + 2, -1)
+        Fb = b._view(L.BUF_FILTERED).view(b.T_local + 2, -1)
+        Fa[a.T_local + 1].copy_(Fb[1])                                                                   # filtered halo frames
+        Fb[0].copy_(Fa[a.T_local])
+        filtered = torch.cat([Fa[1:a.T_local + 1], Fb[1:b.T_local + 1]]).clone()
     opts[0]._view(L.BUF_HALO_RECV).view(2, -1)[1].copy_(halos[1][0])           # rank 0 <- rank 1's first frame
     opts[1]._view(L.BUF_HALO_RECV).view(2, -1)[0].copy_(halos[0][1])           # rank 1 <- rank 0's last frame
     opts[0].ctx.call('mh_fit_grads', 0, 1, opts[0]._stream())
@@ -394,6 +409,8 @@ def _two_shard_cycle(pkg, L, g, data, meta, cycle):
              'betas': opts[0].ctx.get_grad(L.P_BETAS, (1, N, 10)), 'xscale': opts[0].ctx.get_grad(L.P_XSCALE, (1, N, 1, 1))}
     for o in opts:
         o.ctx.close()
+    if refresh:
+        return log, grads, filtered
     return log, grads
 
 
@@ -407,6 +424,35 @@ def test_two_shards_equal_one(pkg, L, cycle):
         assert abs(v - ref) <= 1e-4 * abs(ref) + 1e-9, (k, v, ref)
     for nm, gr in grads.items():
         ref = g[f'c{cycle}_g_{nm}'].reshape(gr.shape)
+        assert np.abs(gr - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, nm
+
+
+def test_sharded_filter_refresh_equals_single(pkg, L):
+    """The One-Euro refresh run shard after shard with the filter state handed over (``CARRY_OUT`` -> ``CARRY_IN``, ``first = 0``)
+    gives the SAME filtered vertices, bit for bit, as one context scanning the whole sequence; with the filtered boundary frames
+    swapped the cycle-50 gradients then reproduce the unsharded reference cycle."""
+    import torch
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch = meta[:5]
+    c = 50
+    one = gh.make_optimizer(pkg, g, data, meta)
+    gh.prepare(one, g, data, meta)
+    ctx, st = one.ctx, one._stream()
+    ctx.set_param(L.P_POSES_T, g[f'c{c}_p_poses_T'], st); ctx.set_param(L.P_POSES_SMPL, g[f'c{c}_p_poses_smpl'], st)
+    ctx.set_param(L.P_BETAS, g[f'c{c}_p_betas'], st); ctx.set_param(L.P_XSCALE, g[f'c{c}_p_xscale'], st)
+    ctx.call('mh_refresh_filters', 0.01, 0.02, 0.001, 0.5, 25.0, 1, st)
+    torch.cuda.synchronize()
+    F1 = one._view(L.BUF_FILTERED).view(T + 2, -1)[1:T + 1].clone()
+    one.ctx.close()
+    log, grads, F2 = _two_shard_cycle(pkg, L, g, data, meta, c, refresh=True)
+    assert torch.equal(F1, F2)                                                   # bit for bit
+    ref_f = torch.from_numpy(g['verts_filtered'].reshape(T, N, -1)).to(F1.device)
+    assert float((F1.view(T, N, -1)[..., :3 * L.V] - ref_f).abs().max()) < 2e-6  # metres, vs the reference's filtered vertices
+    for k, v in log.items():
+        ref = float(g[f'c{c}_log_{k}'])
+        assert abs(v - ref) <= 1e-4 * abs(ref) + 1e-9, (k, v, ref)
+    for nm, gr in grads.items():
+        ref = g[f'c{c}_g_{nm}'].reshape(gr.shape)
         assert np.abs(gr - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, nm
 
 
