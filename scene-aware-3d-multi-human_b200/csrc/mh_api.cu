@@ -128,6 +128,9 @@ extern "C" int mh_create(mh_ctx** out, const mh_dims* dims) {
     MH_TRY(dev_alloc(c, &c->lowidx, nb));
     MH_TRY(dev_alloc(c, &c->dA, nb * 288));
     MH_TRY(dev_alloc(c, &c->gT, nb * 4));
+    MH_TRY(dev_alloc(c, &c->shared_part, TN * 12));
+    c->LP = (int)(8 * TN);
+    MH_TRY(dev_alloc(c, &c->lpart, (int64_t)MH_L_COUNT * c->LP));
     MH_TRY(dev_alloc(c, &c->dpf_part, (int64_t)(MH_KSPLIT + 1) * nb * MH_NEXT));
     MH_TRY(dev_alloc(c, &c->order, TN));
     MH_TRY(dev_alloc(c, &c->premask, TN));
@@ -697,6 +700,7 @@ extern "C" int mh_fit_grads(mh_ctx* c, int32_t use_prev, int32_t use_next, void*
 #define MH_MARK(k) do { if (ev) MH_CUDA(c, cudaEventRecord(ev[k], st)); } while (0)
     MH_MARK(0);
     MH_CUDA(c, cudaMemsetAsync(c->grads, 0, sizeof(float) * (c->n_params + MH_L_COUNT), st));
+    MH_TRY(mh_loss_begin(c, st));
     MH_TRY(mh_terms_gather(c, use_prev, use_next, st));
     MhSmplArgs a = {c->params + c->off[MH_P_BETAS], d.N, 0, c->theta_all, c->trans_all, c->params + c->off[MH_P_XSCALE], c->nb, d.N,
                     c->vshaped, c->Jrest, c->A, c->pf, c->vposed, c->verts, c->j17, c->lowidx};

@@ -98,6 +98,8 @@ struct mh_ctx {
     int* lowidx;               // (nb)  argmax_v y   (optimizer.py:487)
     float* dA;                 // (nb, 24, 12)
     float* gT;                 // (nb, 4): sum dV (3), sum <dV, v_local>
+    float* lpart; int LP;      // (MH_L_COUNT, LP) loss partials of one cycle, one slot per contributor (LP = 8 T N), summed in a fixed order
+    float* shared_part;        // (T*N, 12): per-body contributions to the shared-leaf gradients (10 betas, xscale), reduced in a fixed order
     float* dpf_part;           // (MH_KSPLIT + 1, nb, MH_NEXT)
     // depth order / silhouette prepass
     int* order;                // (T, N) persons sorted near -> far (optimizer.py:450)
@@ -157,6 +159,8 @@ int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st);
 int mh_terms_gather(mh_ctx* c, int use_prev, int use_next, cudaStream_t st);
 int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st);
 int mh_terms_post(mh_ctx* c, cudaStream_t st);
+int mh_loss_begin(mh_ctx* c, cudaStream_t st);      // zero the loss partials of the cycle
+int mh_loss_reduce(mh_ctx* c, cudaStream_t st);     // losses[slot] += fixed-order sum of the slot's partials
 int mh_init_iter_grads(mh_ctx* c, int use_prev, int use_next, cudaStream_t st);
 // mh_render.cu
 int mh_render_alloc(mh_ctx* c);

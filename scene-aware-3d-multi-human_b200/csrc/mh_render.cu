@@ -47,7 +47,7 @@ struct MhRenderScratch {
     int nctas;
     size_t smem;
     int* counter;
-    float* gsg; int nslab;
+    long long* gsg; int nslab;
     long long* prof;
     int maxbins;               // tile bins per body before the binning granularity is coarsened (<= R_MAXBINS)
     int bincap_use, wcap_use;  // capacities handed to the kernel (<= the allocated ones; testing aid)
@@ -62,7 +62,7 @@ struct RenderParams {
     const float* zmin_lin; const float* zmax_lin;
     float* pfout; int* devflags;
     int nslab;                    // depth slabs of the tile lists (<= 256)
-    float* gsg;                   // per-CTA NDC-gradient rows (MH_LD3V floats each), zero between bodies
+    long long* gsg;               // per-CTA NDC-gradient rows (MH_LD3V 64-bit fixed-point sums each), zero between bodies
     uint16_t* binlist; int bincap;
     uint2* fbin;                  // per-CTA scratch: packed bin range + depth slab per face
     int* wpix; int* wface; float* wz; int wcap;
@@ -180,9 +180,9 @@ __device__ __forceinline__ void frag_values_desc(uint32_t da, float px, float py
     *sd = inside ? -d : d;
 }
 
-__device__ __forceinline__ void grad_add(float* p, float v);
+__device__ __forceinline__ void grad_add(long long* p, float v);
 
-__device__ __forceinline__ void sil_grad_desc(float* sg, uint32_t da, float px, float py, float gd) {
+__device__ __forceinline__ void sil_grad_desc(long long* sg, uint32_t da, float px, float py, float gd) {
     const float4 q0 = lds128<0>(da), q1 = lds128<16>(da), q2 = lds128<32>(da), q4 = lds128<64>(da);
     const float vx[3] = {q0.x, q0.z, q1.x}, vy[3] = {q0.y, q0.w, q1.y};
     const float il[3] = {q2.z, q2.w, q4.x};                              // edges 01, 02, 12
@@ -248,9 +248,13 @@ __device__ __forceinline__ void frag_values(const float* sv, const int32_t* __re
 }
 
 // gradient scatter: shared-memory float atomics are compare-and-swap loops (ATOMS.CAST.SPIN) that retry when the pixels of a
-// warp hit the same vertex; the gradients go instead as fire-and-forget reductions (RED.E.ADD.F32) to a per-CTA row that stays in L2
-__device__ __forceinline__ void grad_add(float* p, float v) {
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+// warp hit the same vertex; the gradients go instead as fire-and-forget reductions to a per-CTA row that stays in L2.  The sums are
+// 64-bit FIXED-POINT (2^-44 NDC-gradient units, +-5e5 range): integer addition is associative, so the per-vertex sum does not depend
+// on the order in which the pixels of the body arrive -- float reductions made every cycle differ in the last bits from run to run
+#define MH_GFIX 17592186044416.0f          // 2^44
+__device__ __forceinline__ void grad_add(long long* p, float v) {
+    const long long q = __float2ll_rn(fminf(fmaxf(v, -131072.0f), 131072.0f) * MH_GFIX);
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(q) : "memory");
 }
 
 
@@ -297,7 +301,7 @@ __device__ __forceinline__ void make_desc(const RenderParams& P, const float* sv
 // Backward of the unsigned squared edge distance of one silhouette fragment: d = |p - a - t (b - a)|^2 on the nearest edge
 // (first minimum in the order 01, 02, 12, as mh_face_bwd), dd/da = -2 q (1 - t), dd/db = -2 q t.  Reciprocal multiplies: the
 // gradient tolerance (1e-3 of the maximum) does not need the oracle's divisions.
-__device__ __forceinline__ void sil_grad(float* sg, const float* sv, const int32_t* __restrict__ faces, int f, float px, float py, float gd) {
+__device__ __forceinline__ void sil_grad(long long* sg, const float* sv, const int32_t* __restrict__ faces, int f, float px, float py, float gd) {
     const int iv[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
     const float vx[3] = {sv[3 * iv[0]], sv[3 * iv[1]], sv[3 * iv[2]]};
     const float vy[3] = {sv[3 * iv[0] + 1], sv[3 * iv[1] + 1], sv[3 * iv[2] + 1]};
@@ -323,7 +327,7 @@ template <int MODE>      // MODE 0: losses + gradients ; 1: dense zbuf / alpha p
 __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sv = reinterpret_cast<float*>(smem_raw);                                   // MH_LD3V  NDC vertices
-    float* sg = P.gsg + (size_t)blockIdx.x * MH_LD3V;                                 // MH_LD3V  NDC gradients: global (L2), zero on entry
+    long long* sg = P.gsg + (size_t)blockIdx.x * MH_LD3V;                             // MH_LD3V  NDC gradients (fixed point): global (L2), zero on entry
     unsigned long long* dkey = reinterpret_cast<unsigned long long*>(smem_raw + SO_DKEY);
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw + SO_SKEY);
     int* tcount = reinterpret_cast<int*>(smem_raw + SO_TCOUNT);
@@ -807,11 +811,12 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         float* dv = P.dverts + b * MH_LD3V;
         for (int v = tid; v < MH_V; v += R_THREADS) {
             // read at L2 (where the reductions landed), clear for the next body
-            const float gx = __ldcg(&sg[3 * v]), gy = __ldcg(&sg[3 * v + 1]), gz = __ldcg(&sg[3 * v + 2]);
-            if (gx != 0.f) sg[3 * v] = 0.f;
-            if (gy != 0.f) sg[3 * v + 1] = 0.f;
-            if (gz != 0.f) sg[3 * v + 2] = 0.f;
-            if (gx == 0.f && gy == 0.f && gz == 0.f) continue;
+            const long long qx = __ldcg(&sg[3 * v]), qy = __ldcg(&sg[3 * v + 1]), qz = __ldcg(&sg[3 * v + 2]);
+            if (qx != 0) sg[3 * v] = 0;
+            if (qy != 0) sg[3 * v + 1] = 0;
+            if (qz != 0) sg[3 * v + 2] = 0;
+            if ((qx | qy | qz) == 0) continue;
+            const float gx = __ll2float_rn(qx) * (1.0f / MH_GFIX), gy = __ll2float_rn(qy) * (1.0f / MH_GFIX), gz = __ll2float_rn(qz) * (1.0f / MH_GFIX);
             const float X = vw[3 * v], Y = vw[3 * v + 1], Z = vw[3 * v + 2];
             const float iz = 1.0f / Z;
             // x_ndc = -k00 X / Z + k02 ; y_ndc = -k11 Y / Z + k12 ; z_view = Z
@@ -842,8 +847,8 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wface, n * rs->wcap * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wz, n * rs->wcap * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->gsg, n * MH_LD3V * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->gsg, n * MH_LD3V * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(long long));
     { const char* v = getenv("MH_RENDER_NSLAB"); rs->nslab = v ? std::min(std::max(atoi(v), 1), 256) : R_NSLAB; }     // development switch
     rs->prof = nullptr;
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));

@@ -41,17 +41,72 @@ __global__ void k_joint_prep(const float* __restrict__ betas, int rows, const fl
     Jrest[i] = acc;
 }
 
-// one thread per body
-__global__ void k_pose_prep(const float* __restrict__ theta, const float* __restrict__ Jrest, int nbodies, int N,
-                            int per_body_shape, float* __restrict__ A, float* __restrict__ pf) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// Kinematic tree as the warp sees it: lane j = joint j.  parent, depth, up to three children (joints 0 and 9 have three).
+struct MhTreeNode { int8_t parent, depth, child[3]; };
+__device__ const MhTreeNode d_tree[MH_NJ] = {
+    {-1, 0, {1, 2, 3}},   {0, 1, {4, -1, -1}},  {0, 1, {5, -1, -1}},  {0, 1, {6, -1, -1}},  {1, 2, {7, -1, -1}},  {2, 2, {8, -1, -1}},
+    {3, 2, {9, -1, -1}},  {4, 3, {10, -1, -1}}, {5, 3, {11, -1, -1}}, {6, 3, {12, 13, 14}}, {7, 4, {-1, -1, -1}}, {8, 4, {-1, -1, -1}},
+    {9, 4, {15, -1, -1}}, {9, 4, {16, -1, -1}}, {9, 4, {17, -1, -1}}, {12, 5, {-1, -1, -1}}, {13, 5, {18, -1, -1}}, {14, 5, {19, -1, -1}},
+    {16, 6, {20, -1, -1}}, {17, 6, {21, -1, -1}}, {18, 7, {22, -1, -1}}, {19, 7, {23, -1, -1}}, {20, 8, {-1, -1, -1}}, {21, 8, {-1, -1, -1}}};
+#define MH_TREE_DEPTH 8
+
+// Forward chain of one body in a warp (smpl.py:716-746): lane j holds joint j's rotation R, global rotation GR, global translation
+// Gt and its PARENT's global rotation PGR; the tree is walked level by level with shuffles from the parent lane.  Same per-joint
+// arithmetic as mh_pose_forward (mh_math.cuh), which the host-side derivative tests check.
+struct MhJointState { float R[9], GR[9], Gt[3], PGR[9], rel[3]; };
+__device__ __forceinline__ void warp_chain_forward(const float th[3], const float Jj[3], int j, const MhTreeNode nd, MhJointState& S) {
+    if (j < 22) mh_rodrigues(th, S.R);
+    else { S.R[0] = 1; S.R[1] = 0; S.R[2] = 0; S.R[3] = 0; S.R[4] = 1; S.R[5] = 0; S.R[6] = 0; S.R[7] = 0; S.R[8] = 1; }
+    const int p = nd.parent < 0 ? 0 : nd.parent;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) S.rel[e] = Jj[e] - __shfl_sync(0xffffffffu, Jj[e], p);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { S.GR[e] = S.R[e]; S.PGR[e] = 0.f; }
+    S.Gt[0] = Jj[0]; S.Gt[1] = Jj[1]; S.Gt[2] = Jj[2];
+    for (int d = 1; d <= MH_TREE_DEPTH; ++d) {
+        float pGR[9], pGt[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) pGR[e] = __shfl_sync(0xffffffffu, S.GR[e], p);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) pGt[e] = __shfl_sync(0xffffffffu, S.Gt[e], p);
+        if (nd.depth == d) {
+            float o[3];
+            mh_mat3_mul(pGR, S.R, S.GR);
+            mh_mat3_vec(pGR, S.rel, o);
+            S.Gt[0] = o[0] + pGt[0]; S.Gt[1] = o[1] + pGt[1]; S.Gt[2] = o[2] + pGt[2];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) S.PGR[e] = pGR[e];
+        }
+    }
+}
+
+// one WARP per body, lane j = joint j (lanes 24..31 shadow joint 23 and write nothing)
+__global__ void __launch_bounds__(128) k_pose_prep(const float* __restrict__ theta, const float* __restrict__ Jrest, int nbodies, int N,
+                                                   int per_body_shape, float* __restrict__ A, float* __restrict__ pf) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= nbodies) return;
+    const int lane = threadIdx.x & 31, j = min(lane, MH_NJ - 1);
     const int row = per_body_shape ? b : (b % N);
-    float th[72], J[72], Al[288], pfl[207];
-    for (int i = 0; i < 72; ++i) { th[i] = theta[(size_t)b * 72 + i]; J[i] = Jrest[(size_t)row * 72 + i]; }
-    mh_pose_forward(th, J, Al, pfl, nullptr);
-    for (int i = 0; i < 288; ++i) A[(size_t)b * 288 + i] = Al[i];
-    for (int i = 0; i < MH_KPF; ++i) pf[(size_t)b * MH_KPF + i] = (i < MH_NPF_LIVE) ? pfl[i] : 0.0f;
+    const MhTreeNode nd = d_tree[j];
+    float th[3], Jj[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { th[e] = theta[(size_t)b * 72 + 3 * j + e]; Jj[e] = Jrest[(size_t)row * 72 + 3 * j + e]; }
+    MhJointState S;
+    warp_chain_forward(th, Jj, j, nd, S);
+    if (lane >= 1 && lane < 22) {                              // pose feature: R_1..R_21 - I (joints 22, 23 are the identity: rows 189.. are 0)
+#pragma unroll
+        for (int e = 0; e < 9; ++e) pf[(size_t)b * MH_KPF + (lane - 1) * 9 + e] = S.R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+    } else if (lane == 22) {
+        for (int e = MH_NPF_LIVE; e < MH_KPF; ++e) pf[(size_t)b * MH_KPF + e] = 0.0f;
+    }
+    if (lane < MH_NJ) {
+        float rj[3];
+        mh_mat3_vec(S.GR, Jj, rj);
+        float* a = A + (size_t)b * 288 + j * 12;
+        a[0] = S.GR[0]; a[1] = S.GR[1]; a[2] = S.GR[2];  a[3] = S.Gt[0] - rj[0];
+        a[4] = S.GR[3]; a[5] = S.GR[4]; a[6] = S.GR[5];  a[7] = S.Gt[1] - rj[1];
+        a[8] = S.GR[6]; a[9] = S.GR[7]; a[10] = S.GR[8]; a[11] = S.Gt[2] - rj[2];
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -212,7 +267,7 @@ int mh_smpl_forward_run(mh_ctx* c, const MhSmplArgs& a, cudaStream_t st) {
     MH_LAUNCHED(c);
     k_joint_prep<<<mh_cdiv(a.shape_rows * 72, 128), 128, 0, st>>>(a.betas, a.shape_rows, c->Jt, c->Js, a.Jrest);
     MH_LAUNCHED(c);
-    k_pose_prep<<<mh_cdiv(a.nbodies, 64), 64, 0, st>>>(a.theta, a.Jrest, a.nbodies, a.N, a.per_body_shape, a.A, a.pf);
+    k_pose_prep<<<mh_cdiv(a.nbodies, 4), 128, 0, st>>>(a.theta, a.Jrest, a.nbodies, a.N, a.per_body_shape, a.A, a.pf);
     MH_LAUNCHED(c);
     // tensor cores (mh_gemm_tc.cu); MH_GEMM_TC=0 selects the FP32 SIMT kernel for A/B measurements
     static const int use_tc = [] { const char* v = getenv("MH_GEMM_TC"); return v ? atoi(v) : 1; }();
@@ -372,32 +427,129 @@ __global__ void k_reduce_partials(const float* __restrict__ Dpart, float* __rest
     D[o] = a;       // D aliases split 0 after the reduction? no: separate region, see caller
 }
 
-// one thread per local body: chain + Rodrigues backward, gradients into the flat gradient buffer
-__global__ void k_pose_bwd(const float* __restrict__ theta_all, const float* __restrict__ Jrest, const float* __restrict__ dA,
-                           const float* __restrict__ dpf, const float* __restrict__ gT, const float* __restrict__ Js,
-                           const float* __restrict__ xscale, int N, int T, float* __restrict__ g_trans,
-                           float* __restrict__ g_theta, float* __restrict__ g_betas, float* __restrict__ g_xscale) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // local person-frame index t*N + n
+// one WARP per local body, lane j = joint j: chain + Rodrigues backward (mh_pose_backward's algebra, children -> root level by
+// level with shuffles from the child lanes).  dL/dtheta and dL/dT go to the flat gradient buffer; the body's contribution to the
+// SHARED leaves (10 betas + xscale) goes to its own row of `shared_part`, summed in a fixed order by k_shared_reduce -- float
+// atomics would make the shared gradients depend on the order the bodies finish in.
+#define MH_NSHARED 12          // 10 betas, xscale, pad
+__global__ void __launch_bounds__(128) k_pose_bwd(const float* __restrict__ theta_all, const float* __restrict__ Jrest, const float* __restrict__ dA,
+                                                  const float* __restrict__ dpf, const float* __restrict__ gT, const float* __restrict__ Js,
+                                                  const float* __restrict__ xscale, int N, int T, float* __restrict__ g_trans,
+                                                  float* __restrict__ g_theta, float* __restrict__ shared_part) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // local person-frame index t*N + n
     if (i >= T * N) return;
+    const int lane = threadIdx.x & 31, j = min(lane, MH_NJ - 1);
+    const bool act = lane < MH_NJ;
     const int b = i + N;                                      // slot-major body index (slot 0 is the halo)
     const int n = i % N;
-    float th[72], J[72], dAl[288], dpfl[207], dth[72], dJ[72];
-    for (int e = 0; e < 72; ++e) { th[e] = theta_all[(size_t)b * 72 + e]; J[e] = Jrest[(size_t)n * 72 + e]; }
-    for (int e = 0; e < 288; ++e) dAl[e] = dA[(size_t)b * 288 + e];
-    const float* dp = dpf + (size_t)b * MH_NEXT;
-    for (int e = 0; e < 207; ++e) dpfl[e] = (e < MH_NPF_LIVE) ? dp[e] : 0.f;
-    mh_pose_backward(th, J, dAl, dpfl, dth, dJ);
-    for (int e = 0; e < 72; ++e) g_theta[(size_t)i * 72 + e] += dth[e];
-    g_trans[(size_t)i * 3] += gT[(size_t)b * 4]; g_trans[(size_t)i * 3 + 1] += gT[(size_t)b * 4 + 1];
-    g_trans[(size_t)i * 3 + 2] += gT[(size_t)b * 4 + 2];
-    // beta: shape-blend path (rows 192..201 of the extended basis) + rest-joint path
-    for (int l = 0; l < MH_NBETA; ++l) {
-        float a = dp[MH_KPF + l];
-        for (int e = 0; e < 72; ++e) a = fmaf(Js[e * MH_NBETA + l], dJ[e], a);
-        atomicAdd(g_betas + n * MH_NBETA + l, a);
+    const MhTreeNode nd = d_tree[j];
+    float th[3], Jj[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { th[e] = theta_all[(size_t)b * 72 + 3 * j + e]; Jj[e] = Jrest[(size_t)n * 72 + 3 * j + e]; }
+    MhJointState S;
+    warp_chain_forward(th, Jj, j, nd, S);
+    // A.R = G.R ; A.t = G.t - G.R J   =>  dG.R = dA.R - dA.t J^T ; dG.t = dA.t ; dJ = -G.R^T dA.t
+    float dGR[9], dGt[3], dJ[3], dR[9];
+    {
+        float a[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) a[e] = act ? dA[(size_t)b * 288 + j * 12 + e] : 0.f;
+        dGt[0] = a[3]; dGt[1] = a[7]; dGt[2] = a[11];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dGR[r * 3 + k] = a[r * 4 + k] - dGt[r] * Jj[k];
+        float o[3];
+        mh_mat3t_vec(S.GR, dGt, o);
+        dJ[0] = -o[0]; dJ[1] = -o[1]; dJ[2] = -o[2];
     }
-    const float s = powf(1.1f, xscale[n]);
-    atomicAdd(g_xscale + n, 0.09531017980432493f * s * gT[(size_t)b * 4 + 3]);     // d(1.1^x)/dx = ln(1.1) 1.1^x
+#pragma unroll
+    for (int e = 0; e < 9; ++e) dR[e] = 0.f;
+    for (int d = MH_TREE_DEPTH; d >= 1; --d) {
+        // joints of depth d are complete (their children are deeper): their own dR and what they hand to the parent
+        float cR[9], ct[3], cJ[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) cR[e] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { ct[e] = 0.f; cJ[e] = 0.f; }
+        if (act && nd.depth == d) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    // dG_p.R += dG_j.R R_j^T + dG_j.t rel_j^T ; dR_j = G_p.R^T dG_j.R
+                    cR[r * 3 + k] = dGR[r * 3] * S.R[k * 3] + dGR[r * 3 + 1] * S.R[k * 3 + 1] + dGR[r * 3 + 2] * S.R[k * 3 + 2] + dGt[r] * S.rel[k];
+                    dR[r * 3 + k] = S.PGR[r] * dGR[k] + S.PGR[3 + r] * dGR[3 + k] + S.PGR[6 + r] * dGR[6 + k];
+                }
+            float drel[3];
+            mh_mat3t_vec(S.PGR, dGt, drel);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) { ct[e] = dGt[e]; dJ[e] += drel[e]; cJ[e] = -drel[e]; }
+        }
+        // parents (depth d - 1) gather from their children; only joints 0 and 9 have more than one
+        const int nslots = (d == 1 || d == 4) ? 3 : 1;
+        for (int k = 0; k < nslots; ++k) {
+            const int c = nd.child[k];
+            const bool take = act && (nd.depth == d - 1) && (c >= 0);
+            const int src = take ? c : lane;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) { const float v = __shfl_sync(0xffffffffu, cR[e], src); if (take) dGR[e] += v; }
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const float v = __shfl_sync(0xffffffffu, ct[e], src), u = __shfl_sync(0xffffffffu, cJ[e], src);
+                if (take) { dGt[e] += v; dJ[e] += u; }
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) dR[e] = dGR[e];
+        dJ[0] += dGt[0]; dJ[1] += dGt[1]; dJ[2] += dGt[2];
+    }
+    const float* dp = dpf + (size_t)b * MH_NEXT;
+    if (lane >= 1 && lane < 22) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) dR[e] += dp[(lane - 1) * 9 + e];
+    }
+    if (lane < 22) {
+        float dth[3];
+        mh_rodrigues_bwd(th, dR, dth);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) g_theta[(size_t)i * 72 + 3 * lane + e] += dth[e];
+    }
+    if (lane < 3) g_trans[(size_t)i * 3 + lane] += gT[(size_t)b * 4 + lane];
+    // beta: shape-blend path (rows 192..201 of the extended basis) + rest-joint path ; xscale: d(1.1^x)/dx = ln(1.1) 1.1^x
+    float* sp = shared_part + (size_t)i * MH_NSHARED;
+    for (int l = 0; l < MH_NBETA; ++l) {
+        float a = 0.f;
+        if (act) {
+#pragma unroll
+            for (int e = 0; e < 3; ++e) a = fmaf(Js[(3 * j + e) * MH_NBETA + l], dJ[e], a);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) sp[l] = a + dp[MH_KPF + l];
+    }
+    if (lane == 0) sp[MH_NBETA] = 0.09531017980432493f * powf(1.1f, xscale[n]) * gT[(size_t)b * 4 + 3];
+}
+
+// shared-leaf gradients: person n's sum over its T local frames, in a fixed order (strided partial sums, then a fixed tree)
+__global__ void __launch_bounds__(256) k_shared_reduce(const float* __restrict__ shared_part, int N, int T, float* __restrict__ g_betas,
+                                                       float* __restrict__ g_xscale) {
+    __shared__ float sm[256];
+    const int n = blockIdx.x, l = blockIdx.y, tid = threadIdx.x;
+    float a = 0.f;
+    for (int t = tid; t < T; t += 256) a += shared_part[((size_t)t * N + n) * MH_NSHARED + l];
+    sm[tid] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) sm[tid] += sm[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (l < MH_NBETA) g_betas[n * MH_NBETA + l] += sm[0];
+        else g_xscale[n] += sm[0];
+    }
 }
 
 int mh_gemm_bwd_simt(mh_ctx* c, const float* E, float* dpf_part, int M, int first_body, int nb_total, cudaStream_t st) {
@@ -419,9 +571,10 @@ int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st) {
     float* dpf = c->dpf_part + (size_t)MH_KSPLIT * c->nb * MH_NEXT;       // reduced copy lives after the partials
     k_reduce_partials<<<mh_cdiv((int64_t)M * MH_NEXT, 256), 256, 0, st>>>(c->dpf_part, dpf, first, M, c->nb);
     MH_LAUNCHED(c);
-    k_pose_bwd<<<mh_cdiv(M, 32), 32, 0, st>>>(c->theta_all, c->Jrest, c->dA, dpf, c->gT, c->Js, xs, N, T,
-                                              c->grads + c->off[MH_P_POSES_T], c->grads + c->off[MH_P_POSES_SMPL],
-                                              c->grads + c->off[MH_P_BETAS], c->grads + c->off[MH_P_XSCALE]);
+    k_pose_bwd<<<mh_cdiv(M, 4), 128, 0, st>>>(c->theta_all, c->Jrest, c->dA, dpf, c->gT, c->Js, xs, N, T,
+                                              c->grads + c->off[MH_P_POSES_T], c->grads + c->off[MH_P_POSES_SMPL], c->shared_part);
+    MH_LAUNCHED(c);
+    k_shared_reduce<<<dim3(N, MH_NBETA + 1), 256, 0, st>>>(c->shared_part, N, T, c->grads + c->off[MH_P_BETAS], c->grads + c->off[MH_P_XSCALE]);
     MH_LAUNCHED(c);
     return MH_OK;
 }

@@ -65,7 +65,7 @@ struct CamParams { float K[9]; float Kd[5]; int has_kd; float w17[MH_NJR]; };
 __global__ void k_body_terms(const float* __restrict__ j17, const float* __restrict__ pose2d, const float* __restrict__ theta,
                              const float* __restrict__ theta_ref, const float* __restrict__ valid, CamParams cam, int T, int N, float W,
                              float H, float thr, float coef_proj, float coef_poses, float* __restrict__ gj17,
-                             float* __restrict__ g_theta, float* __restrict__ losses) {
+                             float* __restrict__ g_theta, float* __restrict__ lpart, int LP) {
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);       // local person-frame
     const int lane = threadIdx.x & 31;
     if (i >= T * N) return;
@@ -94,7 +94,9 @@ __global__ void k_body_terms(const float* __restrict__ j17, const float* __restr
         g_theta[(size_t)i * 72 + e] = -coef_poses * vld * signf(df);
     }
     l2d = warp_sum(l2d); lp = warp_sum(lp);
-    if (lane == 0) { atomicAdd(losses + MH_L_POSE2D, l2d); atomicAdd(losses + MH_L_REF_POSES, lp); }
+    // loss partials: one slot per contributor, summed in a fixed order by k_loss_reduce (float atomics would make the logged
+    // losses depend on the order the warps finish in)
+    if (lane == 0) { lpart[(size_t)MH_L_POSE2D * LP + i] = l2d; lpart[(size_t)MH_L_REF_POSES * LP + i] = lp; }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) k_dverts_init(const float* __restrict__ v
                                                      const float* __restrict__ gj17, const int* __restrict__ cptr,
                                                      const int* __restrict__ cjoint, const float* __restrict__ cw, int T, int N, int t0,
                                                      int T_total, int use_prev, int use_next, int has_filters, float coef,
-                                                     float* __restrict__ dverts, float* __restrict__ losses) {
+                                                     float* __restrict__ dverts, float* __restrict__ lpart, int LP) {
     __shared__ float sm[32];
     const int i = blockIdx.y;                    // local person-frame
     const int s = i / N + 1;                     // slot
@@ -134,14 +136,14 @@ __global__ void __launch_bounds__(256) k_dverts_init(const float* __restrict__ v
     }
     if (has_filters) {
         loss = block_sum(loss, sm);
-        if (threadIdx.x == 0 && loss != 0.f) atomicAdd(losses + MH_L_FILTER_VERTS, loss);
+        if (threadIdx.x == 0) lpart[(size_t)MH_L_FILTER_VERTS * LP + (size_t)blockIdx.y * gridDim.x + blockIdx.x] = loss;
     }
 }
 
 // -------------------------------------------------------------------------------------------------
 // velocity term on the translations (optimizer.py:560-561; init: :758-760)
 __global__ void k_velocity(const float* __restrict__ trans_all, int T, int N, int t0, int T_total, int use_prev, int use_next, float coef,
-                           float* __restrict__ g_trans, float* __restrict__ losses) {
+                           float* __restrict__ g_trans, float* __restrict__ lpart, int LP) {
     __shared__ float sm[32];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // (t, n, k)
     float loss = 0.f;
@@ -160,7 +162,7 @@ __global__ void k_velocity(const float* __restrict__ trans_all, int T, int N, in
         g_trans[idx] += g;
     }
     loss = block_sum(loss, sm);
-    if (threadIdx.x == 0 && loss != 0.f) atomicAdd(losses + MH_L_VEL, loss);
+    if (threadIdx.x == 0) lpart[(size_t)MH_L_VEL * LP + blockIdx.x] = loss;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -181,7 +183,7 @@ template <int KNN_Q>
 __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict__ verts, const int* __restrict__ lowidx,
                                                          const float* __restrict__ scene, int64_t M, int N, int TN, float coef,
                                                          float* __restrict__ contact, float* __restrict__ g_trans,
-                                                         float* __restrict__ losses) {
+                                                         float* __restrict__ lpart, int LP) {
     __shared__ float smin[KNN_Q][KNN_THREADS];
     __shared__ float cd[KNN_Q][KNN_CAP];
     __shared__ int ci[KNN_Q][KNN_CAP];
@@ -271,16 +273,19 @@ __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict
         for (int k = 0; k < KNN_Q; ++k) if (k == q) yq = y[k];
         const float cdv = my - yq;                              // contact_dist_vertical (:501)
         const float r = cdv + 0.02f;                            // target.y = T.y + cdv + 0.02 (:502-503)
-        atomicAdd(losses + MH_L_CONTACT, fabsf(r));
+        lpart[(size_t)MH_L_CONTACT * LP + i] = fabsf(r);
         g_trans[(size_t)i * 3 + 1] += coef * -signf(r);         // d|T - target|/dT.y with the target detached (:504-506)
         contact[(size_t)i * 4] = cdv;
         contact[(size_t)i * 4 + 1] = cdv > -0.20f ? 1.0f : 0.0f;   // in_thr_contact_region (:509-510)
     }
 }
 
-// foot sliding (optimizer.py:512-518): one CTA per local batch segment; pairs are ADJACENT ENTRIES OF ONE BATCH
+// foot sliding (optimizer.py:512-518): one CTA per local batch segment; pairs are ADJACENT ENTRIES OF ONE BATCH.  Gather form: the
+// thread of body (t, n) applies BOTH gradients that reach the body -- as the later frame of pair (t-1, t), at its own lowest vertex, and
+// as the earlier frame of pair (t, t+1), at the lowest vertex of frame t+1 -- so no two threads touch the same row (no atomics: the
+// sum does not depend on an execution order)
 __global__ void k_foot(const float* __restrict__ verts, const int* __restrict__ lowidx, const float* __restrict__ contact, int T, int N,
-                       int B, float coef, float* __restrict__ dverts, float* __restrict__ losses) {
+                       int B, float coef, float* __restrict__ dverts, float* __restrict__ lpart, int LP) {
     __shared__ float sm[32];
     __shared__ float sden;
     const int k = blockIdx.x;
@@ -296,23 +301,35 @@ __global__ void k_foot(const float* __restrict__ verts, const int* __restrict__ 
     __syncthreads();
     const float den = sden;
     float loss = 0.f;
-    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
-        const int t = ta + 1 + p / N, n = p % N;
+    // gradient of pair (t - 1, t) w.r.t. coordinate q of vertex lowidx[t] of frame t (and minus that for frame t - 1)
+    auto pair_grad = [&](int t, int n, int q, float* absdf) {
         const float in = contact[((size_t)t * N + n) * 4 + 1];
         const size_t bt = (size_t)(t + 1) * N + n, bp = bt - N;
         const int li = lowidx[bt];
+        const float df = in * verts[bt * MH_LD3V + 3 * li + q] - in * verts[bp * MH_LD3V + 3 * li + q];
+        *absdf = fabsf(df);
+        return coef * in * signf(df) / den;
+    };
+    const int nbod = (tb - ta) * N;
+    for (int p = threadIdx.x; p < nbod; p += blockDim.x) {
+        const int t = ta + p / N, n = p % N;
+        const size_t bt = (size_t)(t + 1) * N + n;
+        float* row = dverts + bt * MH_LD3V;
         for (int q = 0; q < 3; ++q) {
-            const float df = in * verts[bt * MH_LD3V + 3 * li + q] - in * verts[bp * MH_LD3V + 3 * li + q];
-            loss += fabsf(df);
-            const float g = coef * in * signf(df) / den;
-            if (g != 0.f) {
-                atomicAdd(dverts + bt * MH_LD3V + 3 * li + q, g);
-                atomicAdd(dverts + bp * MH_LD3V + 3 * li + q, -g);
+            float a;
+            if (t > ta) {                                         // later frame of pair (t - 1, t): counted here for the loss
+                const float g = pair_grad(t, n, q, &a);
+                loss += a;
+                if (g != 0.f) row[3 * lowidx[bt] + q] += g;
+            }
+            if (t + 1 < tb) {                                     // earlier frame of pair (t, t + 1)
+                const float g = pair_grad(t + 1, n, q, &a);
+                if (g != 0.f) row[3 * lowidx[bt + N] + q] -= g;
             }
         }
     }
     loss = block_sum(loss, sm);
-    if (threadIdx.x == 0) atomicAdd(losses + MH_L_FOOT, loss / den);
+    if (threadIdx.x == 0) lpart[(size_t)MH_L_FOOT * LP + blockIdx.x] = loss / den;
 }
 
 static CamParams cam_of(const mh_ctx* c) {
@@ -331,13 +348,13 @@ int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) 
     float* g_trans = c->grads + c->off[MH_P_POSES_T];
     k_body_terms<<<mh_cdiv(TN, 4), 128, 0, st>>>(c->j17, c->pose2d, c->params + c->off[MH_P_POSES_SMPL], c->theta_ref, c->valid, cam_of(c),
                                                  d.T, d.N, (float)d.W, (float)d.H, c->c.joint_confidence_thr, c->c.proj2d, c->c.reg_poses,
-                                                 c->gj17, c->grads + c->off[MH_P_POSES_SMPL], losses);
+                                                 c->gj17, c->grads + c->off[MH_P_POSES_SMPL], c->lpart, c->LP);
     MH_LAUNCHED(c);
     k_dverts_init<<<dim3(8, TN), 256, 0, st>>>(c->verts, c->filtered, c->gj17, c->cptr, c->cjoint, c->cw, d.T, d.N, d.t0, d.T_total,
-                                               use_prev, use_next, c->has_filters ? 1 : 0, c->c.reg_verts_filter, c->dverts, losses);
+                                               use_prev, use_next, c->has_filters ? 1 : 0, c->c.reg_verts_filter, c->dverts, c->lpart, c->LP);
     MH_LAUNCHED(c);
     k_velocity<<<mh_cdiv(TN * 3, 256), 256, 0, st>>>(c->trans_all, d.T, d.N, d.t0, d.T_total, use_prev, use_next, c->c.reg_velocity,
-                                                     g_trans, losses);
+                                                     g_trans, c->lpart, c->LP);
     MH_LAUNCHED(c);
     if (c->M > 0) {
         // person-frames per CTA: as many as keep two waves of CTAs -- measured: 256 CTAs of 2 are slower than 512 CTAs of 1 on 148 SMs
@@ -345,11 +362,11 @@ int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) 
         const int w2 = 2 * c->num_sms;
         int Q = TN >= 8 * w2 ? 8 : TN >= 4 * w2 ? 4 : TN >= 2 * w2 ? 2 : 1;
         if (const char* v = getenv("MH_KNN_Q")) { const int q = atoi(v); if (q == 1 || q == 2 || q == 4 || q == 8) Q = q; }
-#define MH_CONTACT(QQ) k_contact<QQ><<<mh_cdiv(TN, QQ), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, losses)
+#define MH_CONTACT(QQ) k_contact<QQ><<<mh_cdiv(TN, QQ), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, c->lpart, c->LP)
         if (Q == 8) MH_CONTACT(8); else if (Q == 4) MH_CONTACT(4); else if (Q == 2) MH_CONTACT(2); else MH_CONTACT(1);
 #undef MH_CONTACT
         MH_LAUNCHED(c);
-        k_foot<<<mh_cdiv(d.T, d.B), 128, 0, st>>>(c->verts, c->lowidx, c->contact, d.T, d.N, d.B, c->c.reg_foot_sliding, c->dverts, losses);
+        k_foot<<<mh_cdiv(d.T, d.B), 128, 0, st>>>(c->verts, c->lowidx, c->contact, d.T, d.N, d.B, c->c.reg_foot_sliding, c->dverts, c->lpart, c->LP);
         MH_LAUNCHED(c);
     }
     return MH_OK;
@@ -359,7 +376,7 @@ int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) 
 // after the render stage: depth-range gradients and the depth / silhouette loss sums, one thread per frame
 __global__ void k_frame_finalize(const float* __restrict__ pfout, const float* __restrict__ zmin_lin, const float* __restrict__ zmax_lin,
                                  int T, int N, float coef_depth, float* __restrict__ g_zmin, float* __restrict__ g_zmax,
-                                 float* __restrict__ losses) {
+                                 float* __restrict__ lpart, int LP) {
     __shared__ float sm[32];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     float ld = 0.f, ls = 0.f;
@@ -384,7 +401,7 @@ __global__ void k_frame_finalize(const float* __restrict__ pfout, const float* _
     }
     ld = block_sum(ld, sm);
     ls = block_sum(ls, sm);
-    if (threadIdx.x == 0) { atomicAdd(losses + MH_L_DEPTH, ld); atomicAdd(losses + MH_L_SILHOUETTE, ls); }
+    if (threadIdx.x == 0) { lpart[(size_t)MH_L_DEPTH * LP + blockIdx.x] = ld; lpart[(size_t)MH_L_SILHOUETTE * LP + blockIdx.x] = ls; }
 }
 
 // shape prior (weighted by the batch size per batch, :526) and the scale priors (once per batch, :531-542)
@@ -416,10 +433,36 @@ __global__ void k_shared_priors(const float* __restrict__ betas, const float* __
         const float g = coef_scales * 2.0f * (sc - 1.0f) / (float)N + (coef_scales > 0.f ? 1.0f : 0.0f) * 2.0f * tot;
         g_xscale[n] += (float)nbatch_local * g * 0.09531017980432493f * sc;
     }
-    if (tid == 0) {
-        atomicAdd(losses + MH_L_REF_POSES, (float)T_local * lb);
-        atomicAdd(losses + MH_L_SCALE, (float)nbatch_local * (tot * tot + s2 / (float)N));
+    if (tid == 0) {                 // the only block, after k_loss_reduce in stream order: plain adds
+        losses[MH_L_REF_POSES] += (float)T_local * lb;
+        losses[MH_L_SCALE] += (float)nbatch_local * (tot * tot + s2 / (float)N);
     }
+}
+
+// losses[slot] += sum of the slot's partials, in a fixed order (strided partial sums per thread, then a fixed tree)
+__global__ void __launch_bounds__(256) k_loss_reduce(const float* __restrict__ lpart, int LP, float* __restrict__ losses) {
+    __shared__ float sm[256];
+    const int slot = blockIdx.x, tid = threadIdx.x;
+    float a = 0.f;
+    for (int e = tid; e < LP; e += 256) a += lpart[(size_t)slot * LP + e];
+    sm[tid] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) sm[tid] += sm[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) losses[slot] += sm[0];
+}
+
+int mh_loss_begin(mh_ctx* c, cudaStream_t st) {
+    MH_CUDA(c, cudaMemsetAsync(c->lpart, 0, sizeof(float) * (size_t)MH_L_COUNT * c->LP, st));
+    return MH_OK;
+}
+
+int mh_loss_reduce(mh_ctx* c, cudaStream_t st) {
+    k_loss_reduce<<<MH_L_COUNT, 256, 0, st>>>(c->lpart, c->LP, c->grads + c->n_params);
+    MH_LAUNCHED(c);
+    return MH_OK;
 }
 
 int mh_terms_post(mh_ctx* c, cudaStream_t st) {
@@ -428,9 +471,10 @@ int mh_terms_post(mh_ctx* c, cudaStream_t st) {
     if (c->c.depth != 0.f || c->c.silhouette != 0.f) {
         k_frame_finalize<<<mh_cdiv(d.T, 128), 128, 0, st>>>(c->pfout, c->params + c->off[MH_P_ZMIN_LIN], c->params + c->off[MH_P_ZMAX_LIN],
                                                             d.T, d.N, c->c.depth, c->grads + c->off[MH_P_ZMIN_LIN],
-                                                            c->grads + c->off[MH_P_ZMAX_LIN], losses);
+                                                            c->grads + c->off[MH_P_ZMAX_LIN], c->lpart, c->LP);
         MH_LAUNCHED(c);
     }
+    MH_TRY(mh_loss_reduce(c, st));
     k_shared_priors<<<1, 128, 0, st>>>(c->params + c->off[MH_P_BETAS], c->betas_ref, c->params + c->off[MH_P_XSCALE], d.N, d.T,
                                        mh_cdiv(d.T, d.B), c->c.reg_poses, c->c.reg_scales, c->grads + c->off[MH_P_BETAS],
                                        c->grads + c->off[MH_P_XSCALE], losses);
@@ -443,7 +487,7 @@ int mh_terms_post(mh_ctx* c, cudaStream_t st) {
 //   loss_2d = mean over (T_total, N, 17, 2) of (vis * proj - vis * gt)^2   [pixels]
 __global__ void k_init_2d(const float* __restrict__ j17, const float* __restrict__ vis, const float* __restrict__ pose2d,
                           const float* __restrict__ trans, const float* __restrict__ xscale, CamParams cam, int T, int N, float inv_count,
-                          float coef_proj, float* __restrict__ g_trans, float* __restrict__ losses) {
+                          float coef_proj, float* __restrict__ g_trans, float* __restrict__ lpart, int LP) {
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (i >= T * N) return;
@@ -464,7 +508,7 @@ __global__ void k_init_2d(const float* __restrict__ j17, const float* __restrict
     }
     l = warp_sum(l); g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
     if (lane == 0) {
-        atomicAdd(losses + MH_L_INIT_2D, l);
+        lpart[(size_t)MH_L_INIT_2D * LP + i] = l;
         g_trans[(size_t)i * 3] += g0; g_trans[(size_t)i * 3 + 1] += g1; g_trans[(size_t)i * 3 + 2] += g2;
     }
 }
@@ -478,13 +522,15 @@ int mh_init_iter_grads(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) {
     float* g_trans = c->grads + c->off[MH_P_POSES_T];
     MH_CUDA(c, cudaMemsetAsync(g_trans, 0, sizeof(float) * TN * 3, st));
     MH_CUDA(c, cudaMemsetAsync(losses, 0, sizeof(float) * MH_L_COUNT, st));
+    MH_TRY(mh_loss_begin(c, st));
     MH_TRY(mh_terms_gather(c, use_prev, use_next, st));
     const float inv_count = 1.0f / ((float)d.T_total * d.N * MH_NJR * 2);
     k_init_2d<<<mh_cdiv(TN, 4), 128, 0, st>>>(c->init_j17, c->init_vis, c->pose2d, c->params + c->off[MH_P_POSES_T],
-                                              c->params + c->off[MH_P_XSCALE], cam_of(c), d.T, d.N, inv_count, c->c.proj2d, g_trans, losses);
+                                              c->params + c->off[MH_P_XSCALE], cam_of(c), d.T, d.N, inv_count, c->c.proj2d, g_trans, c->lpart, c->LP);
     MH_LAUNCHED(c);
     k_velocity<<<mh_cdiv(TN * 3, 256), 256, 0, st>>>(c->trans_all, d.T, d.N, d.t0, d.T_total, use_prev, use_next, c->c.reg_velocity, g_trans,
-                                                     losses);
+                                                     c->lpart, c->LP);
     MH_LAUNCHED(c);
+    MH_TRY(mh_loss_reduce(c, st));
     return MH_OK;
 }
