@@ -214,6 +214,13 @@ int mh_scene_set_back(mh_ctx* ctx, int32_t t_local0, int32_t count, const uint8_
  * MH_BUF_MEDIAN_AUX (planes 0-2 SUM, planes 3-5 MIN). */
 int mh_scene_median_pass(mh_ctx* ctx, int32_t which, int32_t pass, void* stream);
 /* results to HOST: depth (H,W) f32 + mask (H,W) u8 (which = 0) or image (H,W,3) u8 (which = 1); blocking */
+/* Device-resident scene update of one cycle >= 30 (optimizer.py:578-584) after the median passes of the depth: median depth ->
+ * postprocess_depthmap (utils.py:174-209: bilateral filter, Sobel edge mask, two erosions, fill-in sweeps of utils.py:91-135) ->
+ * update_scene_pointcloud (optimizer.py:605-616), all on the device.  depth_host_or_null: (H,W) post-processed depth map. */
+int mh_scene_update_from_median(mh_ctx* ctx, int32_t use_bilateral_filter, int32_t fillin_ksize, float* depth_host_or_null, void* stream);
+/* postprocess_depthmap (utils.py:174-209) of a host depth map (H,W) on the device; mask_host_or_null (H,W) u8 {0,1} */
+int mh_postprocess_depthmap(mh_ctx* ctx, const float* depth_host, const uint8_t* mask_host_or_null, int32_t use_bilateral_filter,
+                            int32_t fillin_ksize, float* out_host, void* stream);
 int mh_scene_median_finish(mh_ctx* ctx, int32_t which, float* depth_host, uint8_t* mask_host, uint8_t* img_host, void* stream);
 
 /* ---- debugging / input synthesis ---------------------------------------------------------------- */

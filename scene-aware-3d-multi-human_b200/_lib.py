@@ -67,6 +67,8 @@ def _load():
         'mh_ingest_frames': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         'mh_ingest_frames_u8': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         'mh_finalize_ingest': (c_int32, [ctx, c_void_p]),
+        'mh_scene_update_from_median': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p]),
+        'mh_postprocess_depthmap': (c_int32, [ctx, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
         'mh_set_scene': (c_int32, [ctx, c_void_p, c_int64, c_void_p]),
         'mh_set_scene_from_depth': (c_int32, [ctx, c_void_p, c_void_p, c_void_p]),
         'mh_set_param': (c_int32, [ctx, c_int32, c_void_p, c_int64, c_void_p]),

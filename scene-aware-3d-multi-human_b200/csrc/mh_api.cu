@@ -64,6 +64,7 @@ extern "C" int mh_create(mh_ctx** out, const mh_dims* dims) {
     c->optim_scale = true;
     c->rs = nullptr;
     c->scene_state = nullptr;
+    c->scene_post = nullptr;
     c->M = 0;
     c->events = nullptr; c->timing = false; c->timing_iter = 0;
     for (int k = 0; k < MH_NJR; ++k) c->w17[k] = 1.0f;
@@ -158,6 +159,7 @@ extern "C" void mh_destroy(mh_ctx* c) {
     cudaDeviceSynchronize();
     mh_render_free(c);
     mh_scene_free(c);
+    mh_scenepost_free(c);
     if (c->events) { for (int i = 0; i < MH_TIMING_RING * MH_TIMING_EVENTS; ++i) cudaEventDestroy(c->events[i]); delete[] c->events; }
     for (void* p : c->allocs) cudaFree(p);
     if (c->stage) cudaFree(c->stage);

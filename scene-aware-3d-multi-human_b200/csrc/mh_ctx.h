@@ -116,6 +116,7 @@ struct mh_ctx {
     float* transfilt;          // (T*N*3) filtered translations (only a not-None flag upstream)
     MhRenderScratch* rs;
     void* scene_state;         // mh_scene.cu
+    void* scene_post;          // mh_scenepost.cu
     // stage timing (bench)
     cudaEvent_t* events; bool timing; int64_t timing_iter;
 };
@@ -176,6 +177,10 @@ int mh_scene_from_depth(mh_ctx* c, const float* depth_dev, const uint8_t* mask_d
 int mh_ingest_compact(mh_ctx* c, int t0, int count, int seg_is_u8, cudaStream_t st);
 int mh_ingest_derive(mh_ctx* c, cudaStream_t st);
 int mh_expand_planes(mh_ctx* c, int t, float* seg_dev, cudaStream_t st);
+// mh_scenepost.cu
+int mh_scene_postprocess_dev(mh_ctx* c, const float* depth_dev, const uint8_t* mask_dev, int use_bilateral, int fillin_ksize, cudaStream_t st);
+const float* mh_scene_post_result(mh_ctx* c);
+void mh_scenepost_free(mh_ctx* c);
 // mh_scene.cu
 void mh_scene_free(mh_ctx* c);
 int mh_scene_views(mh_ctx* c, int which, void** ptr, int64_t* n);

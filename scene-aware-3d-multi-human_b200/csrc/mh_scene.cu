@@ -332,6 +332,54 @@ extern "C" int mh_scene_median_finish(mh_ctx* c, int32_t which, float* depth_hos
     return MH_OK;
 }
 
+// Device-resident scene update of one fit() cycle (optimizer.py:578-584) after the median passes: median depth -> postprocess_depthmap
+// (mh_scenepost.cu) -> scene point cloud; nothing but the hole counts of the fill-in sweeps crosses the bus.  depth_host_or_null receives
+// the post-processed depth map (get_optimized_variables()['scene_depth']) when the caller wants it.
+extern "C" int mh_scene_update_from_median(mh_ctx* c, int32_t use_bilateral, int32_t fillin_ksize, float* depth_host_or_null, void* stream) {
+    if (!c) return MH_E_ARG;
+    cudaSetDevice(c->d.device);
+    MhSceneState* s = scene_state(c);
+    if (!s) MH_FAIL(c, MH_E_STATE, "mh_scene_update_from_median: no scene state (mh_scene_set_back + median passes first)");
+    if (!c->camera_set) MH_FAIL(c, MH_E_STATE, "mh_scene_update_from_median: mh_set_camera first");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t HW = s->HW;
+    k_med_finish_depth<<<mh_cdiv(HW, 256), 256, 0, st>>>(s->aux, s->prefix, s->ntot, HW, s->out_depth, s->out_mask);
+    MH_LAUNCHED(c);
+    MH_TRY(mh_scene_postprocess_dev(c, s->out_depth, s->out_mask, use_bilateral, fillin_ksize, st));
+    const float* res = mh_scene_post_result(c);
+    MH_TRY(mh_scene_from_depth(c, res, s->out_mask, st));
+    if (depth_host_or_null) {
+        MH_CUDA(c, cudaMemcpyAsync(depth_host_or_null, res, sizeof(float) * HW, cudaMemcpyDeviceToHost, st));
+        MH_CUDA(c, cudaStreamSynchronize(st));
+    }
+    return MH_OK;
+}
+
+// postprocess_depthmap (utils.py:174-209) of a HOST depth map on the device (testing aid and stand-alone use): mask_host_or_null u8 {0,1}
+extern "C" int mh_postprocess_depthmap(mh_ctx* c, const float* depth_host, const uint8_t* mask_host_or_null, int32_t use_bilateral,
+                                       int32_t fillin_ksize, float* out_host, void* stream) {
+    if (!c) return MH_E_ARG;
+    cudaSetDevice(c->d.device);
+    if (!depth_host || !out_host) MH_FAIL(c, MH_E_ARG, "mh_postprocess_depthmap: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t HW = (int64_t)c->d.H * c->d.W;
+    float* dd = nullptr; uint8_t* dm = nullptr;
+    MH_CUDA(c, cudaMalloc((void**)&dd, HW * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(dd, depth_host, HW * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && mask_host_or_null) {
+        e = cudaMalloc((void**)&dm, HW);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dm, mask_host_or_null, HW, cudaMemcpyHostToDevice, st);
+    }
+    int r = MH_OK;
+    if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "mh_postprocess_depthmap: %s", cudaGetErrorString(e)); r = MH_E_CUDA; }
+    if (r == MH_OK) r = mh_scene_postprocess_dev(c, dd, dm, use_bilateral, fillin_ksize, st);
+    if (r == MH_OK && cudaMemcpyAsync(out_host, mh_scene_post_result(c), HW * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) r = MH_E_CUDA;
+    cudaStreamSynchronize(st);
+    cudaFree(dd);
+    if (dm) cudaFree(dm);
+    return r;
+}
+
 int mh_scene_views(mh_ctx* c, int which, void** ptr, int64_t* n) {
     MhSceneState* s = scene_state(c);
     if (!s) MH_FAIL(c, MH_E_STATE, "scene median buffers do not exist yet (mh_scene_set_back first)");

@@ -400,14 +400,15 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
             if self._dist:
                 sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
             if cycle >= 30 and self.scene_update:
-                ma = self._update_scene_geometry()
+                self._update_scene_geometry(read_back=(cycle == num_iter - 1))
+                ma = True
             ctx.call('mh_fit_update', lr, st)
             lr *= 0.99
             losses = ctx.read_losses(st)
             optim_log.append(sharding.log_from_loss_block(losses, n_batches))
         if ma is not None:
             # the median image only depends on constant inputs: evaluated once instead of every cycle (optimizer.py:581, 595-600)
-            scene_mask = ma[1].copy()
+            scene_mask = self._median_result(0)[1].copy()
             scene_img = self._device_median(1) if self._have_images else None
             if scene_img is not None:
                 while scene_mask.min() == 0:
@@ -447,7 +448,11 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
 
     def _device_median(self, which):
         """Masked temporal median over ALL frames (``fhsog.py:180-202``) by exact radix selection on the device; the
-        per-pixel digit histograms are summed over the ranks between passes (``csrc/mh_scene.cu``)."""
+        per-pixel digit histograms are summed over the ranks between passes (``csrc/mh_scene.cu``).  Returns host arrays."""
+        self._median_passes(which)
+        return self._median_result(which)
+
+    def _median_passes(self, which):
         ctx, st = self.ctx, self._stream()
         HW = self.img_h * self.img_w
         npass = 10 if which == 0 else 4
@@ -462,6 +467,9 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
                     aux = self._view(L.BUF_MEDIAN_AUX)
                     torch.distributed.all_reduce(aux[:planes * HW], op=torch.distributed.ReduceOp.SUM, group=self.group)
                     torch.distributed.all_reduce(aux[3 * HW:(3 + planes) * HW], op=torch.distributed.ReduceOp.MIN, group=self.group)
+
+    def _median_result(self, which):
+        ctx, st = self.ctx, self._stream()
         if which == 0:
             depth = np.empty((self.img_h, self.img_w), np.float32)
             mask = np.empty((self.img_h, self.img_w), np.uint8)
@@ -471,15 +479,24 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         ctx.call('mh_scene_median_finish', 1, None, None, L.ptr(img), st)
         return img
 
-    def _update_scene_geometry(self):
-        """``optimizer.py:578-584``: masked temporal median of the per-frame scene depths (device) -> bilateral / edge /
-        fill-in post-processing of ONE depth map (host, ``scene.py``) -> scene point cloud (device).  Every rank computes
-        the same map."""
-        ma_depth, ma_mask = self._device_median(0)
-        scene_depth = scene_ops.postprocess_depthmap(ma_depth, ma_mask, use_bilateral_filter=True)
-        self.scene_depth = scene_depth
-        self.update_scene_pointcloud(scene_depth, ma_mask)
-        return ma_depth, ma_mask
+    def _update_scene_geometry(self, read_back=False):
+        """``optimizer.py:578-584``, all on the device: masked temporal median of the per-frame scene depths (``mh_scene.cu``) ->
+        ``postprocess_depthmap`` (bilateral filter, Sobel edge mask, erosions, fill-in sweeps: ``mh_scenepost.cu``) -> scene point
+        cloud.  Every rank computes the same map.  ``read_back``: fetch the post-processed depth map (the ``scene_depth`` output)."""
+        self._median_passes(0)
+        out = np.empty((self.img_h, self.img_w), np.float32) if read_back else None
+        self.ctx.call('mh_scene_update_from_median', 1, 7, L.ptr(out), self._stream())
+        self.scene_pcd = True
+        self.scene_depth = out if read_back else True
+
+    def postprocess_depthmap(self, depth, mask=None, fillin_ksize=7, use_bilateral_filter=False):
+        """``mhmocap.utils.postprocess_depthmap`` (``utils.py:174-209``) on the device (``scene.postprocess_depthmap`` is the host
+        mirror the parity tests compare it with)."""
+        d = L.f32(depth)
+        m = None if mask is None else np.ascontiguousarray(np.asarray(mask) > 0).astype(np.uint8)
+        out = np.empty_like(d)
+        self.ctx.call('mh_postprocess_depthmap', L.ptr(d), L.ptr(m), int(bool(use_bilateral_filter)), int(fillin_ksize), L.ptr(out), self._stream())
+        return out
 
     def update_scene_pointcloud(self, scene_depth, scene_mask):
         """``optimizer.py:605-616``: inverse-project the pixel centres with the scene depth, keep ``mask > 0.5``."""

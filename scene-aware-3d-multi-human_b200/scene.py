@@ -24,9 +24,12 @@ def aggregate_scene_geometry_median(depths, images, backmasks):
 def fillin_values(x, mask, filter_size, metric='median'):
     """One fill-in sweep: every pixel with ``mask == 0`` that has a valid pixel inside its ``filter_size`` window
     (clipped at the border) takes the ``metric`` of the valid ones and becomes valid."""
-    assert x.shape[0:2] == mask.shape, f'Error: invalid x/mask shapes {x.shape}/{mask.shape}'
-    assert filter_size > 1, f'Error: invalid filter size {filter_size}, must be > 1'
-    assert metric in ('median', 'mean', 'max', 'min'), f'Error: invalid metric {metric}'
+    if tuple(x.shape[:2]) != tuple(mask.shape):
+        raise ValueError(f'x is {x.shape[:2]} but the mask is {mask.shape}')
+    if filter_size < 2:
+        raise ValueError(f'the window must span at least 2 pixels, got {filter_size}')
+    if metric not in ('median', 'mean', 'max', 'min'):
+        raise ValueError(f'unknown reduction {metric!r}')
     reduce_fn = {'median': np.nanmedian, 'mean': np.nanmean, 'max': np.nanmax, 'min': np.nanmin}[metric]
     k = filter_size // 2
     H, W = mask.shape
