@@ -30,9 +30,10 @@ Parity status
 -------------
 * Reference-owned arithmetic (SMPL, projection, loss algebra, priors, temporal
   terms, RMSprop/Adam): PINNED -- checked against the reference's own functions
-  imported from ``/root/reference`` (``tests/test_oracle_vs_reference.py``, runs
-  only where the reference is mounted) and against the committed golden vectors
-  in ``tests/golden/`` generated by the unmodified reference.
+  imported from ``/root/reference`` by the generators ``tests/golden/make_golden.py``,
+  ``make_eval_golden.py`` and ``make_init_w17_golden.py`` (they run only where the
+  reference is mounted) and, at test time, against the committed golden vectors
+  they wrote to ``tests/golden/`` (``tests/test_oracle_golden.py``).
 * Rasteriser / silhouette shader: PARITY UNPINNED.  The algorithm lives in the
   third-party dependency ``pytorch3d`` (conda channel ``pytorch3d``, unpinned in
   the reference's ``environment.yml:13``; ~0.5-0.7), whose source is not under

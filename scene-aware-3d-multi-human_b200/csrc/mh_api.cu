@@ -9,6 +9,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "mh_ctx.h"
@@ -103,6 +105,7 @@ extern "C" int mh_create(mh_ctx** out, const mh_dims* dims) {
     MH_TRY(dev_alloc(c, &c->cbits, d.T * HW));
     MH_TRY(dev_alloc(c, &c->ebits, d.T * HW));
     c->stage = nullptr; c->stage_floats = 0;
+    c->pack_buf[0] = c->pack_buf[1] = nullptr; c->pack_ev[0] = c->pack_ev[1] = nullptr; c->pack_words = 0; c->pack_idx = 0; c->host_nonbinary = false;
     MH_TRY(dev_alloc(c, &c->pose2d, TN * 17 * 3));
     MH_TRY(dev_alloc(c, &c->theta_ref, TN * 72));
     MH_TRY(dev_alloc(c, &c->valid, TN));
@@ -163,6 +166,7 @@ extern "C" void mh_destroy(mh_ctx* c) {
     if (c->events) { for (int i = 0; i < MH_TIMING_RING * MH_TIMING_EVENTS; ++i) cudaEventDestroy(c->events[i]); delete[] c->events; }
     for (void* p : c->allocs) cudaFree(p);
     if (c->stage) cudaFree(c->stage);
+    for (int i = 0; i < 2; ++i) { if (c->pack_buf[i]) cudaFreeHost(c->pack_buf[i]); if (c->pack_ev[i]) cudaEventDestroy(c->pack_ev[i]); }
     delete c;
 }
 
@@ -326,6 +330,46 @@ extern "C" int mh_ingest_frames_u8(mh_ctx* c, int32_t t0, int32_t count, const f
     return ingest_frames(c, t0, count, depths, seg, 1, pose2d, theta_ref, valid, stream);
 }
 
+// float32 {0., 1.} masks (count, N, HW) -> one 32-bit plane per frame on the HOST, all cores: the reference dataset delivers 4 N bytes
+// per pixel and frame (utils.py:329-331); packed, 4 bytes cross the bus instead.  Returns true when a value other than 0 / 1 was seen.
+static bool pack_masks_host(const float* seg, int count, int N, int64_t HW, uint32_t* out) {
+    const int64_t total = (int64_t)count * HW;
+    const int nthr = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const int64_t chunk = 8192;                                   // pixels per work item: the output chunk stays in L1 over the N passes
+    std::atomic<int64_t> next(0);
+    std::atomic<int> bad(0);
+    auto work = [&]() {
+        int mybad = 0;
+        for (;;) {
+            const int64_t i0 = next.fetch_add(chunk);
+            if (i0 >= total) break;
+            const int64_t i1 = std::min(total, i0 + chunk);
+            int64_t i = i0;
+            while (i < i1) {                                      // a chunk may straddle a frame boundary
+                const int64_t t = i / HW, p0 = i - t * HW, n_here = std::min(i1 - i, HW - p0);
+                uint32_t* o = out + i;
+                for (int64_t p = 0; p < n_here; ++p) o[p] = 0u;
+                for (int n = 0; n < N; ++n) {
+                    const float* s = seg + ((int64_t)t * N + n) * HW + p0;
+                    const uint32_t bit = 1u << n;
+                    for (int64_t p = 0; p < n_here; ++p) {
+                        const float v = s[p];
+                        o[p] |= (v != 0.f) ? bit : 0u;
+                        mybad |= (v != 0.f) & (v != 1.0f);
+                    }
+                }
+                i += n_here;
+            }
+        }
+        if (mybad) bad.store(1);
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < nthr; ++k) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return bad.load() != 0;
+}
+
 static int ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* depths, const void* seg, int seg_is_u8, const float* pose2d,
                          const float* theta_ref, const float* valid, void* stream) {
     API_BEGIN(c);
@@ -334,6 +378,32 @@ static int ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* dept
     if (t0 < 0 || count < 1 || t0 + count > d.T) MH_FAIL(c, MH_E_ARG, "mh_ingest_frames: frames [%d, %d) outside [0, %d)", t0, t0 + count, d.T);
     if (!pose2d || !theta_ref || !valid) MH_FAIL(c, MH_E_ARG, "mh_ingest_frames: null buffer");
     const int64_t HW = (int64_t)d.H * d.W, nseg = (int64_t)count * d.N * HW, need = seg_is_u8 ? (nseg + 3) / 4 : nseg;
+    // float32 masks are compacted on the host (MH_INGEST_HOST_PACK=0: on the device after a full-size copy, for A/B measurements)
+    static const bool host_pack = [] { const char* v = getenv("MH_INGEST_HOST_PACK"); return v ? atoi(v) != 0 : true; }();
+    if (seg && !seg_is_u8 && host_pack) {
+        const int64_t words = (int64_t)count * HW;
+        if (words > c->pack_words) {
+            MH_CUDA(c, cudaStreamSynchronize(st));
+            for (int i = 0; i < 2; ++i) {
+                if (c->pack_buf[i]) cudaFreeHost(c->pack_buf[i]);
+                c->pack_buf[i] = nullptr;
+                MH_CUDA(c, cudaHostAlloc((void**)&c->pack_buf[i], sizeof(uint32_t) * words, cudaHostAllocDefault));
+                if (!c->pack_ev[i]) MH_CUDA(c, cudaEventCreateWithFlags(&c->pack_ev[i], cudaEventDisableTiming));
+            }
+            c->pack_words = words;
+        }
+        const int bi = c->pack_idx;
+        c->pack_idx ^= 1;
+        MH_CUDA(c, cudaEventSynchronize(c->pack_ev[bi]));           // the copy that last read this buffer is done (no-op the first time)
+        if (depths) MH_CUDA(c, cudaMemcpyAsync(c->depth + (int64_t)t0 * HW, depths, sizeof(float) * count * HW, cudaMemcpyHostToDevice, st));
+        if (pack_masks_host(reinterpret_cast<const float*>(seg), count, d.N, HW, c->pack_buf[bi])) c->host_nonbinary = true;
+        MH_CUDA(c, cudaMemcpyAsync(c->cbits + (int64_t)t0 * HW, c->pack_buf[bi], sizeof(uint32_t) * words, cudaMemcpyHostToDevice, st));
+        MH_CUDA(c, cudaEventRecord(c->pack_ev[bi], st));
+        MH_CUDA(c, cudaMemcpyAsync(c->pose2d + (int64_t)t0 * d.N * 51, pose2d, sizeof(float) * count * d.N * 51, cudaMemcpyHostToDevice, st));
+        MH_CUDA(c, cudaMemcpyAsync(c->theta_ref + (int64_t)t0 * d.N * 72, theta_ref, sizeof(float) * count * d.N * 72, cudaMemcpyHostToDevice, st));
+        MH_CUDA(c, cudaMemcpyAsync(c->valid + (int64_t)t0 * d.N, valid, sizeof(float) * count * d.N, cudaMemcpyHostToDevice, st));
+        return MH_OK;
+    }
     if (seg && need > c->stage_floats) {
         MH_CUDA(c, cudaStreamSynchronize(st));
         if (c->stage) cudaFree(c->stage);
@@ -358,7 +428,11 @@ extern "C" int mh_finalize_ingest(mh_ctx* c, void* stream) {
     int flags[8];
     MH_CUDA(c, cudaMemcpyAsync(flags, c->devflags, sizeof(flags), cudaMemcpyDeviceToHost, st));
     MH_CUDA(c, cudaStreamSynchronize(st));
-    if (flags[0]) MH_FAIL(c, MH_E_ARG, "ingest: seg_mask holds values other than 0 / 1 (instance masks must be binary, utils.py:329-331)");
+    if (flags[0] || c->host_nonbinary) {
+        c->host_nonbinary = false;
+        cudaMemsetAsync(c->devflags, 0, sizeof(int), st);
+        MH_FAIL(c, MH_E_ARG, "ingest: seg_mask holds values other than 0 / 1 (instance masks must be binary, utils.py:329-331)");
+    }
     c->ingested = true;
     return MH_OK;
 }

@@ -64,6 +64,8 @@ struct mh_ctx {
     uint32_t* ebits;           // (T, H*W)   bit n = erode(erode(seg_mask[t,n]))       (optimizer.py:306-309, 434)
     float* stage;              // staging for one ingest call (count, N, H*W) f32
     int64_t stage_floats;
+    // host-side compaction of float32 masks (ingest): two pinned buffers of packed bit planes, each with the event of its last copy
+    uint32_t* pack_buf[2]; cudaEvent_t pack_ev[2]; int64_t pack_words; int pack_idx; bool host_nonbinary;
     float* pose2d;             // (T, N, 17, 3)
     float* theta_ref;          // (T, N, 72)
     float* valid;              // (T, N)

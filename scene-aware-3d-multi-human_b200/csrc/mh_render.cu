@@ -39,6 +39,9 @@
 #define KEY_EMPTY 0xffffffffffffffffull
 #define R_DESC 1024               // (face, tile) descriptors staged per chunk (5 float4 each)
 #define R_QUEUE 64                // survivor queue entries per warp (fewer than 32 wait, a pass adds at most 32)
+#ifndef MH_R_ROWPASS
+#define MH_R_ROWPASS 1            // 1: a prune pass covers whole rows of the face's rectangle (lane -> (row, column) fixed per face, the pixel
+#endif                            //    index advances by a constant) ; 0: 32 consecutive pixels of the rectangle in row-major order
 
 struct MhRenderScratch {
     uint16_t* binlist; int bincap;
@@ -294,7 +297,12 @@ __device__ __forceinline__ void make_desc(const RenderParams& P, const float* sv
     d[0] = make_float4(x0, y0, x1, y1);
     d[1] = make_float4(x2, y2, z0, z1);
     d[2] = make_float4(z2, __frcp_rn(den), l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), l02 <= MH_KEPS ? 0.f : __frcp_rn(l02));
-    d[3] = make_float4(__int_as_float(rect), __int_as_float(inner), __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))), __int_as_float((65536 + w - 1) / w));
+#if MH_R_ROWPASS
+    const int lanemap = ((65536 + w - 1) / w) | ((32 / w) << 20);           // 1 / w (16.16 fixed point, <= 65536) | whole rows per pass
+#else
+    const int lanemap = (65536 + w - 1) / w;
+#endif
+    d[3] = make_float4(__int_as_float(rect), __int_as_float(inner), __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))), __int_as_float(lanemap));
     d[4] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), __int_as_float(f), __uint_as_float((unsigned)i0 | ((unsigned)i1 << 16)), __int_as_float(i2));
 }
 
@@ -641,19 +649,59 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                 const float4 q3 = lds128<48>(sb + SO_SDESC + k * 80);
                 const int rect = __float_as_int(q3.x), inner = __float_as_int(q3.y);
                 const unsigned zbits = __float_as_uint(q3.z);
-                const int magic = __float_as_int(q3.w);
+                const int lanemap = __float_as_int(q3.w);
                 const int w = (rect >> 10) & 63;                          // 0: binned conservatively, nothing of the face in this tile
                 const int c0 = rect & 31, r0 = (rect >> 5) & 31;
-                const int npix = w * ((rect >> 16) & 63);
+                const int h = (rect >> 16) & 63;
                 const int jc0 = inner & 31, jr0 = (inner >> 5) & 31;
                 const unsigned jw = (inner >> 10) & 63, jh = (inner >> 16) & 63;
                 const unsigned ebase = (unsigned)k << 10;
-                if (lane == 0 && npix) { RS_ADD(0, 1); RS_ADD(1, npix); }
-                // PRUNE passes over the face's rectangle
+                if (lane == 0 && w) { RS_ADD(0, 1); RS_ADD(1, w * h); }
+#if MH_R_ROWPASS
+                // PRUNE passes over whole rows of the face's rectangle: lane -> (row lr, column lc) of the first rows once per face,
+                // then only the pixel index advances.  A pixel survives when the face's nearest vertex is not behind the key it could
+                // displace (the depth words of the keys alone, conservative on ties); outside the inner rectangle the face cannot be
+                // a silhouette fragment at all
+                if (w == 0) continue;
+                const int rpp = lanemap >> 20;                            // whole rows per pass (32 / w)
+                const int lr = (lane * (lanemap & 0xfffff)) >> 16;        // lane / w
+                const int lx = c0 + lane - lr * w;
+                const bool lane_ok = lr < rpp;
+                // per-lane bounds fold the lane tests in: a lane beyond the last whole row (or outside the inner columns) has an
+                // empty range.  Every lane loads (addresses stay inside the key planes), the range tests apply afterwards
+                int pix = lane_ok ? (r0 + lr) * TW + lx : 0;
+                const int pend = lane_ok ? (r0 + h) * TW : 0;
+                const unsigned ipix0 = (unsigned)(jr0 * TW);
+                const unsigned ipixn = (lane_ok && ((unsigned)(lx - jc0) < jw)) ? jh * TW : 0u;      // inner rows are rows of the rectangle
+                const int step = rpp * TW;
+#pragma unroll 1
+                for (int rb = 0; rb < h; rb += rpp) {
+                    RS_WARP(2);
+                    const uint32_t ka = sb + 8 * pix;
+                    const unsigned td = lds32<SO_DKEY + 4>(ka), ts = lds32<SO_SKEY + 3 * SK_STRIDE + 4>(ka);
+                    const bool pd = (pix < pend) && (zbits <= td);
+                    const bool ps = ((unsigned)pix - ipix0 < ipixn) && (zbits <= ts);
+                    const unsigned bal = __ballot_sync(0xffffffffu, pd || ps);
+                    if (pd || ps) {
+                        sts32<0>(qa + 4 * (qn + __popc(bal & ltmask)), ebase | (unsigned)pix | (pd ? 1u << 20 : 0u) | (ps ? 1u << 21 : 0u));
+                        RS_ADD(3, 1);
+                    }
+                    qn += __popc(bal);
+                    pix += step;
+                    if (qn >= 32) {                                       // a full batch
+                        __syncwarp();
+                        qn -= 32;
+                        evaluate(lds32<0>(qa + 4 * (qn + lane)));
+                        __syncwarp();
+                    }
+                }
+#else
+                const int npix = w * h;
+                // PRUNE passes over the face's rectangle, 32 consecutive pixels (row-major) per pass
                 for (int o = lane; o - lane < npix; o += 32) {
                     RS_WARP(2);
                     const bool valid = o < npix;
-                    const int row = (o * magic) >> 16;
+                    const int row = (o * lanemap) >> 16;
                     const int col = o - row * w;
                     const int lx = c0 + col, ly = r0 + row;
                     const int pix = ly * TW + lx;
@@ -679,6 +727,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
                         __syncwarp();
                     }
                 }
+#endif
               }
               __syncwarp();
               if (lane < qn) evaluate(lds32<0>(qa + 4 * lane));           // the rest

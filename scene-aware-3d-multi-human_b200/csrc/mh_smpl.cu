@@ -181,6 +181,23 @@ __global__ void __launch_bounds__(256) k_gemm_fwd(const float* __restrict__ Am, 
 }
 
 // -------------------------------------------------------------------------------------------------
+// The body's 24 joint transforms (24 x 12 floats = 1152 bytes, contiguous) are staged into shared memory by ONE TMA bulk copy
+// (cp.async.bulk + mbarrier complete_tx) issued by thread 0 while the other threads set up; every thread then waits on the barrier.
+__device__ __forceinline__ void stage_transforms_issue(float* sA, unsigned long long* bar, const float* src) {
+    const uint32_t b32 = (uint32_t)__cvta_generic_to_shared(bar), d32 = (uint32_t)__cvta_generic_to_shared(sA);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "n"(288 * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d32), "l"(src), "n"(288 * 4), "r"(b32)
+                 : "memory");
+}
+__device__ __forceinline__ void stage_transforms_wait(unsigned long long* bar) {
+    const uint32_t b32 = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(b32) : "memory");
+}
+
 // one CTA per body
 __global__ void __launch_bounds__(256) k_skin_fwd(const float* __restrict__ vposed, const float* __restrict__ A,
                                                   const uint8_t* __restrict__ wj, const float* __restrict__ ww, int KW,
@@ -189,15 +206,17 @@ __global__ void __launch_bounds__(256) k_skin_fwd(const float* __restrict__ vpos
                                                   const float* __restrict__ rw, float* __restrict__ verts,
                                                   float* __restrict__ j17, int* __restrict__ lowidx, int first_body) {
     const int b = first_body + blockIdx.x;
-    __shared__ float sA[288];
+    __shared__ __align__(16) float sA[288];
+    __shared__ __align__(8) unsigned long long bar;
     __shared__ float sred[8];
     __shared__ int sredi[8];
     const int tid = threadIdx.x;
-    for (int i = tid; i < 288; i += 256) sA[i] = A[(size_t)b * 288 + i];
+    if (tid == 0) stage_transforms_issue(sA, &bar, A + (size_t)b * 288);
     const float s = xscale ? powf(1.1f, xscale[b % N]) : 1.0f;            // optimizer.py:681
     const float t0 = trans ? trans[(size_t)b * 3] : 0.f, t1 = trans ? trans[(size_t)b * 3 + 1] : 0.f,
                 t2 = trans ? trans[(size_t)b * 3 + 2] : 0.f;
-    __syncthreads();
+    __syncthreads();                                                      // the barrier object is initialised
+    stage_transforms_wait(&bar);
     const float* vp = vposed + (size_t)b * MH_LD3V;
     float* vo = verts + (size_t)b * MH_LD3V;
     float besty = -INFINITY;
@@ -295,10 +314,11 @@ __global__ void __launch_bounds__(256) k_skin_bwd(float* __restrict__ dverts, co
                                                   const float* __restrict__ xscale, int N, float* __restrict__ dA,
                                                   float* __restrict__ gT, int first_body) {
     const int b = first_body + blockIdx.x;
-    __shared__ float sA[288];
+    __shared__ __align__(16) float sA[288];
+    __shared__ __align__(8) unsigned long long bar;
     __shared__ float sred[8][4];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < 288; i += 256) sA[i] = A[(size_t)b * 288 + i];
+    if (tid == 0) stage_transforms_issue(sA, &bar, A + (size_t)b * 288);   // consumed in phase 2; phase 1 runs meanwhile
     const float s = powf(1.1f, xscale[b % N]);
     float* dv = dverts + (size_t)b * MH_LD3V;
     const float* vp = vposed + (size_t)b * MH_LD3V;
@@ -323,6 +343,7 @@ __global__ void __launch_bounds__(256) k_skin_bwd(float* __restrict__ dverts, co
             for (int e = 0; e < 12; ++e) dA[((size_t)b * MH_NJ + j) * 12 + e] = acc[e];
     }
     __syncthreads();
+    stage_transforms_wait(&bar);
     // phase 2: per vertex  dv_posed = (sum_j W_ij A_j.R)^T (s dV) ; sum dV ; sum <dV, v_local>
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, ss = 0.f;
     for (int v = tid; v < V_; v += 256) {
