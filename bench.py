@@ -343,11 +343,13 @@ def run_init_loop(opt, aux, w, L, iters=50, warmup=5):
     ctx.call('mh_init_begin', L.ptr(aux['pose2d']), L.ptr(aux['theta_ref']), L.ptr(betas), 0.15, st)
     sh = sys.modules[type(opt).__module__.rsplit('.', 1)[0] + '.sharding']
 
-    def it(k, lr):
+    def it(k, lr):                                   # as SMPLDepthSequenceOptimizer.__init_global_poses, without the loss readback
+        if opt._lib_comm or not opt._dist:
+            ctx.call('mh_init_cycle', lr, k + 1, st)
+            return
         hp, hn = opt._exchange_halo()
         ctx.call('mh_init_grads', hp, hn, st)
-        if opt._dist:
-            sh.allreduce_shared(opt._view(L.BUF_SHARED), opt.group)
+        sh.allreduce_shared(opt._view(L.BUF_SHARED), opt.group)
         ctx.call('mh_init_update', lr, k + 1, st)
 
     lr = 0.5
@@ -423,7 +425,9 @@ def run_e2e(pkg, w, device, opt_dev, aux, steps):
                                          allow_partial_loader=True, **COEFS)
     opt.init_optimized_variables(pose2d, theta_ref, betas, valid, num_iter=100, batch_size=B)
     opt.set_scene_pcd(aux['cloud'])
+    t_init = time.perf_counter()
     log = opt.fit(loader, num_iter=50 + steps, start_cycle=50)
+    t_fit = time.perf_counter()
     out = opt.get_optimized_variables()
     torch.cuda.synchronize(device)
     dt = time.perf_counter() - t_begin
@@ -431,6 +435,8 @@ def run_e2e(pkg, w, device, opt_dev, aux, steps):
         tt = torch.tensor([dt], device=device, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
+    print(f'e2e phases (rank {opt.rank}): construct + init {t_init - t_begin:.3f} s | fit (ingest {getattr(opt, "ingest_seconds", 0.0):.3f} s + '
+          f'{steps} cycles) {t_fit - t_init:.3f} s | read back {time.perf_counter() - t_fit:.3f} s', file=sys.stderr)
     d2h = sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray)) + (steps + 100) * 16 * 4
     h2d = opt.h2d_bytes + pose2d.nbytes + theta_ref.nbytes + betas.nbytes + aux['cloud'].nbytes
     opt.ctx.close()

@@ -214,6 +214,24 @@ int mh_scene_set_back(mh_ctx* ctx, int32_t t_local0, int32_t count, const uint8_
  * MH_BUF_MEDIAN_AUX (planes 0-2 SUM, planes 3-5 MIN). */
 int mh_scene_median_pass(mh_ctx* ctx, int32_t which, int32_t pass, void* stream);
 /* results to HOST: depth (H,W) f32 + mask (H,W) u8 (which = 0) or image (H,W,3) u8 (which = 1); blocking */
+/* ---- library-owned communicator and fused cycles (mh_set_comm; 8e) -------------------------------------------------
+ * The reference is single-process (predict.py:267-271); these serve this build's frame sharding.  NCCL is bound at run time
+ * (dlopen): without it mh_comm_unique_id / mh_set_comm return MH_E_STATE and the caller exchanges the buffers of mh_device_view
+ * itself (optimizer.py does so through torch.distributed). */
+/* 128-byte NCCL unique id, produced on ONE rank and handed to every rank's mh_set_comm by the caller */
+int mh_comm_unique_id(mh_ctx* ctx, uint8_t* out128);
+/* collective over the mh_dims.world ranks: the context creates and owns an ncclComm_t.  prev_rank / next_rank: ranks owning the
+ * frames before / after this rank's range, -1 at the ends of the sequence */
+int mh_set_comm(mh_ctx* ctx, const uint8_t* unique_id128, int32_t prev_rank, int32_t next_rank);
+int mh_has_comm(mh_ctx* ctx);
+/* one fit() cycle (optimizer.py:375-587) enqueued on `stream`: [halo exchange] -> mh_fit_grads -> [all-reduce of the shared-leaf
+ * gradients and losses] -> mh_fit_update(lr).  A context with world > 1 needs mh_set_comm first. */
+int mh_fit_cycle(mh_ctx* ctx, float lr, void* stream);
+/* the same without the step (the caller rebuilds the scene between the gradients and mh_fit_update, optimizer.py:578-587) */
+int mh_fit_cycle_grads(mh_ctx* ctx, void* stream);
+/* one iteration of the translation init (optimizer.py:743-761): [halo] -> mh_init_grads -> [all-reduce] -> mh_init_update */
+int mh_init_cycle(mh_ctx* ctx, float lr, int32_t step, void* stream);
+
 /* Device-resident scene update of one cycle >= 30 (optimizer.py:578-584) after the median passes of the depth: median depth ->
  * postprocess_depthmap (utils.py:174-209: bilateral filter, Sobel edge mask, two erosions, fill-in sweeps of utils.py:91-135) ->
  * update_scene_pointcloud (optimizer.py:605-616), all on the device.  depth_host_or_null: (H,W) post-processed depth map. */

@@ -67,6 +67,12 @@ def _load():
         'mh_ingest_frames': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         'mh_ingest_frames_u8': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         'mh_finalize_ingest': (c_int32, [ctx, c_void_p]),
+        'mh_comm_unique_id': (c_int32, [ctx, c_void_p]),
+        'mh_set_comm': (c_int32, [ctx, c_void_p, c_int32, c_int32]),
+        'mh_has_comm': (c_int32, [ctx]),
+        'mh_fit_cycle': (c_int32, [ctx, c_float, c_void_p]),
+        'mh_fit_cycle_grads': (c_int32, [ctx, c_void_p]),
+        'mh_init_cycle': (c_int32, [ctx, c_float, c_int32, c_void_p]),
         'mh_scene_update_from_median': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p]),
         'mh_postprocess_depthmap': (c_int32, [ctx, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
         'mh_set_scene': (c_int32, [ctx, c_void_p, c_int64, c_void_p]),

@@ -67,6 +67,7 @@ extern "C" int mh_create(mh_ctx** out, const mh_dims* dims) {
     c->rs = nullptr;
     c->scene_state = nullptr;
     c->scene_post = nullptr;
+    c->comm = nullptr;
     c->M = 0;
     c->events = nullptr; c->timing = false; c->timing_iter = 0;
     for (int k = 0; k < MH_NJR; ++k) c->w17[k] = 1.0f;
@@ -163,6 +164,7 @@ extern "C" void mh_destroy(mh_ctx* c) {
     mh_render_free(c);
     mh_scene_free(c);
     mh_scenepost_free(c);
+    mh_comm_free(c);
     if (c->events) { for (int i = 0; i < MH_TIMING_RING * MH_TIMING_EVENTS; ++i) cudaEventDestroy(c->events[i]); delete[] c->events; }
     for (void* p : c->allocs) cudaFree(p);
     if (c->stage) cudaFree(c->stage);
@@ -335,7 +337,7 @@ extern "C" int mh_ingest_frames_u8(mh_ctx* c, int32_t t0, int32_t count, const f
 static bool pack_masks_host(const float* seg, int count, int N, int64_t HW, uint32_t* out) {
     const int64_t total = (int64_t)count * HW;
     const int nthr = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-    const int64_t chunk = 8192;                                   // pixels per work item: the output chunk stays in L1 over the N passes
+    const int64_t chunk = 2048;                                   // pixels per work item: the 8 KB output chunk stays in L1 over the N passes
     std::atomic<int64_t> next(0);
     std::atomic<int> bad(0);
     auto work = [&]() {
@@ -379,7 +381,10 @@ static int ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* dept
     if (!pose2d || !theta_ref || !valid) MH_FAIL(c, MH_E_ARG, "mh_ingest_frames: null buffer");
     const int64_t HW = (int64_t)d.H * d.W, nseg = (int64_t)count * d.N * HW, need = seg_is_u8 ? (nseg + 3) / 4 : nseg;
     // float32 masks are compacted on the host (MH_INGEST_HOST_PACK=0: on the device after a full-size copy, for A/B measurements)
-    static const bool host_pack = [] { const char* v = getenv("MH_INGEST_HOST_PACK"); return v ? atoi(v) != 0 : true; }();
+    // -- only when this process is alone on the host: with one rank per GPU the ranks' copies run in parallel over their own PCIe
+    // links while the packing threads would all share the same cores and memory channels
+    static const int host_pack_env = [] { const char* v = getenv("MH_INGEST_HOST_PACK"); return v ? atoi(v) : -1; }();
+    const bool host_pack = host_pack_env >= 0 ? host_pack_env != 0 : d.world == 1;
     if (seg && !seg_is_u8 && host_pack) {
         const int64_t words = (int64_t)count * HW;
         if (words > c->pack_words) {

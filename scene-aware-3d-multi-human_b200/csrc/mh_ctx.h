@@ -119,6 +119,7 @@ struct mh_ctx {
     MhRenderScratch* rs;
     void* scene_state;         // mh_scene.cu
     void* scene_post;          // mh_scenepost.cu
+    void* comm;                // mh_comm.cu: the NCCL communicator this context owns (mh_set_comm), or null
     // stage timing (bench)
     cudaEvent_t* events; bool timing; int64_t timing_iter;
 };
@@ -179,6 +180,8 @@ int mh_scene_from_depth(mh_ctx* c, const float* depth_dev, const uint8_t* mask_d
 int mh_ingest_compact(mh_ctx* c, int t0, int count, int seg_is_u8, cudaStream_t st);
 int mh_ingest_derive(mh_ctx* c, cudaStream_t st);
 int mh_expand_planes(mh_ctx* c, int t, float* seg_dev, cudaStream_t st);
+// mh_comm.cu
+void mh_comm_free(mh_ctx* c);
 // mh_scenepost.cu
 int mh_scene_postprocess_dev(mh_ctx* c, const float* depth_dev, const uint8_t* mask_dev, int use_bilateral, int fillin_ksize, cudaStream_t st);
 const float* mh_scene_post_result(mh_ctx* c);

@@ -185,6 +185,39 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         w = np.ascontiguousarray(self.pose17j_weights, np.float32)
         self.ctx.call('mh_set_joint_weights', w.ctypes.data_as(L.FP))
         self._views = {}
+        self._lib_comm = self._dist and self._setup_lib_comm()
+
+    def _setup_lib_comm(self):
+        """Hand the per-cycle exchanges (halo frames, all-reduce of the shared leaves) to a communicator the library owns
+        (``mh_set_comm``: NCCL bound at run time), so that one C call enqueues a whole cycle.  Falls back to ``torch.distributed`` on
+        the library's device buffers when NCCL cannot be loaded, when the process group is not NCCL (the CPU tests use gloo) or
+        when ``MH_LIB_COMM=0``.  Collective: every rank of the group takes the same branch."""
+        dist = torch.distributed
+        if not (dist.is_available() and dist.is_initialized()):
+            return False                                                    # ranks emulated inside one process (tests)
+        if os.environ.get('MH_LIB_COMM', '1') == '0' or dist.get_backend(self.group) != 'nccl':
+            return False
+        uid = np.zeros(128, np.uint8)
+        ok = 1
+        if self.rank == 0:
+            try:
+                self.ctx.call('mh_comm_unique_id', L.ptr(uid))
+            except L.MhError:
+                ok = 0
+        box = [(ok, uid.tobytes())]
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.broadcast_object_list(box, src=src, group=self.group)
+        ok, raw = box[0]
+        if not ok:
+            return False
+        uid = np.frombuffer(raw, np.uint8).copy()
+        flag = torch.ones(1, device=self.device)
+        try:
+            self.ctx.call('mh_set_comm', L.ptr(uid), -1 if self.prev is None else self.prev, -1 if self.next is None else self.next)
+        except L.MhError:
+            flag.zero_()
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)         # all or nobody
+        return bool(flag.item() > 0)
 
     def _view(self, which):
         """torch tensor aliasing a device buffer of the library (for the NCCL plumbing)."""
@@ -292,11 +325,13 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         log = []
         count = float(self.T_total * self.num_people * 17 * 2)
         for it in range(num_iter):
-            hp, hn = self._exchange_halo()
-            ctx.call('mh_init_grads', hp, hn, st)
-            if self._dist:
+            if self._lib_comm or not self._dist:
+                ctx.call('mh_init_cycle', lr, it + 1, st)                  # halo, gradients, all-reduce, Adam step: one call
+            else:
+                hp, hn = self._exchange_halo()
+                ctx.call('mh_init_grads', hp, hn, st)
                 sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
-            ctx.call('mh_init_update', lr, it + 1, st)
+                ctx.call('mh_init_update', lr, it + 1, st)
             lr *= 0.95
             losses = ctx.read_losses(st)
             log.append({'loss_2d': np.float32(losses[L.L_INIT_2D] / count)})
@@ -380,7 +415,10 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         schedule -- learning rate, filter refreshes, scene updates -- at that cycle: cycles ``start_cycle .. num_iter - 1`` run."""
         ctx, st = self.ctx, self._stream()
         if not self._ingested:
+            import time
+            t0 = time.perf_counter()
             self._ingest(dataloader)
+            self.ingest_seconds = time.perf_counter() - t0
         if not self.optim_scale_factor:
             print('WARNING!!! Not optimizing scale_factor!')
         ctx.call('mh_reset_optimizer', st)
@@ -395,14 +433,14 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         for cycle in cycles:
             if (cycle >= 30) and (cycle % update_filters_every == 0):
                 self._refresh_filters(min_cutoff1, beta1, min_cutoff2, beta2)
-            hp, hn = self._exchange_halo()
-            ctx.call('mh_fit_grads', hp, hn, st)
-            if self._dist:
-                sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
             if cycle >= 30 and self.scene_update:
+                # the scene is rebuilt between this cycle's gradients (which still see the previous cloud) and the step (optimizer.py:578-587)
+                self._cycle(None)
                 self._update_scene_geometry(read_back=(cycle == num_iter - 1))
                 ma = True
-            ctx.call('mh_fit_update', lr, st)
+                ctx.call('mh_fit_update', lr, st)
+            else:
+                self._cycle(lr)
             lr *= 0.99
             losses = ctx.read_losses(st)
             optim_log.append(sharding.log_from_loss_block(losses, n_batches))
@@ -416,14 +454,25 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
             self.scene_img, self.scene_mask = scene_img, scene_mask
         return optim_log
 
-    def step_device_only(self, lr):
-        """One cycle without any host readback (bench inner loop): halo, gradients, all-reduce, update."""
-        hp, hn = self._exchange_halo()
+    def _cycle(self, lr):
+        """One optimisation cycle: halo exchange, gradients, all-reduce of the shared leaves and -- unless ``lr`` is None -- the
+        RMSprop step."""
         st = self._stream()
+        if self._lib_comm or not self._dist:                                # one C call, nothing but kernels and NCCL on the stream
+            if lr is None:
+                self.ctx.call('mh_fit_cycle_grads', st)
+            else:
+                self.ctx.call('mh_fit_cycle', lr, st)
+            return
+        hp, hn = self._exchange_halo()
         self.ctx.call('mh_fit_grads', hp, hn, st)
-        if self._dist:
-            sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
-        self.ctx.call('mh_fit_update', lr, st)
+        sharding.allreduce_shared(self._view(L.BUF_SHARED), self.group)
+        if lr is not None:
+            self.ctx.call('mh_fit_update', lr, st)
+
+    def step_device_only(self, lr):
+        """One cycle without any host readback (bench inner loop)."""
+        self._cycle(lr)
 
     def _refresh_filters(self, mc1, b1, mc2, b2, frame_rate=25):
         """``optimizer.py:383-392``: the One-Euro scan is sequential in time, so the ranks run it one after the other,

@@ -22,8 +22,13 @@ def _dense(a):
     return np.array(a, dtype=np.float32)
 
 
+_CACHE = {}
+
+
 def load_smpl_model(model_path, alphapose_regressor=REGRESSOR_ALPHAPOSE, mupots_regressor=REGRESSOR_MUPOTS, gender='neutral'):
-    """``model_path``: directory holding ``SMPL_<GENDER>.pkl`` (or the pickle itself) and the regressor ``.npy`` files."""
+    """``model_path``: directory holding ``SMPL_<GENDER>.pkl`` (or the pickle itself) and the regressor ``.npy`` files.
+    The converted arrays are cached per process (keyed by the files' paths, sizes and modification times): a process that fits many
+    sequences -- one optimiser per sequence, ``predict.py:290-306`` -- reads and converts the model once.  Read-only: do not modify."""
     if os.path.isdir(model_path):
         pkl = os.path.join(model_path, 'SMPL_{}.pkl'.format(gender.upper()))
         base = model_path
@@ -32,6 +37,11 @@ def load_smpl_model(model_path, alphapose_regressor=REGRESSOR_ALPHAPOSE, mupots_
         base = os.path.dirname(model_path)
     if not os.path.exists(pkl):
         raise FileNotFoundError('Path {} does not exist!'.format(pkl))
+    ap = alphapose_regressor if os.path.isabs(alphapose_regressor) else os.path.join(base, alphapose_regressor)
+    mp = mupots_regressor if os.path.isabs(mupots_regressor) else os.path.join(base, mupots_regressor)
+    key = tuple((os.path.abspath(f), os.path.getsize(f), os.path.getmtime(f)) for f in (pkl, ap, mp) if os.path.exists(f))
+    if key in _CACHE:
+        return _CACHE[key]
     with open(pkl, 'rb') as f:
         d = pickle.load(f, encoding='latin1')
     posedirs = _dense(d['posedirs'])
@@ -46,9 +56,10 @@ def load_smpl_model(model_path, alphapose_regressor=REGRESSOR_ALPHAPOSE, mupots_
         'lbs_weights': _dense(d['weights']),
         'parents': parents.astype(np.int32),
     }
-    ap = alphapose_regressor if os.path.isabs(alphapose_regressor) else os.path.join(base, alphapose_regressor)
     model['J_regressor_alphapose'] = np.ascontiguousarray(np.load(ap).T.astype(np.float32))
-    mp = mupots_regressor if os.path.isabs(mupots_regressor) else os.path.join(base, mupots_regressor)
     if os.path.exists(mp):
         model['J_regressor_mupots'] = np.ascontiguousarray(np.load(mp).T.astype(np.float32))
+    for v in model.values():
+        v.setflags(write=False)
+    _CACHE[key] = model
     return model
