@@ -220,9 +220,13 @@ int mh_scene_median_pass(mh_ctx* ctx, int32_t which, int32_t pass, void* stream)
  * itself (optimizer.py does so through torch.distributed). */
 /* 128-byte NCCL unique id, produced on ONE rank and handed to every rank's mh_set_comm by the caller */
 int mh_comm_unique_id(mh_ctx* ctx, uint8_t* out128);
-/* collective over the mh_dims.world ranks: the context creates and owns an ncclComm_t.  prev_rank / next_rank: ranks owning the
- * frames before / after this rank's range, -1 at the ends of the sequence */
-int mh_set_comm(mh_ctx* ctx, const uint8_t* unique_id128, int32_t prev_rank, int32_t next_rank);
+/* collective over the mh_dims.world ranks of `ctx` (its rank / world / device are used): creates an ncclComm_t that outlives the
+ * context -- ncclCommInitRank takes seconds on an 8-GPU node, a process creates it once for all the sequences it fits */
+int mh_comm_create(mh_ctx* ctx, const uint8_t* unique_id128, void** handle);
+void mh_comm_destroy(void* handle);
+/* attach a communicator to a context of the same rank / world / device.  prev_rank / next_rank: ranks owning the frames before /
+ * after this rank's range, -1 at the ends of the sequence */
+int mh_set_comm(mh_ctx* ctx, void* handle, int32_t prev_rank, int32_t next_rank);
 int mh_has_comm(mh_ctx* ctx);
 /* one fit() cycle (optimizer.py:375-587) enqueued on `stream`: [halo exchange] -> mh_fit_grads -> [all-reduce of the shared-leaf
  * gradients and losses] -> mh_fit_update(lr).  A context with world > 1 needs mh_set_comm first. */

@@ -68,6 +68,8 @@ def _load():
         'mh_ingest_frames_u8': (c_int32, [ctx, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         'mh_finalize_ingest': (c_int32, [ctx, c_void_p]),
         'mh_comm_unique_id': (c_int32, [ctx, c_void_p]),
+        'mh_comm_create': (c_int32, [ctx, c_void_p, ctypes.POINTER(c_void_p)]),
+        'mh_comm_destroy': (None, [c_void_p]),
         'mh_set_comm': (c_int32, [ctx, c_void_p, c_int32, c_int32]),
         'mh_has_comm': (c_int32, [ctx]),
         'mh_fit_cycle': (c_int32, [ctx, c_float, c_void_p]),

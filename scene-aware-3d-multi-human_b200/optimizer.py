@@ -18,6 +18,7 @@ Differences from the reference that a caller can observe (all documented in DESI
     ``batch_size=`` extension of ``init_optimized_variables`` every rank runs the (cheap) translation init on the WHOLE
     sequence and the frames are sharded when ``fit`` sees the first batch.
 """
+import ctypes
 import math
 import os
 
@@ -31,6 +32,7 @@ from . import sharding
 from . import smpl_io
 
 L = _lib
+_LIB_COMMS = {}              # (process group, rank, world, device) -> handle of mh_comm_create, kept for the life of the process
 
 
 def _device_ordinal(device):
@@ -197,6 +199,13 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
             return False                                                    # ranks emulated inside one process (tests)
         if os.environ.get('MH_LIB_COMM', '1') == '0' or dist.get_backend(self.group) != 'nccl':
             return False
+        # the communicator is created once per process and process group (ncclCommInitRank takes seconds on an 8-GPU node) and
+        # attached to every context this process creates afterwards
+        key = (id(self.group) if self.group is not None else 0, self.rank, self.world, self.device_ordinal)
+        prev, nxt = (-1 if self.prev is None else self.prev), (-1 if self.next is None else self.next)
+        if key in _LIB_COMMS:
+            self.ctx.call('mh_set_comm', _LIB_COMMS[key], prev, nxt)
+            return True
         uid = np.zeros(128, np.uint8)
         ok = 1
         if self.rank == 0:
@@ -212,12 +221,17 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
             return False
         uid = np.frombuffer(raw, np.uint8).copy()
         flag = torch.ones(1, device=self.device)
+        handle = ctypes.c_void_p()
         try:
-            self.ctx.call('mh_set_comm', L.ptr(uid), -1 if self.prev is None else self.prev, -1 if self.next is None else self.next)
+            self.ctx.call('mh_comm_create', L.ptr(uid), ctypes.byref(handle))
         except L.MhError:
             flag.zero_()
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)         # all or nobody
-        return bool(flag.item() > 0)
+        if flag.item() <= 0:
+            return False
+        _LIB_COMMS[key] = handle
+        self.ctx.call('mh_set_comm', handle, prev, nxt)
+        return True
 
     def _view(self, which):
         """torch tensor aliasing a device buffer of the library (for the NCCL plumbing)."""
