@@ -242,6 +242,9 @@ extern "C" int mh_set_model(mh_ctx* c, const mh_model* m) {
             if (w != 0.f) { rvert.push_back(v); rw.push_back(w); }
         }
         rptr[k + 1] = (int)rvert.size();
+        double rs = 0.0;
+        for (int e = rptr[k]; e < rptr[k + 1]; ++e) rs += (double)rw[e];
+        c->r17_slack[k] = (float)(1.0 - rs);
     }
     for (int v = 0; v < V; ++v) {
         for (int k = 0; k < MH_NJR; ++k) {

@@ -58,6 +58,7 @@ struct mh_ctx {
     float* pix_y;              // (H)
     mh_coefs c;
     float w17[MH_NJR];         // pose17j_weights after normalisation (optimizer.py:127-130)
+    float r17_slack[MH_NJR];   // 1 - sum of the regressor row: J17 = R17 . V + T (1 - rowsum) (0 for the shipped regressors)
     // ---- frame data: f32 disparity plane per frame + two 32-bit person bit planes per frame ----
     float* depth;              // (T, H*W)
     uint32_t* cbits;           // (T, H*W)   bit n = seg_mask[t,n] > 0                (optimizer.py:407, 475)

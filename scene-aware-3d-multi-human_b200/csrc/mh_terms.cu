@@ -60,17 +60,17 @@ int mh_terms_gather(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) {
 
 // -------------------------------------------------------------------------------------------------
 // one warp per local person-frame: 2D reprojection term + pose prior
-struct CamParams { float K[9]; float Kd[5]; int has_kd; float w17[MH_NJR]; };
+struct CamParams { float K[9]; float Kd[5]; int has_kd; float w17[MH_NJR]; float slack17[MH_NJR]; };
 
 __global__ void k_body_terms(const float* __restrict__ j17, const float* __restrict__ pose2d, const float* __restrict__ theta,
                              const float* __restrict__ theta_ref, const float* __restrict__ valid, CamParams cam, int T, int N, float W,
                              float H, float thr, float coef_proj, float coef_poses, float* __restrict__ gj17,
-                             float* __restrict__ g_theta, float* __restrict__ lpart, int LP) {
+                             float* __restrict__ g_theta, float* __restrict__ g_trans, float* __restrict__ lpart, int LP) {
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);       // local person-frame
     const int lane = threadIdx.x & 31;
     if (i >= T * N) return;
     const size_t b = (size_t)i + N;                                          // slot-major body
-    float l2d = 0.f;
+    float l2d = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
     if (lane < MH_NJR) {
         const float* P = j17 + (b * MH_NJR + lane) * 3;
         const float* q = pose2d + ((size_t)i * MH_NJR + lane) * 3;
@@ -84,7 +84,12 @@ __global__ void k_body_terms(const float* __restrict__ j17, const float* __restr
         mh_project_bwd(Pv, cam.K, cam.has_kd ? cam.Kd : nullptr, coef_proj * 2.0f * du * m / W, coef_proj * 2.0f * dv * m / H, gP);
         float* g = gj17 + (b * MH_NJR + lane) * 3;
         g[0] = gP[0]; g[1] = gP[1]; g[2] = gP[2];
+        // J17 = R17 . V + T (1 - rowsum): the part of dL/dT that does not pass through the vertices (exactly 0 when the regressor
+        // rows sum to 1, as the shipped AlphaPose / MuPoTS regressors do)
+        s0 = cam.slack17[lane] * gP[0]; s1 = cam.slack17[lane] * gP[1]; s2 = cam.slack17[lane] * gP[2];
     }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0 && (s0 != 0.f || s1 != 0.f || s2 != 0.f)) { g_trans[(size_t)i * 3] += s0; g_trans[(size_t)i * 3 + 1] += s1; g_trans[(size_t)i * 3 + 2] += s2; }
     // pose prior: sum |valid * theta_ref - valid * theta|  (optimizer.py:523-525)
     const float vld = valid[i];
     float lp = 0.f;
@@ -338,6 +343,7 @@ static CamParams cam_of(const mh_ctx* c) {
     memcpy(p.Kd, c->Kd, sizeof(p.Kd));
     p.has_kd = c->has_kd ? 1 : 0;
     memcpy(p.w17, c->w17, sizeof(p.w17));
+    memcpy(p.slack17, c->r17_slack, sizeof(p.slack17));
     return p;
 }
 
@@ -348,7 +354,7 @@ int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) 
     float* g_trans = c->grads + c->off[MH_P_POSES_T];
     k_body_terms<<<mh_cdiv(TN, 4), 128, 0, st>>>(c->j17, c->pose2d, c->params + c->off[MH_P_POSES_SMPL], c->theta_ref, c->valid, cam_of(c),
                                                  d.T, d.N, (float)d.W, (float)d.H, c->c.joint_confidence_thr, c->c.proj2d, c->c.reg_poses,
-                                                 c->gj17, c->grads + c->off[MH_P_POSES_SMPL], c->lpart, c->LP);
+                                                 c->gj17, c->grads + c->off[MH_P_POSES_SMPL], g_trans, c->lpart, c->LP);
     MH_LAUNCHED(c);
     k_dverts_init<<<dim3(8, TN), 256, 0, st>>>(c->verts, c->filtered, c->gj17, c->cptr, c->cjoint, c->cw, d.T, d.N, d.t0, d.T_total,
                                                use_prev, use_next, c->has_filters ? 1 : 0, c->c.reg_verts_filter, c->dverts, c->lpart, c->LP);

@@ -232,6 +232,38 @@ def test_init_stage_with_joint_weights(pkg, L):
     opt.ctx.close()
 
 
+def test_regressor_rows_that_do_not_sum_to_one(pkg, L, tmp_path):
+    """``J17 = R17 . V + T (1 - rowsum)``: with a 17-joint regressor whose rows do NOT sum to 1 (the shipped ones do) part of dL/dT
+    bypasses the vertices.  Teacher-forced cycle vs the CPU oracle (autograd) with the same scaled regressor."""
+    import torch
+    from oracle import fit_ref, synth
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch, num_iter, init_iter = meta
+    reg = np.load(os.path.join(gh.model_dir(), 'SMPL_AlphaPose_Regressor_RMSprop_6.npy'))            # (V, 17) on disk
+    scale = np.linspace(0.8, 1.2, 17).astype(np.float32)
+    path = str(tmp_path / 'scaled_regressor.npy')
+    np.save(path, (reg * scale[None, :]).astype(np.float32))
+    opt = gh.make_optimizer(pkg, g, data, meta, smpl_J_reg_alphapose_path=path)
+    log, grads = gh.teacher_forced_cycle(opt, g, data, meta, 31)
+    model = dict(synth.load_model_tensors(gh.model_dir()))
+    model['J_regressor_alphapose'] = np.ascontiguousarray((reg * scale[None, :]).T.astype(np.float32))
+    fr = fit_ref.FitRef(model, (W, H), T, g['cam_K'], gh.COEFS)
+    c = 31
+    fr.set_variables(g[f'c{c}_p_poses_T'], g[f'c{c}_p_poses_smpl'], g[f'c{c}_p_betas'], data['valid_smpl'],
+                     g[f'c{c}_p_zmin_lin'], g[f'c{c}_p_zmax_lin'], g[f'c{c}_p_xscale'])
+    fr.betas_ref = torch.from_numpy(g['init_betas'])
+    fr.set_scene_pcd(g[f'c{c}_scene_pcd'])
+    batches = [np.arange(s, min(s + batch, T)) for s in range(0, T, batch)]
+    olog, _ = fr.cycle_grads(data, batches)
+    ograds = {nm: p.grad.numpy().copy() for nm, p in zip(gh.NAMES, fr.leaves())}
+    assert abs(log['loss_pose24j'] - olog['loss_pose24j']) <= 1e-4 * abs(olog['loss_pose24j'])
+    assert olog['loss_pose24j'] > 10 * float(g[f'c{c}_log_loss_pose24j'])            # the scaled joints are far from the 2-D poses: the term dominates
+    for nm in ('poses_T', 'poses_smpl', 'betas', 'xscale'):
+        ref = ograds[nm].reshape(grads[nm].shape)
+        assert np.abs(grads[nm] - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, (nm, np.abs(grads[nm] - ref).max(), np.abs(ref).max())
+    opt.ctx.close()
+
+
 def test_optimizer_updates_match_torch(c1, L):
     """Fused RMSprop / Adam steps vs torch.optim with identical gradients."""
     import torch

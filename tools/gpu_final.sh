@@ -13,8 +13,9 @@ timeout 600 python bench.py --workload c2 --no-cpu-baseline > gpurun_out/${TAG}_
 CFG="c3 c2"
 if [ -n "$ALL" ]; then
   timeout 900 python bench.py --workload c4 --steps 10 --no-cpu-baseline > gpurun_out/${TAG}_bench_c4_1gpu.json 2> /dev/null
+  timeout 900 python bench.py --workload c5 --steps 10 --no-cpu-baseline > gpurun_out/${TAG}_bench_c5_1gpu.json 2> /dev/null
   timeout 600 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2> /dev/null
-  CFG="c3 c2 c4"
+  CFG="c3 c2 c4 c5"
 fi
 for f in $CFG; do python -c "
 import json

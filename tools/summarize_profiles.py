@@ -26,8 +26,15 @@ for r in rd:
         rows.append((r[ki].split('(')[0], v))
 # the timed region = the last 2 cycles: from the second-to-last k_gather onwards
 gidx = [i for i, (k, _) in enumerate(rows) if 'k_gather' in k]
-start = gidx[-2] if len(gidx) >= 2 else 0
-cyc = rows[start:]
+ridx = [i for i, (k, _) in enumerate(rows) if 'k_render<0>' in k or 'k_renderILi0' in k]
+if len(ridx) >= 2:
+    # the last two fit cycles: from the k_gather before the second-to-last render launch to the RMSprop step after the last one
+    # (bench.py times hot loop A afterwards: its launches are not part of the cycle)
+    start = max(i for i in gidx if i < ridx[-2])
+    end = next(i for i in range(ridx[-1], len(rows)) if 'k_rmsprop' in rows[i][0]) + 1
+else:
+    start, end = (gidx[-2] if len(gidx) >= 2 else 0), len(rows)
+cyc = rows[start:end]
 tot = collections.OrderedDict()
 for k, v in cyc:
     tot[k] = tot.get(k, 0.0) + v
