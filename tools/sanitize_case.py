@@ -19,4 +19,11 @@ d, m = opt._device_median(0)
 opt.update_scene_pointcloud(np.where(m, d, 5.0).astype(np.float32), np.ones((H, W), bool))
 opt.ctx.call('mh_fit_grads', 0, 0, opt._stream())
 opt.ctx.call('mh_fit_update', 0.01, opt._stream())
+# round 2: the device scene update (median -> post-processing -> cloud), the fused cycle call and the u8 ingest entry
+opt._median_passes(0)
+opt.ctx.call('mh_scene_update_from_median', 1, 7, None, opt._stream())
+opt.ctx.call('mh_fit_cycle', 0.01, opt._stream())
+d8 = dict(data); d8['seg_mask'] = data['seg_mask'].astype(np.uint8)
+opt._ingest(gh.ListLoader(d8, meta[4]))
+opt.ctx.call('mh_fit_cycle', 0.01, opt._stream())
 print('ok', {k: round(v, 5) for k, v in log.items()}, opt.ctx.read_losses(opt._stream())[:3])
