@@ -268,6 +268,11 @@ int mh_render_profile(mh_ctx* ctx, int32_t on, long long* out32_host);
 /* testing aid: REDUCE the render capacities (0 keeps a value) so that small inputs reach the coarse-binning path (maxbins)
  * and the MH_E_CAPACITY paths (tile-list entries per body, depth-winner entries per body); clears the capacity flag */
 int mh_debug_set_render_caps(mh_ctx* ctx, int32_t maxbins, int32_t bincap, int32_t wcap);
+/* contact term (optimizer.py:492-500): the 32 nearest scene points of every lowest vertex are searched on a uniform grid over the cloud
+ * (rebuilt by mh_set_scene / mh_set_scene_from_depth), exactly, with the streaming search over the whole cloud as the fallback.
+ * out[0] = person-frames the grid answered in the last cycle, out[1] = grid cells, out[2] = points, out[3] = cell size (micrometres).
+ * The environment variable MH_KNN_GRID=0 (read when the cloud is set) disables the grid. */
+int mh_debug_knn_stats(mh_ctx* ctx, int64_t* out4, void* stream);
 /* testing aid: the pose-corrective contraction alone, C (M, 20672) = A (M, 192) . posedirs, HOST pointers, blocking; use_tc = 1 runs
  * the tcgen05 / TMEM kernel (3 x TF32), 0 the FP32 SIMT kernel (smpl.py:549-553 without the shape term) */
 int mh_debug_gemm_fwd(mh_ctx* ctx, const float* A_host, float* C_host, int32_t M, int32_t use_tc);

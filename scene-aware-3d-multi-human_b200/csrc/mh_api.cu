@@ -67,6 +67,7 @@ extern "C" int mh_create(mh_ctx** out, const mh_dims* dims) {
     c->rs = nullptr;
     c->scene_state = nullptr;
     c->scene_post = nullptr;
+    c->knn = nullptr;
     c->comm = nullptr;
     c->M = 0;
     c->events = nullptr; c->timing = false; c->timing_iter = 0;
@@ -164,6 +165,7 @@ extern "C" void mh_destroy(mh_ctx* c) {
     mh_render_free(c);
     mh_scene_free(c);
     mh_scenepost_free(c);
+    mh_knn_free(c);
     mh_comm_free(c);
     if (c->events) { for (int i = 0; i < MH_TIMING_RING * MH_TIMING_EVENTS; ++i) cudaEventDestroy(c->events[i]); delete[] c->events; }
     for (void* p : c->allocs) cudaFree(p);
@@ -454,7 +456,7 @@ extern "C" int mh_set_scene(mh_ctx* c, const float* pcd, int64_t M, void* stream
         MH_CUDA(c, cudaMemcpyAsync(c->scene, pcd, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     }
     c->M = M;
-    return MH_OK;
+    return mh_knn_build(c, (cudaStream_t)stream);
 }
 
 extern "C" int mh_set_scene_from_depth(mh_ctx* c, const float* depth_host, const uint8_t* mask_host, void* stream) {

@@ -120,6 +120,7 @@ struct mh_ctx {
     MhRenderScratch* rs;
     void* scene_state;         // mh_scene.cu
     void* scene_post;          // mh_scenepost.cu
+    void* knn;                 // mh_terms.cu: uniform grid over the scene cloud for the contact term
     void* comm;                // mh_comm.cu: the NCCL communicator this context owns (mh_set_comm), or null
     // stage timing (bench)
     cudaEvent_t* events; bool timing; int64_t timing_iter;
@@ -164,6 +165,8 @@ int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st);
 int mh_terms_gather(mh_ctx* c, int use_prev, int use_next, cudaStream_t st);
 int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st);
 int mh_terms_post(mh_ctx* c, cudaStream_t st);
+int mh_knn_build(mh_ctx* c, cudaStream_t st);       // (re)build the contact-term grid for the current scene cloud
+void mh_knn_free(mh_ctx* c);
 int mh_loss_begin(mh_ctx* c, cudaStream_t st);      // zero the loss partials of the cycle
 int mh_loss_reduce(mh_ctx* c, cudaStream_t st);     // losses[slot] += fixed-order sum of the slot's partials
 int mh_init_iter_grads(mh_ctx* c, int use_prev, int use_next, cudaStream_t st);

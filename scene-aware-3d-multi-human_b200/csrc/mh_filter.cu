@@ -165,5 +165,5 @@ int mh_scene_from_depth(mh_ctx* c, const float* depth_dev, const uint8_t* mask_d
     MH_CUDA(c, e);
     if (total > 0 && total < MH_KNN) MH_FAIL(c, MH_E_ARG, "scene cloud has only %d points (< %d)", total, MH_KNN);
     c->M = total;
-    return MH_OK;
+    return mh_knn_build(c, st);
 }

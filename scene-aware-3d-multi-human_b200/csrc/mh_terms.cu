@@ -188,7 +188,12 @@ template <int KNN_Q>
 __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict__ verts, const int* __restrict__ lowidx,
                                                          const float* __restrict__ scene, int64_t M, int N, int TN, float coef,
                                                          float* __restrict__ contact, float* __restrict__ g_trans,
-                                                         float* __restrict__ lpart, int LP) {
+                                                         float* __restrict__ lpart, int LP, const uint8_t* __restrict__ resolved) {
+    if (resolved) {               // the grid search (k_contact_grid) answered these person-frames already: nothing to stream
+        bool all = true;
+        for (int q = 0; q < KNN_Q; ++q) { const int i = blockIdx.x * KNN_Q + q; all = all && (i >= TN || resolved[i]); }
+        if (all) return;
+    }
     __shared__ float smin[KNN_Q][KNN_THREADS];
     __shared__ float cd[KNN_Q][KNN_CAP];
     __shared__ int ci[KNN_Q][KNN_CAP];
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict
         }
     }
     __syncthreads();
-    if (tid < nq) {
+    if (tid < nq && !(resolved && resolved[i0 + tid])) {
         const int q = tid, i = i0 + q;
         float my = 0.f;
         for (int r = 0; r < MH_KNN; ++r) my += scene[3 * (size_t)sel[q][r] + 1];
@@ -283,6 +288,282 @@ __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict
         contact[(size_t)i * 4] = cdv;
         contact[(size_t)i * 4 + 1] = cdv > -0.20f ? 1.0f : 0.0f;   // in_thr_contact_region (:509-510)
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Uniform grid over the scene cloud for the contact term: the 32 nearest points of ONE query point lie in a few cells around it, so a
+// warp per person-frame visits the cells shell by shell (Chebyshev distance r = 0, 1, 2, ...) and stops when the 32nd best distance
+// is below (r h)^2 -- every unvisited point is at least r h away.  Exact: same distance arithmetic (d2_point) and the same
+// (distance, index) order as the streaming kernel, which stays as the fallback for queries the grid cannot answer in KG_RMAX shells
+// (a person far away from every scene point).  KG_LEVELS grids with cell sizes h, 4h, 16h: a person-frame the fine grid cannot answer
+// (a jump: the lowest vertex more than 6 h above the floor) is searched again on the next coarser one.  The grids are rebuilt with
+// the cloud (mh_set_scene / mh_set_scene_from_depth).
+#define KG_MAXCELLS (1 << 21)
+#define KG_RMAX 6
+#define KG_LEVELS 3
+#define KG_BUDGET 65536   // points one warp may visit on one level before it gives the person-frame up to the next level / the streaming kernel
+struct MhKnnLevel {
+    float* bbox;        // [6] min xyz, max xyz, then [h, 1/h], dims as ints at +8
+    int* cell_start;    // KG_MAXCELLS + 1 (counts, then exclusive offsets), + block sums
+    float4* gpts;       // (M_max) points sorted by cell: x, y, z, index
+};
+struct MhKnnGrid {
+    MhKnnLevel lev[KG_LEVELS];
+    int* cursor;        // KG_MAXCELLS (build scratch)
+    int* pcell;         // (M_max) cell of every point (build scratch)
+    float* part;        // bbox partials
+    uint8_t* resolved;  // (TN)
+    int64_t M_built;    // points the grids were built for (0: no grid)
+};
+
+__global__ void __launch_bounds__(256) k_kg_bbox(const float* __restrict__ pts, int64_t M, float* __restrict__ part) {
+    __shared__ float s[6][256];
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < M; i += (int64_t)gridDim.x * 256)
+        for (int k = 0; k < 3; ++k) { const float v = pts[3 * i + k]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
+    for (int k = 0; k < 3; ++k) { s[k][threadIdx.x] = mn[k]; s[3 + k][threadIdx.x] = mx[k]; }
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int k = 0; k < 3; ++k) {
+                s[k][threadIdx.x] = fminf(s[k][threadIdx.x], s[k][threadIdx.x + o]);
+                s[3 + k][threadIdx.x] = fmaxf(s[3 + k][threadIdx.x], s[3 + k][threadIdx.x + o]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) part[blockIdx.x * 6 + threadIdx.x] = s[threadIdx.x][0];
+}
+
+// bbox -> cell size (about 48 points per occupied cell of a 2-D surface cloud, at most KG_MAXCELLS cells) and grid dimensions
+__global__ void k_kg_setup(const float* __restrict__ part, int nblk, int64_t M, float* __restrict__ bbox, float scale) {
+    if (threadIdx.x != 0) return;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int b = 0; b < nblk; ++b)
+        for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], part[b * 6 + k]); mx[k] = fmaxf(mx[k], part[b * 6 + 3 + k]); }
+    const float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+    const float area = fmaxf(ex * ey + ey * ez + ex * ez, 1e-6f);
+    float h = fminf(fmaxf(sqrtf(area * 48.0f / (float)M), 0.02f), 1.0f) * scale;
+    int dx, dy, dz;
+    for (;;) {
+        dx = (int)(ex / h) + 1; dy = (int)(ey / h) + 1; dz = (int)(ez / h) + 1;
+        if ((double)dx * dy * dz <= (double)KG_MAXCELLS && dx <= 1024 && dy <= 1024 && dz <= 1024) break;
+        h *= 1.26f;
+    }
+    for (int k = 0; k < 3; ++k) { bbox[k] = mn[k]; bbox[3 + k] = mx[k]; }
+    bbox[6] = h; bbox[7] = 1.0f / h;
+    int* dims = reinterpret_cast<int*>(bbox + 8);
+    dims[0] = dx; dims[1] = dy; dims[2] = dz; dims[3] = dx * dy * dz;
+}
+
+__device__ __forceinline__ int kg_coord(float v, float lo, float ih, int n) { return min(max((int)((v - lo) * ih), 0), n - 1); }
+
+__global__ void k_kg_count(const float* __restrict__ pts, int64_t M, const float* __restrict__ bbox, int* __restrict__ pcell, int* __restrict__ count) {
+    const int* dims = reinterpret_cast<const int*>(bbox + 8);
+    const float ih = bbox[7];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cx = kg_coord(pts[3 * i], bbox[0], ih, dims[0]), cy = kg_coord(pts[3 * i + 1], bbox[1], ih, dims[1]),
+                  cz = kg_coord(pts[3 * i + 2], bbox[2], ih, dims[2]);
+        const int c = (cz * dims[1] + cy) * dims[0] + cx;
+        pcell[i] = c;
+        atomicAdd(&count[c], 1);
+    }
+}
+
+// exclusive scan of count[0 .. ncell] in three steps (1024 cells per block)
+__global__ void __launch_bounds__(1024) k_kg_scan1(int* __restrict__ a, const float* __restrict__ bbox, int* __restrict__ bsum) {
+    __shared__ int s[1024];
+    const int ncell = reinterpret_cast<const int*>(bbox + 8)[3];
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    const int v = (i < ncell) ? a[i] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int t = (threadIdx.x >= o) ? s[threadIdx.x - o] : 0;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (i <= ncell) a[i] = s[threadIdx.x] - v;                  // exclusive inside the block (a[ncell] gets the block-local total so far)
+    if (threadIdx.x == 1023) bsum[blockIdx.x] = s[1023];
+}
+__global__ void k_kg_scan2(int* __restrict__ bsum, int nblk) {
+    if (threadIdx.x != 0) return;
+    int run = 0;
+    for (int b = 0; b < nblk; ++b) { const int v = bsum[b]; bsum[b] = run; run += v; }
+}
+__global__ void __launch_bounds__(1024) k_kg_scan3(int* __restrict__ a, const float* __restrict__ bbox, const int* __restrict__ bsum, int* __restrict__ cursor) {
+    const int ncell = reinterpret_cast<const int*>(bbox + 8)[3];
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    if (i <= ncell) { const int v = a[i] + bsum[blockIdx.x]; a[i] = v; if (i < ncell) cursor[i] = v; }
+}
+
+__global__ void k_kg_scatter(const float* __restrict__ pts, int64_t M, const int* __restrict__ pcell, int* __restrict__ cursor, float4* __restrict__ gpts) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        const int pos = atomicAdd(&cursor[pcell[i]], 1);
+        gpts[pos] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float((int)i));
+    }
+}
+
+// one WARP per local person-frame: lane l holds the (l+1)-th best (distance, index) key found so far
+__global__ void __launch_bounds__(128) k_contact_grid(const float* __restrict__ verts, const int* __restrict__ lowidx, const float* __restrict__ scene,
+                                                      const float4* __restrict__ gpts, const int* __restrict__ cell_start, const float* __restrict__ bbox,
+                                                      int N, int TN, float coef, float* __restrict__ contact, float* __restrict__ g_trans,
+                                                      float* __restrict__ lpart, int LP, uint8_t* __restrict__ resolved, int first) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= TN) return;
+    if (!first && resolved[i]) return;                             // a finer grid answered it
+    const int lane = threadIdx.x & 31;
+    const size_t b = (size_t)i + N;
+    const int li = lowidx[b];
+    const float qx = verts[b * MH_LD3V + 3 * li], qy = verts[b * MH_LD3V + 3 * li + 1], qz = verts[b * MH_LD3V + 3 * li + 2];
+    const int* dims = reinterpret_cast<const int*>(bbox + 8);
+    const int DX = dims[0], DY = dims[1], DZ = dims[2];
+    const float h = bbox[6], ih = bbox[7];
+    const int cx = kg_coord(qx, bbox[0], ih, DX), cy = kg_coord(qy, bbox[1], ih, DY), cz = kg_coord(qz, bbox[2], ih, DZ);
+    unsigned long long best = 0xffffffffffffffffull;              // lane l: (l+1)-th smallest key, ascending over the lanes
+    bool done = false;
+    int visited = 0;
+    for (int r = 0; r <= KG_RMAX && !done && visited <= KG_BUDGET; ++r) {
+        for (int z = cz - r; z <= cz + r; ++z) {
+            if (z < 0 || z >= DZ) continue;
+            for (int y = cy - r; y <= cy + r; ++y) {
+                if (y < 0 || y >= DY) continue;
+                const bool face = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
+                // on the faces of the shell every x in [cx - r, cx + r] belongs to it, elsewhere only the two ends
+                const int xstep = (face || r == 0) ? 1 : 2 * r;
+                for (int x = cx - r; x <= cx + r; x += xstep) {
+                    if (x < 0 || x >= DX) continue;
+                    const int c = (z * DY + y) * DX + x;
+                    const int p0 = cell_start[c], p1 = cell_start[c + 1];
+                    visited += p1 - p0;
+                    for (int p = p0 + lane; p - lane < p1; p += 32) {
+                        unsigned long long cand = 0xffffffffffffffffull;
+                        if (p < p1) {
+                            const float4 g = gpts[p];
+                            cand = ((unsigned long long)__float_as_uint(d2_point(g.x, g.y, g.z, qx, qy, qz)) << 32) | (unsigned)__float_as_int(g.w);
+                        }
+                        // insert, lowest lane first, every candidate that beats the current 32nd best
+                        unsigned long long worst = __shfl_sync(0xffffffffu, best, 31);
+                        unsigned todo = __ballot_sync(0xffffffffu, cand < worst);
+                        while (todo) {
+                            const int src = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const unsigned long long v = __shfl_sync(0xffffffffu, cand, src);
+                            if (v < worst) {
+                                const int pos = __popc(__ballot_sync(0xffffffffu, best < v));       // sorted position of v
+                                const unsigned long long up = __shfl_up_sync(0xffffffffu, best, 1);
+                                if (lane == pos) best = v; else if (lane > pos) best = up;
+                                worst = __shfl_sync(0xffffffffu, best, 31);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // every point not visited yet is at least r h away from the query
+        // (the cell of a point is computed in float: 1e-3 cells of slack cover the rounding of (v - lo) / h)
+        const float rb = fmaxf((float)r - 1e-3f, 0.f) * h;
+        const unsigned long long worst = __shfl_sync(0xffffffffu, best, 31);
+        done = (worst != 0xffffffffffffffffull) && (__uint_as_float((unsigned)(worst >> 32)) < rb * rb);
+    }
+    if (lane == 0) resolved[i] = done ? 1 : 0;
+    if (!done) return;                                             // the streaming kernel answers this one
+    // mean height of the 32 neighbours, summed in rank order as the streaming kernel does (bit-identical result)
+    float my = 0.f;
+    const float yk = scene[3 * (size_t)(unsigned)(best & 0xffffffffull) + 1];
+    for (int k = 0; k < MH_KNN; ++k) my += __shfl_sync(0xffffffffu, yk, k);
+    if (lane == 0) {
+        my *= (1.0f / MH_KNN);
+        const float cdv = my - qy;                              // contact_dist_vertical (:501)
+        const float r = cdv + 0.02f;                            // target.y = T.y + cdv + 0.02 (:502-503)
+        lpart[(size_t)MH_L_CONTACT * LP + i] = fabsf(r);
+        g_trans[(size_t)i * 3 + 1] += coef * -signf(r);         // d|T - target|/dT.y with the target detached (:504-506)
+        contact[(size_t)i * 4] = cdv;
+        contact[(size_t)i * 4 + 1] = cdv > -0.20f ? 1.0f : 0.0f;   // in_thr_contact_region (:509-510)
+    }
+}
+
+static MhKnnGrid* knn_grid(mh_ctx* c) { return reinterpret_cast<MhKnnGrid*>(c->knn); }
+
+void mh_knn_free(mh_ctx* c) {
+    MhKnnGrid* g = knn_grid(c);
+    if (!g) return;
+    for (int l = 0; l < KG_LEVELS; ++l) { cudaFree(g->lev[l].bbox); cudaFree(g->lev[l].cell_start); cudaFree(g->lev[l].gpts); }
+    cudaFree(g->cursor); cudaFree(g->pcell); cudaFree(g->part); cudaFree(g->resolved);
+    delete g;
+    c->knn = nullptr;
+}
+
+// testing aid: out[0] = person-frames the grid search answered in the last cycle, out[1] = cells, out[2] = points the grid holds,
+// out[3] = cell size in micrometres (all 0 without a grid)
+extern "C" int mh_debug_knn_stats(mh_ctx* c, int64_t* out, void* stream) {
+    if (!c || !out) return MH_E_ARG;
+    cudaSetDevice(c->d.device);
+    out[0] = out[1] = out[2] = out[3] = 0;
+    MhKnnGrid* g = knn_grid(c);
+    if (!g || g->M_built != c->M || c->M == 0) return MH_OK;
+    const int TN = c->d.T * c->d.N;
+    std::vector<uint8_t> r(TN);
+    float bb[12];
+    MH_CUDA(c, cudaMemcpyAsync(r.data(), g->resolved, TN, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MH_CUDA(c, cudaMemcpyAsync(bb, g->lev[0].bbox, sizeof(bb), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MH_CUDA(c, cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < TN; ++i) out[0] += r[i];
+    out[1] = reinterpret_cast<const int*>(bb + 8)[3];
+    out[2] = g->M_built;
+    out[3] = (int64_t)(bb[6] * 1e6f);
+    return MH_OK;
+}
+
+// (re)build the grid for the current cloud c->scene[0 .. c->M); MH_KNN_GRID=0 keeps the streaming kernel alone
+int mh_knn_build(mh_ctx* c, cudaStream_t st) {
+    const char* env = getenv("MH_KNN_GRID");
+    const int use_grid = env ? atoi(env) : 1;
+    MhKnnGrid* g = knn_grid(c);
+    if (!use_grid || c->M < MH_KNN) { if (g) g->M_built = 0; return MH_OK; }
+    const mh_dims& d = c->d;
+    if (!g) {
+        g = new MhKnnGrid();
+        memset(g, 0, sizeof(*g));
+        const int64_t Mmax = std::max<int64_t>(d.M_max, 1);
+        cudaError_t e = cudaMalloc((void**)&g->cursor, sizeof(int) * KG_MAXCELLS);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&g->pcell, sizeof(int) * Mmax);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&g->part, sizeof(float) * 6 * 256);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&g->resolved, (size_t)d.T * d.N);
+        for (int l = 0; l < KG_LEVELS && e == cudaSuccess; ++l) {
+            e = cudaMalloc((void**)&g->lev[l].bbox, sizeof(float) * 16);
+            if (e == cudaSuccess) e = cudaMalloc((void**)&g->lev[l].cell_start, sizeof(int) * (KG_MAXCELLS + 1 + 4096));
+            if (e == cudaSuccess) e = cudaMalloc((void**)&g->lev[l].gpts, sizeof(float4) * Mmax);
+        }
+        c->knn = g;
+        if (e != cudaSuccess) { mh_knn_free(c); MH_FAIL(c, MH_E_CUDA, "contact grid: %s", cudaGetErrorString(e)); }
+    }
+    const int64_t M = c->M;
+    const int nb = (int)std::min<int64_t>(256, (M + 255) / 256);
+    const int gp = (int)std::min<int64_t>(2048, (M + 255) / 256);
+    const int nsb = KG_MAXCELLS / 1024 + 1;                        // covers index ncell <= KG_MAXCELLS
+    k_kg_bbox<<<nb, 256, 0, st>>>(c->scene, M, g->part);
+    MH_LAUNCHED(c);
+    float scale = 1.0f;
+    for (int l = 0; l < KG_LEVELS; ++l, scale *= 4.0f) {
+        MhKnnLevel& v = g->lev[l];
+        int* bsum = v.cell_start + KG_MAXCELLS + 1;
+        k_kg_setup<<<1, 32, 0, st>>>(g->part, nb, M, v.bbox, scale);
+        MH_LAUNCHED(c);
+        MH_CUDA(c, cudaMemsetAsync(v.cell_start, 0, sizeof(int) * (KG_MAXCELLS + 1), st));
+        k_kg_count<<<gp, 256, 0, st>>>(c->scene, M, v.bbox, g->pcell, v.cell_start);
+        MH_LAUNCHED(c);
+        k_kg_scan1<<<nsb, 1024, 0, st>>>(v.cell_start, v.bbox, bsum);
+        MH_LAUNCHED(c);
+        k_kg_scan2<<<1, 32, 0, st>>>(bsum, nsb);
+        MH_LAUNCHED(c);
+        k_kg_scan3<<<nsb, 1024, 0, st>>>(v.cell_start, v.bbox, bsum, g->cursor);
+        MH_LAUNCHED(c);
+        k_kg_scatter<<<gp, 256, 0, st>>>(c->scene, M, g->pcell, g->cursor, v.gpts);
+        MH_LAUNCHED(c);
+    }
+    g->M_built = M;
+    return MH_OK;
 }
 
 // foot sliding (optimizer.py:512-518): one CTA per local batch segment; pairs are ADJACENT ENTRIES OF ONE BATCH.  Gather form: the
@@ -368,7 +649,18 @@ int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st) 
         const int w2 = 2 * c->num_sms;
         int Q = TN >= 8 * w2 ? 8 : TN >= 4 * w2 ? 4 : TN >= 2 * w2 ? 2 : 1;
         if (const char* v = getenv("MH_KNN_Q")) { const int q = atoi(v); if (q == 1 || q == 2 || q == 4 || q == 8) Q = q; }
-#define MH_CONTACT(QQ) k_contact<QQ><<<mh_cdiv(TN, QQ), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, c->lpart, c->LP)
+        // grid search first (a warp per person-frame); the streaming kernel then only runs for the person-frames it could not answer
+        MhKnnGrid* kg = knn_grid(c);
+        const uint8_t* resolved = nullptr;
+        if (kg && kg->M_built == c->M) {
+            for (int l = 0; l < KG_LEVELS; ++l) {
+                k_contact_grid<<<mh_cdiv(TN, 4), 128, 0, st>>>(c->verts, c->lowidx, c->scene, kg->lev[l].gpts, kg->lev[l].cell_start, kg->lev[l].bbox, d.N, TN,
+                                                               c->c.reg_contact, c->contact, g_trans, c->lpart, c->LP, kg->resolved, l == 0);
+                MH_LAUNCHED(c);
+            }
+            resolved = kg->resolved;
+        }
+#define MH_CONTACT(QQ) k_contact<QQ><<<mh_cdiv(TN, QQ), KNN_THREADS, 0, st>>>(c->verts, c->lowidx, c->scene, c->M, d.N, TN, c->c.reg_contact, c->contact, g_trans, c->lpart, c->LP, resolved)
         if (Q == 8) MH_CONTACT(8); else if (Q == 4) MH_CONTACT(4); else if (Q == 2) MH_CONTACT(2); else MH_CONTACT(1);
 #undef MH_CONTACT
         MH_LAUNCHED(c);

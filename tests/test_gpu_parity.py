@@ -385,6 +385,59 @@ def test_contact_knn_one_million_points_with_ties(pkg, L):
     opt.ctx.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('kind', ['floor', 'deep', 'far', 'sparse', 'thin'])
+def test_contact_grid_equals_streaming_search(pkg, L, kind, monkeypatch):
+    """The uniform-grid search of the contact term (a warp per person-frame, shells of cells around the lowest vertex) against the
+    streaming search over the whole cloud: same 32 neighbours in the same (distance, index) order, so the loss and every gradient are
+    BITWISE equal.  'deep': the floor 1.5 m below the feet, out of reach of the fine grid (answered by a coarser level); 'far': no scene
+    point within the shells any level visits (every person-frame falls back to the streaming kernel);
+    'sparse': 40 points in all; 'thin': all points on one line (a degenerate bounding box)."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch = meta[:5]
+    opt = gh.make_optimizer(pkg, g, data, meta, coefs=dict(gh.COEFS, depth=0.0, silhouette=0.0), max_scene_points=300000)
+    gh.prepare(opt, g, data, meta)
+    rng = np.random.default_rng(5)
+    if kind == 'floor':
+        M = 300000
+        cloud = np.stack([rng.uniform(-4, 4, M), 1.0 + 0.02 * rng.standard_normal(M), rng.uniform(1, 9, M)], -1)
+        cloud[5000:5100] = cloud[5000]
+    elif kind == 'deep':
+        M = 300000
+        cloud = np.stack([rng.uniform(-4, 4, M), 2.5 + 0.02 * rng.standard_normal(M), rng.uniform(1, 9, M)], -1)
+    elif kind == 'far':
+        M = 100000
+        cloud = np.stack([rng.uniform(40, 44, M), rng.uniform(0.8, 1.2, M), rng.uniform(60, 64, M)], -1)
+    elif kind == 'sparse':
+        cloud = np.stack([rng.uniform(-2, 2, 40), rng.uniform(0.5, 1.5, 40), rng.uniform(2, 6, 40)], -1)
+    else:
+        M = 20000
+        cloud = np.stack([np.zeros(M), np.ones(M), rng.uniform(1, 9, M)], -1)
+    cloud = cloud.astype(np.float32)
+    ctx, st = opt.ctx, opt._stream()
+    c = 31
+    for which, key in ((L.P_POSES_T, 'poses_T'), (L.P_POSES_SMPL, 'poses_smpl'), (L.P_BETAS, 'betas'), (L.P_XSCALE, 'xscale')):
+        ctx.set_param(which, g[f'c{c}_p_{key}'], st)
+    ctx.set_param(L.P_ZMIN_LIN, g[f'c{c}_p_zmin_lin'], st); ctx.set_param(L.P_ZMAX_LIN, g[f'c{c}_p_zmax_lin'], st)
+    out = {}
+    for grid in ('1', '0'):
+        monkeypatch.setenv('MH_KNN_GRID', grid)
+        opt.set_scene_pcd(cloud)                                                   # (re)builds the grid, or drops it
+        ctx.call('mh_fit_grads', 0, 0, st)
+        out[grid] = (ctx.read_losses(st).copy(), opt._view(L.BUF_GRADS).cpu().numpy().copy())
+        stats = np.zeros(4, np.int64)
+        ctx.call('mh_debug_knn_stats', L.ptr(stats), st)
+        if grid == '0':
+            assert stats[2] == 0                                                   # no grid: the streaming kernel alone
+        else:
+            assert stats[2] == len(cloud) and stats[1] >= 1
+            assert stats[0] == (0 if kind == 'far' else T * N), stats              # who answered
+    assert np.isfinite(out['1'][0]).all() and out['1'][0][L.L_CONTACT] > 0
+    assert np.array_equal(out['1'][0].view(np.uint32), out['0'][0].view(np.uint32))
+    assert np.array_equal(out['1'][1].view(np.uint32), out['0'][1].view(np.uint32))
+    opt.ctx.close()
+
+
 def _two_shard_cycle(pkg, L, g, data, meta, cycle, refresh=False):
     """World-size-2 frame sharding emulated on ONE GPU: two contexts (rank 0 / 1), halo frames and the shared gradient block
     exchanged through the host exactly as sharding.exchange_halo / allreduce_shared do over NCCL.  ``refresh``: the filtered
