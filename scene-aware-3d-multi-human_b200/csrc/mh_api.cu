@@ -339,6 +339,20 @@ extern "C" int mh_ingest_frames_u8(mh_ctx* c, int32_t t0, int32_t count, const f
 
 // float32 {0., 1.} masks (count, N, HW) -> one 32-bit plane per frame on the HOST, all cores: the reference dataset delivers 4 N bytes
 // per pixel and frame (utils.py:329-331); packed, 4 bytes cross the bus instead.  Returns true when a value other than 0 / 1 was seen.
+// one person's row of a chunk: the widest vector unit of the host is picked at load time (function multi-versioning)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx512f", "avx2", "default")))
+#endif
+static int mh_pack_row(const float* s, uint32_t* o, int64_t n, uint32_t bit) {
+    int bad = 0;
+    for (int64_t p = 0; p < n; ++p) {
+        const float v = s[p];
+        o[p] |= (v != 0.f) ? bit : 0u;
+        bad |= (v != 0.f) & (v != 1.0f);
+    }
+    return bad;
+}
+
 static bool pack_masks_host(const float* seg, int count, int N, int64_t HW, uint32_t* out) {
     const int64_t total = (int64_t)count * HW;
     const int nthr = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
@@ -357,13 +371,7 @@ static bool pack_masks_host(const float* seg, int count, int N, int64_t HW, uint
                 uint32_t* o = out + i;
                 for (int64_t p = 0; p < n_here; ++p) o[p] = 0u;
                 for (int n = 0; n < N; ++n) {
-                    const float* s = seg + ((int64_t)t * N + n) * HW + p0;
-                    const uint32_t bit = 1u << n;
-                    for (int64_t p = 0; p < n_here; ++p) {
-                        const float v = s[p];
-                        o[p] |= (v != 0.f) ? bit : 0u;
-                        mybad |= (v != 0.f) & (v != 1.0f);
-                    }
+                    mybad |= mh_pack_row(seg + ((int64_t)t * N + n) * HW + p0, o, n_here, 1u << n);
                 }
                 i += n_here;
             }

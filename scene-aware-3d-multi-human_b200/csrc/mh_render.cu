@@ -39,9 +39,9 @@
 #define KEY_EMPTY 0xffffffffffffffffull
 #define R_DESC 1024               // (face, tile) descriptors staged per chunk (5 float4 each)
 #define R_QUEUE 64                // survivor queue entries per warp (fewer than 32 wait, a pass adds at most 32)
-#ifndef MH_R_ROWPASS
-#define MH_R_ROWPASS 1            // 1: a prune pass covers whole rows of the face's rectangle (lane -> (row, column) fixed per face, the pixel
-#endif                            //    index advances by a constant) ; 0: 32 consecutive pixels of the rectangle in row-major order
+#ifndef MH_R_GRAB
+#define MH_R_GRAB 1               // faces a warp takes from the tile's list per hand-out (one shared-memory atomic); measured 1 < 2 < 3 < 4 (balance at the tile barrier)
+#endif
 
 struct MhRenderScratch {
     uint16_t* binlist; int bincap;
@@ -263,11 +263,11 @@ __device__ __forceinline__ void grad_add(long long* p, float v) {
 
 // Descriptor of one (face, tile) item -- everything P2 needs, computed ONCE by one thread (the tile's faces are spread over
 // the 1024 threads) instead of redundantly by the 32 lanes of the warp that rasterises the face:
-//   d0 = x0 y0 x1 y1 | d1 = x2 y2 z0 z1 | d2 = z2 1/den 1/|e01|^2 1/|e02|^2 | d3 = rect inner zbits magic | d4 = 1/|e12|^2 face i0|i1<<16 i2
-// rect  = c0 | r0 << 5 | w << 10 | h << 16 : the face's pixel rectangle inside the tile, EXACT for the oracle's bbox test (bbox
-//         inflated by sqrt(blur) of the depth raster), so the pair loop needs no per-pixel bbox test; w = 0: nothing in this tile
-// inner = same packing: the only pixels where the face can be a SILHOUETTE fragment (bbox inflated by the silhouette radius x 1.001
-//         and 0.01 px: conservative, the exact distance test follows per pixel)
+//   d0 = x0 y0 x1 y1 | d1 = x2 y2 z0 z1 | d2 = z2 1/den 1/|e01|^2 1/|e02|^2 | d3 = span inner zbits lanes | d4 = 1/|e12|^2 face i0|i1<<16 i2
+// d3    = span inner zbits lanes (layouts in make_desc): the face's pixel rectangle inside the tile, EXACT for the oracle's bbox test
+//         (bbox inflated by sqrt(blur) of the depth raster), so the pair loop needs no per-pixel bbox test, and the INNER rectangle,
+//         the only pixels where the face can be a SILHOUETTE fragment (bbox inflated by the silhouette radius x 1.001 and 0.01 px:
+//         conservative, the exact distance test follows per pixel)
 // zbits = bits of a lower bound of every fragment depth of the face (its nearest vertex)
 __device__ __forceinline__ void make_desc(const RenderParams& P, const float* sv, int f, int ox, int oy, int txmax, int tymax, float4* d) {
     const int i0 = P.faces[3 * f], i1 = P.faces[3 * f + 1], i2 = P.faces[3 * f + 2];
@@ -286,10 +286,15 @@ __device__ __forceinline__ void make_desc(const RenderParams& P, const float* sv
     if (c0 > c1 || r0 > r1) { d[3] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
     int ic0 = max((int)fmaxf(ceilf(pix_of(bxmax - P.r_d + P.r_s, P.W, P.rx) - 0.01f), 0.f), c0), ic1 = min((int)fminf(floorf(pix_of(bxmin + P.r_d - P.r_s, P.W, P.rx) + 0.01f), (float)(P.W - 1)), c1);
     int ir0 = max((int)fmaxf(ceilf(pix_of(bymax - P.r_d + P.r_s, P.H, P.ry) - 0.01f), 0.f), r0), ir1 = min((int)fminf(floorf(pix_of(bymin + P.r_d - P.r_s, P.H, P.ry) + 0.01f), (float)(P.H - 1)), r1);
-    int inner = 0;
-    if (ic0 <= ic1 && ir0 <= ir1) inner = (ic0 - ox) | ((ir0 - oy) << 5) | ((ic1 - ic0 + 1) << 10) | ((ir1 - ir0 + 1) << 16);
-    const int w = c1 - c0 + 1;
-    const int rect = (c0 - ox) | ((r0 - oy) << 5) | (w << 10) | ((r1 - r0 + 1) << 16);
+    // the three words the prune passes decode (pass = whole rows of the rectangle, 32 / w of them; lane -> (row lr, column) once per face):
+    //   span  = first pixel r0 * TW + c0 | end (r0 + h) * TW << 10 | pixels per pass rpp * TW << 21          (0: nothing in this tile)
+    //   inner = first inner pixel row jr0 * TW | inner rows jh * TW << 10 | first inner column - c0 << 21 | inner columns << 26
+    //   lanes = ceil(65536 / w) (lane / w in 16.16 fixed point) | TW - w << 17 | lanes in use rpp * w << 23
+    const int w = c1 - c0 + 1, h = r1 - r0 + 1, rpp = 32 / w;
+    const unsigned span = (unsigned)((r0 - oy) * TW + (c0 - ox)) | ((unsigned)((r0 - oy + h) * TW) << 10) | ((unsigned)(rpp * TW) << 21);
+    unsigned inner = 0u;
+    if (ic0 <= ic1 && ir0 <= ir1) inner = (unsigned)((ir0 - oy) * TW) | ((unsigned)((ir1 - ir0 + 1) * TW) << 10) | ((unsigned)(ic0 - c0) << 21) | ((unsigned)(ic1 - ic0 + 1) << 26);
+    const unsigned lanes = (unsigned)((65536 + w - 1) / w) | ((unsigned)(TW - w) << 17) | ((unsigned)(rpp * w) << 23);
     const float den = MH_ADD(mh_edge(x2, y2, x0, y0, x1, y1), MH_KEPS);
     const float ex12 = x2 - x1, ey12 = y2 - y1, ex20 = x0 - x2, ey20 = y0 - y2, ex01 = x1 - x0, ey01 = y1 - y0;
     const float l01 = ex01 * ex01 + ey01 * ey01, l02 = ex20 * ex20 + ey20 * ey20, l12 = ex12 * ex12 + ey12 * ey12;
@@ -297,12 +302,7 @@ __device__ __forceinline__ void make_desc(const RenderParams& P, const float* sv
     d[0] = make_float4(x0, y0, x1, y1);
     d[1] = make_float4(x2, y2, z0, z1);
     d[2] = make_float4(z2, __frcp_rn(den), l01 <= MH_KEPS ? 0.f : __frcp_rn(l01), l02 <= MH_KEPS ? 0.f : __frcp_rn(l02));
-#if MH_R_ROWPASS
-    const int lanemap = ((65536 + w - 1) / w) | ((32 / w) << 20);           // 1 / w (16.16 fixed point, <= 65536) | whole rows per pass
-#else
-    const int lanemap = (65536 + w - 1) / w;
-#endif
-    d[3] = make_float4(__int_as_float(rect), __int_as_float(inner), __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))), __int_as_float(lanemap));
+    d[3] = make_float4(__uint_as_float(span), __uint_as_float(inner), __uint_as_float(__float_as_uint(fmaxf(zmin * (1.0f - 1e-6f), 0.f))), __uint_as_float(lanes));
     d[4] = make_float4(l12 <= MH_KEPS ? 0.f : __frcp_rn(l12), __int_as_float(f), __uint_as_float((unsigned)i0 | ((unsigned)i1 << 16)), __int_as_float(i2));
 }
 
@@ -640,94 +640,72 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
               };
               int qn = 0;                                                 // queued survivors (warp-uniform)
               int kn = 0;
-              if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);
+              if (lane == 0) kn = atoms_add(sb + SO_SINT + 4 * 40, MH_R_GRAB);
               for (;;) {
-                // next face of the chunk (dynamic hand-out, one index ahead)
-                const int k = __shfl_sync(0xffffffffu, kn, 0);
-                if (k >= ccnt) break;
-                if (lane == 0) kn = atoms_inc(sb + SO_SINT + 4 * 40);
-                const float4 q3 = lds128<48>(sb + SO_SDESC + k * 80);
-                const int rect = __float_as_int(q3.x), inner = __float_as_int(q3.y);
-                const unsigned zbits = __float_as_uint(q3.z);
-                const int lanemap = __float_as_int(q3.w);
-                const int w = (rect >> 10) & 63;                          // 0: binned conservatively, nothing of the face in this tile
-                const int c0 = rect & 31, r0 = (rect >> 5) & 31;
-                const int h = (rect >> 16) & 63;
-                const int jc0 = inner & 31, jr0 = (inner >> 5) & 31;
-                const unsigned jw = (inner >> 10) & 63, jh = (inner >> 16) & 63;
-                const unsigned ebase = (unsigned)k << 10;
-                if (lane == 0 && w) { RS_ADD(0, 1); RS_ADD(1, w * h); }
-#if MH_R_ROWPASS
-                // PRUNE passes over whole rows of the face's rectangle: lane -> (row lr, column lc) of the first rows once per face,
-                // then only the pixel index advances.  A pixel survives when the face's nearest vertex is not behind the key it could
-                // displace (the depth words of the keys alone, conservative on ties); outside the inner rectangle the face cannot be
-                // a silhouette fragment at all
-                if (w == 0) continue;
-                const int rpp = lanemap >> 20;                            // whole rows per pass (32 / w)
-                const int lr = (lane * (lanemap & 0xfffff)) >> 16;        // lane / w
-                const int lx = c0 + lane - lr * w;
-                const bool lane_ok = lr < rpp;
-                // per-lane bounds fold the lane tests in: a lane beyond the last whole row (or outside the inner columns) has an
-                // empty range.  Every lane loads (addresses stay inside the key planes), the range tests apply afterwards
-                int pix = lane_ok ? (r0 + lr) * TW + lx : 0;
-                const int pend = lane_ok ? (r0 + h) * TW : 0;
-                const unsigned ipix0 = (unsigned)(jr0 * TW);
-                const unsigned ipixn = (lane_ok && ((unsigned)(lx - jc0) < jw)) ? jh * TW : 0u;      // inner rows are rows of the rectangle
-                const int step = rpp * TW;
+                // next MH_R_GRAB faces of the chunk (dynamic hand-out, one grab ahead; the lists are ordered near -> far, so the coarser
+                // grain falls on the cheap, mostly pruned faces at the end)
+                const int k2 = __shfl_sync(0xffffffffu, kn, 0);
+                if (k2 >= ccnt) break;
+                if (lane == 0) kn = atoms_add(sb + SO_SINT + 4 * 40, MH_R_GRAB);
+                const int kend2 = min(k2 + MH_R_GRAB, ccnt);
 #pragma unroll 1
-                for (int rb = 0; rb < h; rb += rpp) {
-                    RS_WARP(2);
-                    const uint32_t ka = sb + 8 * pix;
-                    const unsigned td = lds32<SO_DKEY + 4>(ka), ts = lds32<SO_SKEY + 3 * SK_STRIDE + 4>(ka);
-                    const bool pd = (pix < pend) && (zbits <= td);
-                    const bool ps = ((unsigned)pix - ipix0 < ipixn) && (zbits <= ts);
-                    const unsigned bal = __ballot_sync(0xffffffffu, pd || ps);
-                    if (pd || ps) {
-                        sts32<0>(qa + 4 * (qn + __popc(bal & ltmask)), ebase | (unsigned)pix | (pd ? 1u << 20 : 0u) | (ps ? 1u << 21 : 0u));
-                        RS_ADD(3, 1);
-                    }
-                    qn += __popc(bal);
-                    pix += step;
-                    if (qn >= 32) {                                       // a full batch
-                        __syncwarp();
-                        qn -= 32;
-                        evaluate(lds32<0>(qa + 4 * (qn + lane)));
-                        __syncwarp();
-                    }
-                }
-#else
-                const int npix = w * h;
-                // PRUNE passes over the face's rectangle, 32 consecutive pixels (row-major) per pass
-                for (int o = lane; o - lane < npix; o += 32) {
-                    RS_WARP(2);
-                    const bool valid = o < npix;
-                    const int row = (o * lanemap) >> 16;
-                    const int col = o - row * w;
-                    const int lx = c0 + col, ly = r0 + row;
-                    const int pix = ly * TW + lx;
-                    const uint32_t ka = sb + 8 * pix;
-                    // prune on the depth words of the keys alone (conservative on ties): no fragment of this face can be nearer
-                    // than its nearest vertex; outside the inner rectangle it cannot be a silhouette fragment at all
-                    const bool inner_px = ((unsigned)(lx - jc0) < jw) && ((unsigned)(ly - jr0) < jh);
-                    const bool pd = valid && (zbits <= lds32<SO_DKEY + 4>(ka));
-                    const bool ps = valid && inner_px && (zbits <= lds32<SO_SKEY + 3 * SK_STRIDE + 4>(ka));
-                    const unsigned bal = __ballot_sync(0xffffffffu, pd || ps);
-                    if (pd || ps) {
-                        unsigned ent = ebase | (unsigned)pix;
-                        if (pd) ent |= 1u << 20;
-                        if (ps) ent |= 1u << 21;
-                        sts32<0>(qa + 4 * (qn + __popc(bal & ltmask)), ent);
-                        RS_ADD(3, 1); if (inner_px) RS_ADD(10, 1);
-                    }
-                    qn += __popc(bal);
-                    if (qn >= 32) {                                       // a full batch
-                        __syncwarp();
-                        qn -= 32;
-                        evaluate(lds32<0>(qa + 4 * (qn + lane)));
-                        __syncwarp();
-                    }
-                }
+                for (int k = k2; k < kend2; ++k) {
+                const float4 q3 = lds128<48>(sb + SO_SDESC + k * 80);
+                const unsigned span = __float_as_uint(q3.x), inner = __float_as_uint(q3.y), zbits = __float_as_uint(q3.z), lanes = __float_as_uint(q3.w);
+                if (span == 0u) continue;                                 // binned conservatively, nothing of the face in this tile
+                // PRUNE passes over whole rows of the face's rectangle: lane -> (row lr, column) of the first rows once per face,
+                // then only the key address advances.  A pixel survives when the face's nearest vertex is not behind the key it could
+                // displace (the depth words of the keys alone, conservative on ties); outside the inner rectangle the face cannot be
+                // a silhouette fragment at all.  Per-lane bounds fold the lane tests in: a lane beyond the last whole row (or outside
+                // the inner columns) has an empty range; every lane loads (addresses stay inside the key planes)
+                const unsigned lr = ((unsigned)lane * (lanes & 0x1ffffu)) >> 16;              // lane / w
+                const unsigned lrt = lr * ((lanes >> 17) & 63u);                               // lr * (TW - w)
+                const bool lane_ok = (unsigned)lane < (lanes >> 23);
+                const unsigned pend = (span >> 10) & 0x7ffu, step = span >> 21;
+                unsigned p = span & 0x3ffu;                                                    // first pixel of the pass (uniform)
+                uint32_t ka = lane_ok ? sb + 8u * (p + (unsigned)lane + lrt) : sb;             // this lane's key slot
+                uint32_t kend = lane_ok ? sb + 8u * pend : 0u;
+                asm volatile("" : "+r"(kend));                            // keep the per-lane bound in a register (ptxas otherwise re-derives the lane test in every pass)
+                const bool col_in = ((unsigned)lane + lrt - (lr << 5)) - ((inner >> 21) & 31u) < (inner >> 26);
+                const uint32_t ika0 = sb + 8u * (inner & 0x3ffu);
+                uint32_t ikn = (lane_ok && col_in) ? 8u * ((inner >> 10) & 0x7ffu) : 0u;
+                asm volatile("" : "+r"(ikn));
+                const unsigned ebase = (unsigned)k << 10;
+#ifdef MH_RSTATS
+                if (lane == 0) { RS_ADD(0, 1); RS_ADD(1, (32u - ((lanes >> 17) & 63u)) * ((pend - (p & ~31u)) >> 5)); }
+                int surv_item = 0;
 #endif
+                for (;;) {
+                    // tight loop: passes until the rectangle ends or a batch is full
+                    do {
+                        RS_WARP(2);
+                        const unsigned td = lds32<SO_DKEY + 4>(ka), ts = lds32<SO_SKEY + 3 * SK_STRIDE + 4>(ka);
+                        const bool pd = (ka < kend) && (zbits <= td);
+                        const bool ps = (ka - ika0 < ikn) && (zbits <= ts);
+                        const unsigned bal = __ballot_sync(0xffffffffu, pd || ps);
+                        if (pd || ps) {
+                            sts32<0>(qa + 4 * (qn + __popc(bal & ltmask)), ebase | ((ka - sb) >> 3) | (pd ? 1u << 20 : 0u) | (ps ? 1u << 21 : 0u));
+                            RS_ADD(3, 1);
+                        }
+                        qn += __popc(bal);
+#ifdef MH_RSTATS
+                        surv_item += __popc(bal);
+#endif
+                        ka += 8u * step;
+                        p += step;
+                    } while (p < pend && qn < 32);
+                    if (qn >= 32) {                                       // a full batch
+                        __syncwarp();
+                        qn -= 32;
+                        evaluate(lds32<0>(qa + 4 * (qn + lane)));
+                        __syncwarp();
+                    }
+                    if (p >= pend) break;
+                }
+#ifdef MH_RSTATS
+                if (surv_item == 0 && lane == 0) RS_ADD(10, 1);
+#endif
+                }
               }
               __syncwarp();
               if (lane < qn) evaluate(lds32<0>(qa + 4 * lane));           // the rest
