@@ -514,7 +514,7 @@ def main():
         if prof[8:].any():
             pf = float(opt.T_local * w['N'] * args.steps)
             sn = ['items', 'slots', 'warp-passes', 'lanes past prune', 'warp-passes past prune', 'lanes past key test', 'warp-passes past key test',
-                  'depth atomics', 'sil inserts', 'not-inside distance evals', 'items without a survivor', 'items a fresh 4x4-block bound would skip']
+                  'depth atomics', 'sil inserts', 'not-inside distance evals', 'items without a survivor', '-']
             print('pair statistics per person-frame:', {n_: round(float(v) / pf, 1) for n_, v in zip(sn, prof[8:20])}, file=sys.stderr)
         prof = prof[:8]
         names = ['load+ndc', 'binning', 'staging', 'pairs', 'per-pixel', 'sums+depth-bwd', 'chain', '-']
