@@ -273,6 +273,12 @@ int mh_debug_set_render_caps(mh_ctx* ctx, int32_t maxbins, int32_t bincap, int32
  * out[0] = person-frames the grid answered in the last cycle, out[1] = grid cells, out[2] = points, out[3] = cell size (micrometres).
  * The environment variable MH_KNN_GRID=0 (read when the cloud is set) disables the grid. */
 int mh_debug_knn_stats(mh_ctx* ctx, int64_t* out4, void* stream);
+/* Device buffers of 256 KB and more are recycled between the contexts of a process (a job that fits many sequences, predict.py:315-357,
+ * creates one optimiser per sequence): mh_destroy parks them, mh_create takes buffers of the same size back.  mh_pool_trim returns the
+ * parked buffers to the driver (done automatically when an allocation fails), mh_pool_bytes says how much is parked.  MH_POOL=0 in
+ * the environment turns the recycling off. */
+void mh_pool_trim(void);
+int64_t mh_pool_bytes(void);
 /* testing aid: the pose-corrective contraction alone, C (M, 20672) = A (M, 192) . posedirs, HOST pointers, blocking; use_tc = 1 runs
  * the tcgen05 / TMEM kernel (3 x TF32), 0 the FP32 SIMT kernel (smpl.py:549-553 without the shape term) */
 int mh_debug_gemm_fwd(mh_ctx* ctx, const float* A_host, float* C_host, int32_t M, int32_t use_tc);

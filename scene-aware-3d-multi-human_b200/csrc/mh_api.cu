@@ -21,8 +21,8 @@ template <typename T>
 static int dev_alloc(mh_ctx* c, T** p, int64_t n) {
     *p = nullptr;
     if (n <= 0) n = 1;
-    cudaError_t e = cudaMalloc((void**)p, (size_t)n * sizeof(T));
-    if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "cudaMalloc(%lld bytes): %s", (long long)(n * sizeof(T)), cudaGetErrorString(e));
+    cudaError_t e = mh_dev_alloc((void**)p, (size_t)n * sizeof(T));
+    if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "mh_dev_alloc(%lld bytes): %s", (long long)(n * sizeof(T)), cudaGetErrorString(e));
     e = cudaMemset(*p, 0, (size_t)n * sizeof(T));
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
     c->allocs.push_back((void*)*p);
@@ -168,8 +168,8 @@ extern "C" void mh_destroy(mh_ctx* c) {
     mh_knn_free(c);
     mh_comm_free(c);
     if (c->events) { for (int i = 0; i < MH_TIMING_RING * MH_TIMING_EVENTS; ++i) cudaEventDestroy(c->events[i]); delete[] c->events; }
-    for (void* p : c->allocs) cudaFree(p);
-    if (c->stage) cudaFree(c->stage);
+    for (void* p : c->allocs) mh_dev_free(p);
+    if (c->stage) mh_dev_free(c->stage);
     for (int i = 0; i < 2; ++i) { if (c->pack_buf[i]) cudaFreeHost(c->pack_buf[i]); if (c->pack_ev[i]) cudaEventDestroy(c->pack_ev[i]); }
     delete c;
 }
@@ -396,7 +396,11 @@ static int ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* dept
     // float32 masks are compacted on the host (MH_INGEST_HOST_PACK=0: on the device after a full-size copy, for A/B measurements)
     // -- only when this process is alone on the host: with one rank per GPU the ranks' copies run in parallel over their own PCIe
     // links while the packing threads would all share the same cores and memory channels
-    static const int host_pack_env = [] { const char* v = getenv("MH_INGEST_HOST_PACK"); return v ? atoi(v) : -1; }();
+    const char* hp_env = getenv("MH_INGEST_HOST_PACK");
+    const int host_pack_env = hp_env ? atoi(hp_env) : -1;
+    // (measured on C3 with pinned masks: host packing 0.20 s, full-size copies + device packing 0.32 s = 53 GB/s over the bus, and a
+    // batch-by-batch mix of the two -- unpacked whenever the copy engine is idle -- 0.22 s: both paths read the same 17 GB of host
+    // memory, which is the limit on this host; the mix was dropped)
     const bool host_pack = host_pack_env >= 0 ? host_pack_env != 0 : d.world == 1;
     if (seg && !seg_is_u8 && host_pack) {
         const int64_t words = (int64_t)count * HW;
@@ -424,9 +428,9 @@ static int ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* dept
     }
     if (seg && need > c->stage_floats) {
         MH_CUDA(c, cudaStreamSynchronize(st));
-        if (c->stage) cudaFree(c->stage);
+        if (c->stage) mh_dev_free(c->stage);
         c->stage = nullptr; c->stage_floats = 0;
-        MH_CUDA(c, cudaMalloc((void**)&c->stage, need * sizeof(float)));
+        MH_CUDA(c, mh_dev_alloc((void**)&c->stage, need * sizeof(float)));
         c->stage_floats = need;
     }
     if (depths) MH_CUDA(c, cudaMemcpyAsync(c->depth + (int64_t)t0 * HW, depths, sizeof(float) * count * HW, cudaMemcpyHostToDevice, st));
@@ -474,8 +478,8 @@ extern "C" int mh_set_scene_from_depth(mh_ctx* c, const float* depth_host, const
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t HW = (int64_t)c->d.H * c->d.W;
     float* dd; uint8_t* dm;
-    MH_CUDA(c, cudaMalloc((void**)&dd, HW * sizeof(float)));
-    MH_CUDA(c, cudaMalloc((void**)&dm, HW));
+    MH_CUDA(c, mh_dev_alloc((void**)&dd, HW * sizeof(float)));
+    MH_CUDA(c, mh_dev_alloc((void**)&dm, HW));
     int r = MH_OK;
     if (cudaMemcpyAsync(dd, depth_host, HW * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(dm, mask_host, HW, cudaMemcpyHostToDevice, st) != cudaSuccess) {
@@ -484,7 +488,7 @@ extern "C" int mh_set_scene_from_depth(mh_ctx* c, const float* depth_host, const
     }
     if (r == MH_OK) r = mh_scene_from_depth(c, dd, dm, st);
     cudaStreamSynchronize(st);
-    cudaFree(dd); cudaFree(dm);
+    mh_dev_free(dd); mh_dev_free(dm);
     return r;
 }
 
@@ -621,7 +625,7 @@ extern "C" int mh_smpl_forward(mh_ctx* c, const float* betas, const float* theta
     // scratch: the per-iteration arrays of the context (overwritten by the next cycle anyway); per-body shapes live in `dverts`
     const int64_t chunk = c->nb;
     float* dbetas;
-    MH_CUDA(c, cudaMalloc((void**)&dbetas, sizeof(float) * chunk * 10));
+    MH_CUDA(c, mh_dev_alloc((void**)&dbetas, sizeof(float) * chunk * 10));
     std::vector<float> hv;
     int r = MH_OK;
     for (int64_t s = 0; s < nbodies && r == MH_OK; s += chunk) {
@@ -639,7 +643,7 @@ extern "C" int mh_smpl_forward(mh_ctx* c, const float* betas, const float* theta
         if (joints17 && cudaMemcpyAsync(joints17 + s * 51, c->j17, sizeof(float) * n * 51, cudaMemcpyDeviceToHost, st) != cudaSuccess) r = MH_E_CUDA;
         if (cudaStreamSynchronize(st) != cudaSuccess) r = MH_E_CUDA;
     }
-    cudaFree(dbetas);
+    mh_dev_free(dbetas);
     if (r == MH_E_CUDA && !c->err[0]) snprintf(c->err, sizeof(c->err), "mh_smpl_forward: %s", cudaGetErrorString(cudaGetLastError()));
     return r;
 }
@@ -686,9 +690,9 @@ extern "C" int mh_smpl_regress(mh_ctx* c, const float* betas, const float* theta
     int *d_rptr = nullptr, *d_rvert = nullptr;
     float *d_rw = nullptr, *dbetas = nullptr, *dj = nullptr;
     int r = MH_OK;
-    if (cudaMalloc((void**)&d_rptr, sizeof(int) * rptr.size()) != cudaSuccess || cudaMalloc((void**)&d_rvert, sizeof(int) * rvert.size()) != cudaSuccess ||
-        cudaMalloc((void**)&d_rw, sizeof(float) * rw.size()) != cudaSuccess || cudaMalloc((void**)&dbetas, sizeof(float) * chunk * 10) != cudaSuccess ||
-        cudaMalloc((void**)&dj, sizeof(float) * chunk * J * 3) != cudaSuccess)
+    if (mh_dev_alloc((void**)&d_rptr, sizeof(int) * rptr.size()) != cudaSuccess || mh_dev_alloc((void**)&d_rvert, sizeof(int) * rvert.size()) != cudaSuccess ||
+        mh_dev_alloc((void**)&d_rw, sizeof(float) * rw.size()) != cudaSuccess || mh_dev_alloc((void**)&dbetas, sizeof(float) * chunk * 10) != cudaSuccess ||
+        mh_dev_alloc((void**)&dj, sizeof(float) * chunk * J * 3) != cudaSuccess)
         r = MH_E_CUDA;
     if (r == MH_OK) {
         cudaMemcpyAsync(d_rptr, rptr.data(), sizeof(int) * rptr.size(), cudaMemcpyHostToDevice, st);
@@ -709,7 +713,7 @@ extern "C" int mh_smpl_regress(mh_ctx* c, const float* betas, const float* theta
         if (cudaMemcpyAsync(joints + s * J * 3, dj, sizeof(float) * n * J * 3, cudaMemcpyDeviceToHost, st) != cudaSuccess) r = MH_E_CUDA;
         if (cudaStreamSynchronize(st) != cudaSuccess) r = MH_E_CUDA;
     }
-    cudaFree(d_rptr); cudaFree(d_rvert); cudaFree(d_rw); cudaFree(dbetas); cudaFree(dj);
+    mh_dev_free(d_rptr); mh_dev_free(d_rvert); mh_dev_free(d_rw); mh_dev_free(dbetas); mh_dev_free(dj);
     if (r == MH_E_CUDA && !c->err[0]) snprintf(c->err, sizeof(c->err), "mh_smpl_regress: %s", cudaGetErrorString(cudaGetLastError()));
     return r;
 }
@@ -730,7 +734,7 @@ extern "C" int mh_init_begin(mh_ctx* c, const float* pose2d, const float* theta,
     const mh_dims& d = c->d;
     const int TN = d.T * d.N;
     float* dbetas;
-    MH_CUDA(c, cudaMalloc((void**)&dbetas, sizeof(float) * TN * 10));
+    MH_CUDA(c, mh_dev_alloc((void**)&dbetas, sizeof(float) * TN * 10));
     MH_CUDA(c, cudaMemcpyAsync(dbetas, betas, sizeof(float) * TN * 10, cudaMemcpyHostToDevice, st));
     MH_CUDA(c, cudaMemcpyAsync(c->theta_all, theta, sizeof(float) * TN * 72, cudaMemcpyHostToDevice, st));
     MH_CUDA(c, cudaMemcpyAsync(c->pose2d, pose2d, sizeof(float) * TN * 51, cudaMemcpyHostToDevice, st));
@@ -747,7 +751,7 @@ extern "C" int mh_init_begin(mh_ctx* c, const float* pose2d, const float* theta,
         cudaMemsetAsync(c->adam_v, 0, sizeof(float) * TN * 3, st);
     }
     cudaStreamSynchronize(st);
-    cudaFree(dbetas);
+    mh_dev_free(dbetas);
     if (r != MH_OK) return r;
     MH_CUDA(c, cudaGetLastError());
     c->init_ready = true;
@@ -896,12 +900,12 @@ extern "C" int mh_scene_depths(mh_ctx* c, int32_t t0, int32_t count, float* out_
     if (t0 < 0 || count < 1 || t0 + count > d.T || !out_host) MH_FAIL(c, MH_E_ARG, "mh_scene_depths: bad range");
     const int64_t HW = (int64_t)d.H * d.W;
     float* tmp;
-    MH_CUDA(c, cudaMalloc((void**)&tmp, sizeof(float) * count * HW));
+    MH_CUDA(c, mh_dev_alloc((void**)&tmp, sizeof(float) * count * HW));
     k_scene_depths<<<dim3(mh_cdiv(HW, 1024), count), 256>>>(c->depth + (int64_t)t0 * HW, c->params + c->off[MH_P_ZMIN_LIN] + t0,
                                                             c->params + c->off[MH_P_ZMAX_LIN] + t0, HW, tmp);
     c->launches++;
     cudaError_t e = cudaMemcpy(out_host, tmp, sizeof(float) * count * HW, cudaMemcpyDeviceToHost);
-    cudaFree(tmp);
+    mh_dev_free(tmp);
     MH_CUDA(c, e);
     return MH_OK;
 }
@@ -913,7 +917,7 @@ extern "C" int mh_debug_render(mh_ctx* c, int32_t t, int32_t n, float* zbuf_host
     if (t < 0 || t >= d.T || n < 0 || n >= d.N) MH_FAIL(c, MH_E_ARG, "mh_debug_render: bad index");
     const int64_t HW = (int64_t)d.H * d.W;
     float* tmp;
-    MH_CUDA(c, cudaMalloc((void**)&tmp, sizeof(float) * 2 * HW));
+    MH_CUDA(c, mh_dev_alloc((void**)&tmp, sizeof(float) * 2 * HW));
     int r = mh_render_debug(c, t, n, tmp, tmp + HW, 0);
     if (r == MH_OK) {
         cudaError_t e = cudaDeviceSynchronize();
@@ -921,7 +925,7 @@ extern "C" int mh_debug_render(mh_ctx* c, int32_t t, int32_t n, float* zbuf_host
         if (e == cudaSuccess && alpha_host) e = cudaMemcpy(alpha_host, tmp + HW, sizeof(float) * HW, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "mh_debug_render: %s", cudaGetErrorString(e)); r = MH_E_CUDA; }
     }
-    cudaFree(tmp);
+    mh_dev_free(tmp);
     return r;
 }
 
@@ -953,7 +957,7 @@ extern "C" int mh_read_planes(mh_ctx* c, int32_t t0, int32_t count, float* depth
     if (depths_host) MH_CUDA(c, cudaMemcpy(depths_host, c->depth + (int64_t)t0 * HW, sizeof(float) * count * HW, cudaMemcpyDeviceToHost));
     if (seg_host) {
         float* tmp;
-        MH_CUDA(c, cudaMalloc((void**)&tmp, sizeof(float) * d.N * HW));
+        MH_CUDA(c, mh_dev_alloc((void**)&tmp, sizeof(float) * d.N * HW));
         int r = MH_OK;
         for (int t = t0; t < t0 + count && r == MH_OK; ++t) {
             r = mh_expand_planes(c, t, tmp, 0);
@@ -962,7 +966,7 @@ extern "C" int mh_read_planes(mh_ctx* c, int32_t t0, int32_t count, float* depth
                 r = MH_E_CUDA;
             }
         }
-        cudaFree(tmp);
+        mh_dev_free(tmp);
         return r;
     }
     return MH_OK;

@@ -165,6 +165,10 @@ int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st);
 int mh_terms_gather(mh_ctx* c, int use_prev, int use_next, cudaStream_t st);
 int mh_terms_pre_raster(mh_ctx* c, int use_prev, int use_next, cudaStream_t st);
 int mh_terms_post(mh_ctx* c, cudaStream_t st);
+// pooled device memory (mh_pool.cu): every device buffer of the library comes from / returns to these
+cudaError_t mh_dev_alloc(void** p, size_t bytes);
+cudaError_t mh_dev_free(void* p);
+template <typename T> static inline cudaError_t mh_dev_alloc(T** p, size_t bytes) { return mh_dev_alloc((void**)p, bytes); }
 int mh_knn_build(mh_ctx* c, cudaStream_t st);       // (re)build the contact-term grid for the current scene cloud
 void mh_knn_free(mh_ctx* c);
 int mh_loss_begin(mh_ctx* c, cudaStream_t st);      // zero the loss partials of the cycle

@@ -79,16 +79,16 @@ extern "C" int mh_one_euro_filter(mh_ctx* c, const float* x_host, float* y_host,
     if (!x_host || !y_host || T < 1 || row_elems < 1) MH_FAIL(c, MH_E_ARG, "mh_one_euro_filter: bad arguments");
     const int64_t n = (int64_t)T * row_elems;
     float *dx, *dy, *carry;
-    MH_CUDA(c, cudaMalloc((void**)&dx, sizeof(float) * n));
-    cudaError_t e = cudaMalloc((void**)&dy, sizeof(float) * n);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&carry, sizeof(float) * 2 * row_elems);
+    MH_CUDA(c, mh_dev_alloc((void**)&dx, sizeof(float) * n));
+    cudaError_t e = mh_dev_alloc((void**)&dy, sizeof(float) * n);
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&carry, sizeof(float) * 2 * row_elems);
     if (e == cudaSuccess) e = cudaMemcpy(dx, x_host, sizeof(float) * n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         k_one_euro<<<mh_cdiv(row_elems, 256), 256>>>(dx, dy, row_elems, row_elems, T, 0, 1, carry, carry, row_elems, frame_rate, min_cutoff, beta);
         c->launches++;
         e = cudaMemcpy(y_host, dy, sizeof(float) * n, cudaMemcpyDeviceToHost);
     }
-    cudaFree(dx); cudaFree(dy); cudaFree(carry);
+    mh_dev_free(dx); mh_dev_free(dy); mh_dev_free(carry);
     MH_CUDA(c, e);
     return MH_OK;
 }
@@ -144,7 +144,7 @@ int mh_scene_from_depth(mh_ctx* c, const float* depth_dev, const uint8_t* mask_d
     const int64_t HW = (int64_t)d.H * d.W;
     const int nblk = mh_cdiv(HW, SC_BLOCK);
     int* counts;
-    MH_CUDA(c, cudaMalloc((void**)&counts, sizeof(int) * (nblk + 1)));
+    MH_CUDA(c, mh_dev_alloc((void**)&counts, sizeof(int) * (nblk + 1)));
     k_scene_count<<<nblk, SC_BLOCK, 0, st>>>(mask_dev, HW, counts);
     c->launches++;
     k_scene_scan<<<1, 1, 0, st>>>(counts, nblk, counts + nblk);
@@ -152,8 +152,8 @@ int mh_scene_from_depth(mh_ctx* c, const float* depth_dev, const uint8_t* mask_d
     int total = 0;
     cudaMemcpyAsync(&total, counts + nblk, sizeof(int), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { cudaFree(counts); MH_CUDA(c, e); }
-    if (total > d.M_max) { cudaFree(counts); MH_FAIL(c, MH_E_CAPACITY, "scene cloud of %d points exceeds M_max = %lld", total, (long long)d.M_max); }
+    if (e != cudaSuccess) { mh_dev_free(counts); MH_CUDA(c, e); }
+    if (total > d.M_max) { mh_dev_free(counts); MH_FAIL(c, MH_E_CAPACITY, "scene cloud of %d points exceeds M_max = %lld", total, (long long)d.M_max); }
     // A = K[:2,:2]^T = [[k00, k10], [k01, k11]] ; inverse in closed form
     const float a = c->K[0], b = c->K[3], cc = c->K[1], dd = c->K[4];
     const float det = a * dd - b * cc;
@@ -161,7 +161,7 @@ int mh_scene_from_depth(mh_ctx* c, const float* depth_dev, const uint8_t* mask_d
     k_scene_scatter<<<nblk, SC_BLOCK, 0, st>>>(depth_dev, mask_dev, d.W, HW, counts, c->K[2], c->K[5], i00, i01, i10, i11, d.M_max, c->scene);
     c->launches++;
     e = cudaStreamSynchronize(st);
-    cudaFree(counts);
+    mh_dev_free(counts);
     MH_CUDA(c, e);
     if (total > 0 && total < MH_KNN) MH_FAIL(c, MH_E_ARG, "scene cloud has only %d points (< %d)", total, MH_KNN);
     c->M = total;

@@ -375,9 +375,9 @@ extern "C" int mh_debug_gemm_fwd(mh_ctx* c, const float* A_host, float* C_host, 
     if (!c || !A_host || !C_host || M <= 0) return MH_E_ARG;
     cudaSetDevice(c->d.device);
     float *A = nullptr, *Z = nullptr, *C = nullptr;
-    MH_CUDA(c, cudaMalloc((void**)&A, sizeof(float) * (size_t)M * MH_KPF));
-    MH_CUDA(c, cudaMalloc((void**)&Z, sizeof(float) * MH_LD3V));
-    MH_CUDA(c, cudaMalloc((void**)&C, sizeof(float) * (size_t)M * MH_LD3V));
+    MH_CUDA(c, mh_dev_alloc((void**)&A, sizeof(float) * (size_t)M * MH_KPF));
+    MH_CUDA(c, mh_dev_alloc((void**)&Z, sizeof(float) * MH_LD3V));
+    MH_CUDA(c, mh_dev_alloc((void**)&C, sizeof(float) * (size_t)M * MH_LD3V));
     MH_CUDA(c, cudaMemcpy(A, A_host, sizeof(float) * (size_t)M * MH_KPF, cudaMemcpyHostToDevice));
     MH_CUDA(c, cudaMemset(Z, 0, sizeof(float) * MH_LD3V));
     MH_CUDA(c, cudaMemset(C, 0xff, sizeof(float) * (size_t)M * MH_LD3V));
@@ -387,7 +387,7 @@ extern "C" int mh_debug_gemm_fwd(mh_ctx* c, const float* A_host, float* C_host, 
         if (e == cudaSuccess) e = cudaMemcpy(C_host, C, sizeof(float) * (size_t)M * MH_LD3V, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { snprintf(c->err, sizeof(c->err), "mh_debug_gemm_fwd: %s", cudaGetErrorString(e)); rc = MH_E_CUDA; }
     }
-    cudaFree(A); cudaFree(Z); cudaFree(C);
+    mh_dev_free(A); mh_dev_free(Z); mh_dev_free(C);
     return rc;
 }
 
@@ -398,8 +398,8 @@ extern "C" int mh_debug_gemm_bwd(mh_ctx* c, const float* E_host, float* D_host, 
     cudaSetDevice(c->d.device);
     float *E = nullptr, *P = nullptr;
     const size_t np = (size_t)MH_KSPLIT * M * MH_NEXT;
-    MH_CUDA(c, cudaMalloc((void**)&E, sizeof(float) * (size_t)M * MH_LD3V));
-    MH_CUDA(c, cudaMalloc((void**)&P, sizeof(float) * np));
+    MH_CUDA(c, mh_dev_alloc((void**)&E, sizeof(float) * (size_t)M * MH_LD3V));
+    MH_CUDA(c, mh_dev_alloc((void**)&P, sizeof(float) * np));
     MH_CUDA(c, cudaMemcpy(E, E_host, sizeof(float) * (size_t)M * MH_LD3V, cudaMemcpyHostToDevice));
     MH_CUDA(c, cudaMemset(P, 0xff, sizeof(float) * np));
     int rc = use_tc ? mh_gemm_bwd_tc(c, E, P, M, 0, M, 0) : mh_gemm_bwd_simt(c, E, P, M, 0, M, 0);
@@ -415,6 +415,6 @@ extern "C" int mh_debug_gemm_bwd(mh_ctx* c, const float* E_host, float* D_host, 
                 D_host[i] = a;
             }
     }
-    cudaFree(E); cudaFree(P);
+    mh_dev_free(E); mh_dev_free(P);
     return rc;
 }

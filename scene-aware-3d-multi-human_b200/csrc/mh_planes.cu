@@ -200,8 +200,8 @@ int mh_render_synth(mh_ctx* c, float y_ground, float z_wall, cudaStream_t st) {
     const mh_dims& d = c->d;
     const int64_t HW = (int64_t)d.H * d.W;
     float* zb; unsigned* mm;
-    MH_CUDA(c, cudaMalloc((void**)&zb, sizeof(float) * (d.N + 1) * HW));
-    MH_CUDA(c, cudaMalloc((void**)&mm, sizeof(unsigned) * 2 * d.T));
+    MH_CUDA(c, mh_dev_alloc((void**)&zb, sizeof(float) * (d.N + 1) * HW));
+    MH_CUDA(c, mh_dev_alloc((void**)&mm, sizeof(unsigned) * 2 * d.T));
     int r = MH_OK;
     std::vector<unsigned> init(2 * d.T);
     for (int t = 0; t < d.T; ++t) { init[2 * t] = 0x7f800000u; init[2 * t + 1] = 0u; }
@@ -216,7 +216,7 @@ int mh_render_synth(mh_ctx* c, float y_ground, float z_wall, cudaStream_t st) {
         c->launches++;
     }
     cudaStreamSynchronize(st);
-    cudaFree(zb); cudaFree(mm);
+    mh_dev_free(zb); mh_dev_free(mm);
     if (r != MH_OK) return r;
     MH_CUDA(c, cudaGetLastError());
     return MH_OK;

@@ -868,13 +868,13 @@ int mh_render_alloc(mh_ctx* c) {
     rs->bincap = 1 << 20;
     rs->wcap = c->d.H * c->d.W;
     const size_t n = (size_t)rs->nctas;
-    cudaError_t e = cudaMalloc((void**)&rs->binlist, n * rs->bincap * sizeof(uint16_t));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->fbin, n * MH_F * sizeof(uint2));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wpix, n * rs->wcap * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wface, n * rs->wcap * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->wz, n * rs->wcap * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->counter, sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&rs->gsg, n * MH_LD3V * sizeof(long long));
+    cudaError_t e = mh_dev_alloc((void**)&rs->binlist, n * rs->bincap * sizeof(uint16_t));
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->fbin, n * MH_F * sizeof(uint2));
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->wpix, n * rs->wcap * sizeof(int));
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->wface, n * rs->wcap * sizeof(int));
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->wz, n * rs->wcap * sizeof(float));
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->counter, sizeof(int));
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->gsg, n * MH_LD3V * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(long long));
     { const char* v = getenv("MH_RENDER_NSLAB"); rs->nslab = v ? std::min(std::max(atoi(v), 1), 256) : R_NSLAB; }     // development switch
     rs->prof = nullptr;
@@ -888,9 +888,9 @@ int mh_render_alloc(mh_ctx* c) {
 
 void mh_render_free(mh_ctx* c) {
     if (!c->rs) return;
-    if (c->rs->prof) cudaFree(c->rs->prof);
-    cudaFree(c->rs->fbin); cudaFree(c->rs->gsg);
-    cudaFree(c->rs->binlist); cudaFree(c->rs->wpix); cudaFree(c->rs->wface); cudaFree(c->rs->wz); cudaFree(c->rs->counter);
+    if (c->rs->prof) mh_dev_free(c->rs->prof);
+    mh_dev_free(c->rs->fbin); mh_dev_free(c->rs->gsg);
+    mh_dev_free(c->rs->binlist); mh_dev_free(c->rs->wpix); mh_dev_free(c->rs->wface); mh_dev_free(c->rs->wz); mh_dev_free(c->rs->counter);
     delete c->rs;
     c->rs = nullptr;
 }
@@ -965,9 +965,9 @@ extern "C" int mh_render_profile(mh_ctx* c, int32_t on, long long* out32_host) {
         MH_CUDA(c, cudaMemcpy(h.data(), rs->prof, n * sizeof(long long), cudaMemcpyDeviceToHost));
         for (int k = 0; k < MH_NPROF; ++k) { out32_host[k] = 0; for (int b = 0; b < rs->nctas; ++b) out32_host[k] += h[(size_t)b * MH_NPROF + k]; }
     }
-    if (on && !rs->prof) MH_CUDA(c, cudaMalloc((void**)&rs->prof, n * sizeof(long long)));
+    if (on && !rs->prof) MH_CUDA(c, mh_dev_alloc((void**)&rs->prof, n * sizeof(long long)));
     if (on) MH_CUDA(c, cudaMemset(rs->prof, 0, n * sizeof(long long)));
-    if (!on && rs->prof) { cudaFree(rs->prof); rs->prof = nullptr; }
+    if (!on && rs->prof) { mh_dev_free(rs->prof); rs->prof = nullptr; }
     return MH_OK;
 }
 

@@ -41,16 +41,16 @@ extern "C" int mh_scene_set_back(mh_ctx* c, int32_t t0, int32_t count, const uin
         memset(s, 0, sizeof(*s));
         s->HW = HW;
         c->scene_state = s;
-        cudaError_t e = cudaMalloc((void**)&s->back, (size_t)d.T * HW);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->hist, sizeof(float) * 16 * HW * 3);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->aux, sizeof(float) * 2 * HW * 3);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->prefix, sizeof(uint32_t) * 3 * HW);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->krem, sizeof(uint32_t) * 3 * HW);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->ntot, sizeof(uint32_t) * HW);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->ab, sizeof(float) * 2 * d.T);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->out_depth, sizeof(float) * HW);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->out_mask, HW);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->out_img, 3 * HW);
+        cudaError_t e = mh_dev_alloc((void**)&s->back, (size_t)d.T * HW);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->hist, sizeof(float) * 16 * HW * 3);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->aux, sizeof(float) * 2 * HW * 3);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->prefix, sizeof(uint32_t) * 3 * HW);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->krem, sizeof(uint32_t) * 3 * HW);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->ntot, sizeof(uint32_t) * HW);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->ab, sizeof(float) * 2 * d.T);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->out_depth, sizeof(float) * HW);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->out_mask, HW);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->out_img, 3 * HW);
         if (e == cudaSuccess) e = cudaMemset(s->back, 0, (size_t)d.T * HW);
         if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "scene state: %s", cudaGetErrorString(e));
     }
@@ -59,7 +59,7 @@ extern "C" int mh_scene_set_back(mh_ctx* c, int32_t t0, int32_t count, const uin
     MH_CUDA(c, cudaMemcpyAsync(s->back + (size_t)t0 * HW, back_host, (size_t)count * HW, cudaMemcpyHostToDevice, st));
     s->has_back = true;
     if (images_host) {
-        if (!s->images) MH_CUDA(c, cudaMalloc((void**)&s->images, (size_t)d.T * HW * 3));
+        if (!s->images) MH_CUDA(c, mh_dev_alloc((void**)&s->images, (size_t)d.T * HW * 3));
         MH_CUDA(c, cudaMemcpyAsync(s->images + (size_t)t0 * HW * 3, images_host, (size_t)count * HW * 3, cudaMemcpyHostToDevice, st));
         s->has_images = true;
     }
@@ -69,9 +69,9 @@ extern "C" int mh_scene_set_back(mh_ctx* c, int32_t t0, int32_t count, const uin
 void mh_scene_free(mh_ctx* c) {
     MhSceneState* s = scene_state(c);
     if (!s) return;
-    cudaFree(s->back); if (s->images) cudaFree(s->images);
-    cudaFree(s->hist); cudaFree(s->aux); cudaFree(s->prefix); cudaFree(s->krem); cudaFree(s->ntot); cudaFree(s->ab);
-    cudaFree(s->out_depth); cudaFree(s->out_mask); cudaFree(s->out_img);
+    mh_dev_free(s->back); if (s->images) mh_dev_free(s->images);
+    mh_dev_free(s->hist); mh_dev_free(s->aux); mh_dev_free(s->prefix); mh_dev_free(s->krem); mh_dev_free(s->ntot); mh_dev_free(s->ab);
+    mh_dev_free(s->out_depth); mh_dev_free(s->out_mask); mh_dev_free(s->out_img);
     delete s;
     c->scene_state = nullptr;
 }
@@ -364,10 +364,10 @@ extern "C" int mh_postprocess_depthmap(mh_ctx* c, const float* depth_host, const
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t HW = (int64_t)c->d.H * c->d.W;
     float* dd = nullptr; uint8_t* dm = nullptr;
-    MH_CUDA(c, cudaMalloc((void**)&dd, HW * sizeof(float)));
+    MH_CUDA(c, mh_dev_alloc((void**)&dd, HW * sizeof(float)));
     cudaError_t e = cudaMemcpyAsync(dd, depth_host, HW * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && mask_host_or_null) {
-        e = cudaMalloc((void**)&dm, HW);
+        e = mh_dev_alloc((void**)&dm, HW);
         if (e == cudaSuccess) e = cudaMemcpyAsync(dm, mask_host_or_null, HW, cudaMemcpyHostToDevice, st);
     }
     int r = MH_OK;
@@ -375,8 +375,8 @@ extern "C" int mh_postprocess_depthmap(mh_ctx* c, const float* depth_host, const
     if (r == MH_OK) r = mh_scene_postprocess_dev(c, dd, dm, use_bilateral, fillin_ksize, st);
     if (r == MH_OK && cudaMemcpyAsync(out_host, mh_scene_post_result(c), HW * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) r = MH_E_CUDA;
     cudaStreamSynchronize(st);
-    cudaFree(dd);
-    if (dm) cudaFree(dm);
+    mh_dev_free(dd);
+    if (dm) mh_dev_free(dm);
     return r;
 }
 

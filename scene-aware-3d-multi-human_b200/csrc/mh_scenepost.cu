@@ -199,15 +199,15 @@ static MhScenePost* post_state(mh_ctx* c, int64_t HW) {
     s->HW = HW;
     cudaError_t e = cudaSuccess;
     float** planes[] = {&s->a, &s->b, &s->g1, &s->g2, &s->dep[0], &s->dep[1]};
-    for (float** p : planes) if (e == cudaSuccess) e = cudaMalloc((void**)p, sizeof(float) * HW);
-    for (int i = 0; i < 2; ++i) if (e == cudaSuccess) e = cudaMalloc((void**)&s->msk[i], HW);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->lut, sizeof(float) * (SP_LUT + 4));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->part, sizeof(double) * 4 * SP_NPART);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->stat, sizeof(double) * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->holes, sizeof(int) * 2);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->offw, sizeof(float) * SP_MAXOFF);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->offdy, sizeof(int) * SP_MAXOFF);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->offdx, sizeof(int) * SP_MAXOFF);
+    for (float** p : planes) if (e == cudaSuccess) e = mh_dev_alloc((void**)p, sizeof(float) * HW);
+    for (int i = 0; i < 2; ++i) if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->msk[i], HW);
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->lut, sizeof(float) * (SP_LUT + 4));
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->part, sizeof(double) * 4 * SP_NPART);
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->stat, sizeof(double) * 8);
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->holes, sizeof(int) * 2);
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->offw, sizeof(float) * SP_MAXOFF);
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->offdy, sizeof(int) * SP_MAXOFF);
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->offdx, sizeof(int) * SP_MAXOFF);
     if (e != cudaSuccess) { delete s; return nullptr; }
     c->scene_post = s;
     return s;
@@ -217,7 +217,7 @@ void mh_scenepost_free(mh_ctx* c) {
     MhScenePost* s = reinterpret_cast<MhScenePost*>(c->scene_post);
     if (!s) return;
     void* ptrs[] = {s->a, s->b, s->g1, s->g2, s->dep[0], s->dep[1], s->msk[0], s->msk[1], s->lut, s->part, s->stat, s->holes, s->offw, s->offdy, s->offdx};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    for (void* p : ptrs) if (p) mh_dev_free(p);
     delete s;
     c->scene_post = nullptr;
 }

@@ -488,8 +488,8 @@ static MhKnnGrid* knn_grid(mh_ctx* c) { return reinterpret_cast<MhKnnGrid*>(c->k
 void mh_knn_free(mh_ctx* c) {
     MhKnnGrid* g = knn_grid(c);
     if (!g) return;
-    for (int l = 0; l < KG_LEVELS; ++l) { cudaFree(g->lev[l].bbox); cudaFree(g->lev[l].cell_start); cudaFree(g->lev[l].gpts); }
-    cudaFree(g->cursor); cudaFree(g->pcell); cudaFree(g->part); cudaFree(g->resolved);
+    for (int l = 0; l < KG_LEVELS; ++l) { mh_dev_free(g->lev[l].bbox); mh_dev_free(g->lev[l].cell_start); mh_dev_free(g->lev[l].gpts); }
+    mh_dev_free(g->cursor); mh_dev_free(g->pcell); mh_dev_free(g->part); mh_dev_free(g->resolved);
     delete g;
     c->knn = nullptr;
 }
@@ -526,14 +526,14 @@ int mh_knn_build(mh_ctx* c, cudaStream_t st) {
         g = new MhKnnGrid();
         memset(g, 0, sizeof(*g));
         const int64_t Mmax = std::max<int64_t>(d.M_max, 1);
-        cudaError_t e = cudaMalloc((void**)&g->cursor, sizeof(int) * KG_MAXCELLS);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&g->pcell, sizeof(int) * Mmax);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&g->part, sizeof(float) * 6 * 256);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&g->resolved, (size_t)d.T * d.N);
+        cudaError_t e = mh_dev_alloc((void**)&g->cursor, sizeof(int) * KG_MAXCELLS);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&g->pcell, sizeof(int) * Mmax);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&g->part, sizeof(float) * 6 * 256);
+        if (e == cudaSuccess) e = mh_dev_alloc((void**)&g->resolved, (size_t)d.T * d.N);
         for (int l = 0; l < KG_LEVELS && e == cudaSuccess; ++l) {
-            e = cudaMalloc((void**)&g->lev[l].bbox, sizeof(float) * 16);
-            if (e == cudaSuccess) e = cudaMalloc((void**)&g->lev[l].cell_start, sizeof(int) * (KG_MAXCELLS + 1 + 4096));
-            if (e == cudaSuccess) e = cudaMalloc((void**)&g->lev[l].gpts, sizeof(float4) * Mmax);
+            e = mh_dev_alloc((void**)&g->lev[l].bbox, sizeof(float) * 16);
+            if (e == cudaSuccess) e = mh_dev_alloc((void**)&g->lev[l].cell_start, sizeof(int) * (KG_MAXCELLS + 1 + 4096));
+            if (e == cudaSuccess) e = mh_dev_alloc((void**)&g->lev[l].gpts, sizeof(float4) * Mmax);
         }
         c->knn = g;
         if (e != cudaSuccess) { mh_knn_free(c); MH_FAIL(c, MH_E_CUDA, "contact grid: %s", cudaGetErrorString(e)); }

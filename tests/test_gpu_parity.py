@@ -796,3 +796,48 @@ def test_coarse_binning_and_capacity_errors(pkg, L):
     opt2.ctx.call('mh_debug_set_render_caps', 0, 64, 0)                        # 64 tile-list entries per body
     with pytest.raises(L.MhError, match='capacity'):
         gh.teacher_forced_cycle(opt2, g, data, meta, 31)
+
+
+class _PinnedLoader(object):
+    """Batches as slices of PINNED host tensors (what a DataLoader with pin_memory=True hands over)."""
+    def __init__(self, inputs, batch):
+        import torch
+        self.t = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in inputs.items()}
+        self.batch, self.T = batch, len(inputs['idxs'])
+
+    def __iter__(self):
+        for s in range(0, self.T, self.batch):
+            yield {k: v[s:s + self.batch] for k, v in self.t.items()}
+
+
+@pytest.mark.parametrize('mode', ['default', 'host', 'device'])
+def test_mask_ingest_paths_give_the_same_planes(pkg, L, mode, monkeypatch):
+    """float32 instance masks reach the device two ways -- packed to bit planes by the host cores (one process per host) or copied
+    full-size and packed on the device (one process per GPU) -- from pageable or pinned memory; the planes, the losses and the
+    gradients of a cycle do not depend on the way."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch = meta[:5]
+    out = {}
+    for which in ('reference', mode):
+        if which == 'reference':
+            monkeypatch.setenv('MH_INGEST_HOST_PACK', '1')                     # pageable source, host packing
+            loader = gh.ListLoader(data, 2)
+        else:
+            if mode == 'default':
+                monkeypatch.delenv('MH_INGEST_HOST_PACK', raising=False)
+            else:
+                monkeypatch.setenv('MH_INGEST_HOST_PACK', '1' if mode == 'host' else '0')
+            loader = _PinnedLoader(data, 2)
+        opt = gh.make_optimizer(pkg, g, data, meta)
+        gh.prepare(opt, g, data, meta, ingest=False)
+        opt._ingest(loader)
+        dep = np.zeros((T, H, W), np.float32); seg = np.zeros((T, N, H, W), np.float32)
+        opt.ctx.call('mh_read_planes', 0, T, L.ptr(dep), L.ptr(seg))
+        log, grads = gh.teacher_forced_cycle(opt, g, data, meta, 31)           # (ingested already: the planes above are used)
+        out[which] = (dep, seg, log, grads)
+        opt.ctx.close()
+    assert np.array_equal(out['reference'][0], out[mode][0]) and np.array_equal(out['reference'][1], out[mode][1])
+    assert np.array_equal(out[mode][1], data['seg_mask'].astype(np.float32))
+    assert out[mode][2] == out['reference'][2]
+    for nm in out[mode][3]:
+        assert np.array_equal(out[mode][3][nm], out['reference'][3][nm]), nm
