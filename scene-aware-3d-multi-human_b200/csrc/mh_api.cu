@@ -37,6 +37,7 @@ static int upload(mh_ctx* c, T** p, const std::vector<T>& h) {
 }
 
 int mh_upload_floats(mh_ctx* c, float** p, const std::vector<float>& h) { return upload(c, p, h); }
+int mh_alloc_floats(mh_ctx* c, float** p, int64_t n) { return dev_alloc(c, p, n); }      // zeroed, released by mh_destroy
 
 extern "C" const char* mh_version(void) { return "mhopt-b200 0.1 (sm_100a)"; }
 
@@ -260,7 +261,7 @@ extern "C" int mh_set_model(mh_ctx* c, const mh_model* m) {
     std::vector<int32_t> faces(m->faces, m->faces + (size_t)MH_F * 3);
     c->KW = KW; c->jnnz = (int)jvert.size(); c->rnnz = (int)rvert.size();
     MH_TRY(upload(c, &c->pext, pext));
-    MH_TRY(mh_gemm_tc_prepare(c, pext));
+    MH_TRY(mh_gemm_tc_prepare(c));
     MH_TRY(upload(c, &c->vtemplate, vt));
     MH_TRY(upload(c, &c->Jt, Jt));
     MH_TRY(upload(c, &c->Js, Js));

@@ -155,8 +155,9 @@ int mh_smpl_forward_run(mh_ctx* c, const MhSmplArgs& a, cudaStream_t st);
 int mh_gemm_fwd_tc(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape,
                    cudaStream_t st);          // mh_gemm_tc.cu: tcgen05 / TMEM, 3 x TF32
 int mh_gemm_bwd_tc(mh_ctx* c, const float* E, float* dpf_part, int M, int first_body, int nb_total, cudaStream_t st);
-int mh_gemm_tc_prepare(mh_ctx* c, const std::vector<float>& pext);      // builds pextF / pextB at mh_set_model
+int mh_gemm_tc_prepare(mh_ctx* c);                                          // builds pextF / pextB from c->pext at mh_set_model
 int mh_upload_floats(mh_ctx* c, float** p, const std::vector<float>& h);    // allocation owned by the context + H2D copy
+int mh_alloc_floats(mh_ctx* c, float** p, int64_t n);                       // zeroed allocation owned by the context
 int mh_gemm_bwd_simt(mh_ctx* c, const float* E, float* dpf_part, int M, int first_body, int nb_total, cudaStream_t st);
 int mh_gemm_fwd_simt(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape, cudaStream_t st);
 int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st);

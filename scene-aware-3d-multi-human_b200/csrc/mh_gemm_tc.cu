@@ -324,47 +324,58 @@ int mh_gemm_bwd_tc(mh_ctx* c, const float* E, float* dpf_part, int M, int first_
 
 // The constant operand of both contractions, split into TF32 hi | lo halves and laid out per (tile, chunk) exactly as the kernels
 // stage it in shared memory, so that one chunk is one contiguous block (one TMA bulk copy).
-static inline float tc_tf32_rna_host(float x) {             // cvt.rna.tf32.f32: nearest, ties away from zero, 10 mantissa bits kept
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    u = (u + 0x1000u) & 0xFFFFE000u;
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
+__device__ __forceinline__ float tc_tf32_rna_bits(float x) {       // cvt.rna.tf32.f32: nearest, ties away from zero, 10 mantissa bits kept
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
-int mh_gemm_tc_prepare(mh_ctx* c, const std::vector<float>& pext) {
-    auto split = [](float x, float& hi, float& lo) { hi = tc_tf32_rna_host(x); lo = tc_tf32_rna_host(x - hi); };
-    // forward: block (column tile nt, chunk it) = [hi: 8 k4 x 256 n units of 4 k | lo: same]
-    const int ntile = mh_cdiv(MH_LD3V, TC_BN), nit = MH_KPF / TC_BK;
-    std::vector<float> F((size_t)ntile * nit * (2 * TC_B_BYTES / 4), 0.f);
-    for (int nt = 0; nt < ntile; ++nt)
-        for (int it = 0; it < nit; ++it) {
-            float* hi = &F[((size_t)nt * nit + it) * (2 * TC_B_BYTES / 4)];
-            float* lo = hi + TC_B_BYTES / 4;
-            for (int k4 = 0; k4 < TC_BK / 4; ++k4)
-                for (int n = 0; n < TC_BN; ++n) {
-                    const int col = nt * TC_BN + n;
-                    if (col >= MH_LD3V) continue;
-                    for (int j = 0; j < 4; ++j)
-                        split(pext[(size_t)(it * TC_BK + 4 * k4 + j) * MH_LD3V + col], hi[(size_t)(k4 * TC_BN + n) * 4 + j], lo[(size_t)(k4 * TC_BN + n) * 4 + j]);
-                }
-        }
-    MH_TRY(mh_upload_floats(c, &c->pextF, F));
-    // backward: block (split ks, chunk it) = [hi: 8 k4 x 208 basis rows units of 4 k | lo: same]
-    const int nitb = TCB_KLEN / TC_BK;
-    std::vector<float> B((size_t)MH_KSPLIT * nitb * (2 * TCB_B_BYTES / 4), 0.f);
-    for (int ks = 0; ks < MH_KSPLIT; ++ks)
-        for (int it = 0; it < nitb; ++it) {
-            float* hi = &B[((size_t)ks * nitb + it) * (2 * TCB_B_BYTES / 4)];
-            float* lo = hi + TCB_B_BYTES / 4;
-            const int k0 = ks * TCB_KLEN + it * TC_BK;
-            for (int k4 = 0; k4 < TC_BK / 4; ++k4)
-                for (int n = 0; n < MH_NEXT; ++n)
-                    for (int j = 0; j < 4; ++j)
-                        split(pext[(size_t)n * MH_LD3V + k0 + 4 * k4 + j], hi[(size_t)(k4 * MH_NEXT + n) * 4 + j], lo[(size_t)(k4 * MH_NEXT + n) * 4 + j]);
-        }
-    MH_TRY(mh_upload_floats(c, &c->pextB, B));
+// forward operand: block (column tile nt, chunk it) = [hi: 8 k4 x 256 n units of 4 k | lo: same]; columns beyond MH_LD3V stay 0
+__global__ void k_tc_layout_fwd(const float* __restrict__ pext, float* __restrict__ F, int ntile, int nit) {
+    const int64_t total = (int64_t)ntile * nit * TC_BK * TC_BN;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(idx % TC_BN);
+        int64_t r = idx / TC_BN;
+        const int kk = (int)(r % TC_BK);                                 // 4 * k4 + j
+        r /= TC_BK;
+        const int it = (int)(r % nit), nt = (int)(r / nit);
+        const int col = nt * TC_BN + n;
+        if (col >= MH_LD3V) continue;
+        const float x = pext[(size_t)(it * TC_BK + kk) * MH_LD3V + col];
+        const float hi = tc_tf32_rna_bits(x), lo = tc_tf32_rna_bits(x - hi);
+        float* blk = F + ((size_t)nt * nit + it) * (2 * TC_B_BYTES / 4);
+        const size_t o = (size_t)((kk >> 2) * TC_BN + n) * 4 + (kk & 3);
+        blk[o] = hi;
+        blk[TC_B_BYTES / 4 + o] = lo;
+    }
+}
+
+// backward operand: block (split ks, chunk it) = [hi: 8 k4 x 208 basis rows units of 4 k | lo: same]
+__global__ void k_tc_layout_bwd(const float* __restrict__ pext, float* __restrict__ B, int nitb) {
+    const int64_t total = (int64_t)MH_KSPLIT * nitb * MH_NEXT * TC_BK;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(idx % TC_BK);
+        int64_t r = idx / TC_BK;
+        const int n = (int)(r % MH_NEXT);
+        r /= MH_NEXT;
+        const int it = (int)(r % nitb), ks = (int)(r / nitb);
+        const float x = pext[(size_t)n * MH_LD3V + ks * TCB_KLEN + it * TC_BK + kk];
+        const float hi = tc_tf32_rna_bits(x), lo = tc_tf32_rna_bits(x - hi);
+        float* blk = B + ((size_t)ks * nitb + it) * (2 * TCB_B_BYTES / 4);
+        const size_t o = (size_t)((kk >> 2) * MH_NEXT + n) * 4 + (kk & 3);
+        blk[o] = hi;
+        blk[TCB_B_BYTES / 4 + o] = lo;
+    }
+}
+
+// Both layouts are derived on the DEVICE from the extended basis c->pext that mh_set_model has just uploaded (on the host the two
+// strided passes over 4.3 M elements were most of the 50-80 ms of mh_set_model)
+int mh_gemm_tc_prepare(mh_ctx* c) {
+    const int ntile = mh_cdiv(MH_LD3V, TC_BN), nit = MH_KPF / TC_BK, nitb = TCB_KLEN / TC_BK;
+    MH_TRY(mh_alloc_floats(c, &c->pextF, (int64_t)ntile * nit * (2 * TC_B_BYTES / 4)));
+    MH_TRY(mh_alloc_floats(c, &c->pextB, (int64_t)MH_KSPLIT * nitb * (2 * TCB_B_BYTES / 4)));
+    k_tc_layout_fwd<<<2048, 256>>>(c->pext, c->pextF, ntile, nit);
+    k_tc_layout_bwd<<<2048, 256>>>(c->pext, c->pextB, nitb);
+    MH_CUDA(c, cudaGetLastError());
+    MH_CUDA(c, cudaStreamSynchronize(0));                                  // mh_set_model is a blocking call, as its uploads are
     return MH_OK;
 }
 
