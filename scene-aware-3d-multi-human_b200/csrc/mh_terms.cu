@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_contact(const float* __restrict
 // (a jump: the lowest vertex more than 6 h above the floor) is searched again on the next coarser one.  The grids are rebuilt with
 // the cloud (mh_set_scene / mh_set_scene_from_depth).
 #define KG_MAXCELLS (1 << 21)
+static_assert(KG_MAXCELLS / 1024 + 1 <= 4096, "k_kg_scan2 scans at most 4096 block sums");
 #define KG_RMAX 6
 #define KG_LEVELS 3
 #define KG_BUDGET 65536   // points one warp may visit on one level before it gives the person-frame up to the next level / the streaming kernel
@@ -373,6 +374,10 @@ __global__ void k_kg_count(const float* __restrict__ pts, int64_t M, const float
 __global__ void __launch_bounds__(1024) k_kg_scan1(int* __restrict__ a, const float* __restrict__ bbox, int* __restrict__ bsum) {
     __shared__ int s[1024];
     const int ncell = reinterpret_cast<const int*>(bbox + 8)[3];
+    if ((int)blockIdx.x * 1024 > ncell) {                                // beyond the grid of this cloud: nothing to add up
+        if (threadIdx.x == 0) bsum[blockIdx.x] = 0;
+        return;
+    }
     const int i = blockIdx.x * 1024 + threadIdx.x;
     const int v = (i < ncell) ? a[i] : 0;
     s[threadIdx.x] = v;
@@ -386,10 +391,22 @@ __global__ void __launch_bounds__(1024) k_kg_scan1(int* __restrict__ a, const fl
     if (i <= ncell) a[i] = s[threadIdx.x] - v;                  // exclusive inside the block (a[ncell] gets the block-local total so far)
     if (threadIdx.x == 1023) bsum[blockIdx.x] = s[1023];
 }
-__global__ void k_kg_scan2(int* __restrict__ bsum, int nblk) {
-    if (threadIdx.x != 0) return;
-    int run = 0;
-    for (int b = 0; b < nblk; ++b) { const int v = bsum[b]; bsum[b] = run; run += v; }
+// exclusive scan of the block sums by ONE block (nblk <= 4096: four consecutive entries per thread)
+__global__ void __launch_bounds__(1024) k_kg_scan2(int* __restrict__ bsum, int nblk) {
+    __shared__ int s[1024];
+    const int i0 = threadIdx.x * 4;
+    int v[4], t = 0;
+    for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < nblk) ? bsum[i0 + k] : 0; t += v[k]; }
+    s[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int u = (threadIdx.x >= o) ? s[threadIdx.x - o] : 0;
+        __syncthreads();
+        s[threadIdx.x] += u;
+        __syncthreads();
+    }
+    int run = s[threadIdx.x] - t;
+    for (int k = 0; k < 4; ++k) { if (i0 + k < nblk) bsum[i0 + k] = run; run += v[k]; }
 }
 __global__ void __launch_bounds__(1024) k_kg_scan3(int* __restrict__ a, const float* __restrict__ bbox, const int* __restrict__ bsum, int* __restrict__ cursor) {
     const int ncell = reinterpret_cast<const int*>(bbox + 8)[3];
@@ -555,7 +572,7 @@ int mh_knn_build(mh_ctx* c, cudaStream_t st) {
         MH_LAUNCHED(c);
         k_kg_scan1<<<nsb, 1024, 0, st>>>(v.cell_start, v.bbox, bsum);
         MH_LAUNCHED(c);
-        k_kg_scan2<<<1, 32, 0, st>>>(bsum, nsb);
+        k_kg_scan2<<<1, 1024, 0, st>>>(bsum, nsb);
         MH_LAUNCHED(c);
         k_kg_scan3<<<nsb, 1024, 0, st>>>(v.cell_start, v.bbox, bsum, g->cursor);
         MH_LAUNCHED(c);
