@@ -38,6 +38,7 @@ static int upload(mh_ctx* c, T** p, const std::vector<T>& h) {
 
 int mh_upload_floats(mh_ctx* c, float** p, const std::vector<float>& h) { return upload(c, p, h); }
 int mh_alloc_floats(mh_ctx* c, float** p, int64_t n) { return dev_alloc(c, p, n); }      // zeroed, released by mh_destroy
+int mh_alloc_ints(mh_ctx* c, int** p, int64_t n) { return dev_alloc(c, p, n); }
 
 extern "C" const char* mh_version(void) { return "mhopt-b200 0.1 (sm_100a)"; }
 
@@ -69,6 +70,7 @@ extern "C" int mh_create(mh_ctx** out, const mh_dims* dims) {
     c->scene_state = nullptr;
     c->scene_post = nullptr;
     c->knn = nullptr;
+    c->scene_counts = nullptr;
     c->comm = nullptr;
     c->M = 0;
     c->events = nullptr; c->timing = false; c->timing_iter = 0;

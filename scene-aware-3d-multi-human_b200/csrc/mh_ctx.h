@@ -121,6 +121,7 @@ struct mh_ctx {
     void* scene_state;         // mh_scene.cu
     void* scene_post;          // mh_scenepost.cu
     void* knn;                 // mh_terms.cu: uniform grid over the scene cloud for the contact term
+    int* scene_counts;         // mh_filter.cu: per-block point counts of the scene-cloud compaction
     void* comm;                // mh_comm.cu: the NCCL communicator this context owns (mh_set_comm), or null
     // stage timing (bench)
     cudaEvent_t* events; bool timing; int64_t timing_iter;
@@ -158,6 +159,7 @@ int mh_gemm_bwd_tc(mh_ctx* c, const float* E, float* dpf_part, int M, int first_
 int mh_gemm_tc_prepare(mh_ctx* c);                                          // builds pextF / pextB from c->pext at mh_set_model
 int mh_upload_floats(mh_ctx* c, float** p, const std::vector<float>& h);    // allocation owned by the context + H2D copy
 int mh_alloc_floats(mh_ctx* c, float** p, int64_t n);                       // zeroed allocation owned by the context
+int mh_alloc_ints(mh_ctx* c, int** p, int64_t n);
 int mh_gemm_bwd_simt(mh_ctx* c, const float* E, float* dpf_part, int M, int first_body, int nb_total, cudaStream_t st);
 int mh_gemm_fwd_simt(mh_ctx* c, const float* pf, const float* vshaped, float* vposed, int nbodies, int Npers, int per_body_shape, cudaStream_t st);
 int mh_smpl_backward_all(mh_ctx* c, cudaStream_t st);

@@ -109,10 +109,25 @@ __global__ void k_scene_count(const uint8_t* __restrict__ mask, int64_t HW, int*
     if (threadIdx.x == 0) counts[blockIdx.x] = s;
 }
 
-__global__ void k_scene_scan(int* __restrict__ counts, int n, int* __restrict__ total) {
-    int run = 0;                                                   // n <= a few thousand: one thread is plenty
-    for (int i = 0; i < n; ++i) { const int v = counts[i]; counts[i] = run; run += v; }
-    *total = run;
+// exclusive scan of the per-block counts by ONE block: thread t owns `per` consecutive entries (a serial chain of n dependent global
+// accesses by one thread was 0.2 ms at 512x512 and 1.6 ms at 1080p)
+__global__ void __launch_bounds__(1024) k_scene_scan(int* __restrict__ counts, int n, int* __restrict__ total) {
+    __shared__ int s[1024];
+    const int per = (n + 1023) / 1024, i0 = threadIdx.x * per;
+    int t = 0;
+    for (int k = 0; k < per; ++k) if (i0 + k < n) t += counts[i0 + k];
+    s[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int u = (threadIdx.x >= o) ? s[threadIdx.x - o] : 0;
+        __syncthreads();
+        s[threadIdx.x] += u;
+        __syncthreads();
+    }
+    int run = s[threadIdx.x] - t;
+    for (int k = 0; k < per; ++k)
+        if (i0 + k < n) { const int v = counts[i0 + k]; counts[i0 + k] = run; run += v; }
+    if (threadIdx.x == 1023) *total = s[1023];
 }
 
 __global__ void k_scene_scatter(const float* __restrict__ depth, const uint8_t* __restrict__ mask, int W, int64_t HW,
@@ -143,26 +158,24 @@ int mh_scene_from_depth(mh_ctx* c, const float* depth_dev, const uint8_t* mask_d
     const mh_dims& d = c->d;
     const int64_t HW = (int64_t)d.H * d.W;
     const int nblk = mh_cdiv(HW, SC_BLOCK);
-    int* counts;
-    MH_CUDA(c, mh_dev_alloc((void**)&counts, sizeof(int) * (nblk + 1)));
+    if (!c->scene_counts) MH_TRY(mh_alloc_ints(c, &c->scene_counts, nblk + 1));      // kept: no allocation / free (= device synchronisation) per scene update
+    int* counts = c->scene_counts;
     k_scene_count<<<nblk, SC_BLOCK, 0, st>>>(mask_dev, HW, counts);
     c->launches++;
-    k_scene_scan<<<1, 1, 0, st>>>(counts, nblk, counts + nblk);
+    k_scene_scan<<<1, 1024, 0, st>>>(counts, nblk, counts + nblk);
     c->launches++;
     int total = 0;
     cudaMemcpyAsync(&total, counts + nblk, sizeof(int), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { mh_dev_free(counts); MH_CUDA(c, e); }
-    if (total > d.M_max) { mh_dev_free(counts); MH_FAIL(c, MH_E_CAPACITY, "scene cloud of %d points exceeds M_max = %lld", total, (long long)d.M_max); }
+    MH_CUDA(c, e);
+    if (total > d.M_max) MH_FAIL(c, MH_E_CAPACITY, "scene cloud of %d points exceeds M_max = %lld", total, (long long)d.M_max);
     // A = K[:2,:2]^T = [[k00, k10], [k01, k11]] ; inverse in closed form
     const float a = c->K[0], b = c->K[3], cc = c->K[1], dd = c->K[4];
     const float det = a * dd - b * cc;
     const float i00 = dd / det, i01 = -b / det, i10 = -cc / det, i11 = a / det;
     k_scene_scatter<<<nblk, SC_BLOCK, 0, st>>>(depth_dev, mask_dev, d.W, HW, counts, c->K[2], c->K[5], i00, i01, i10, i11, d.M_max, c->scene);
     c->launches++;
-    e = cudaStreamSynchronize(st);
-    mh_dev_free(counts);
-    MH_CUDA(c, e);
+    MH_CUDA(c, cudaGetLastError());
     if (total > 0 && total < MH_KNN) MH_FAIL(c, MH_E_ARG, "scene cloud has only %d points (< %d)", total, MH_KNN);
     c->M = total;
     return mh_knn_build(c, st);

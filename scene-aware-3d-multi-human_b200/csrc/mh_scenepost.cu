@@ -21,6 +21,7 @@
 
 #define SP_LUT 4096
 #define SP_MAXOFF 81
+#define SP_SWEEPS 4          // fill-in sweeps enqueued per host look at the hole counters
 #define SP_NPART 256
 
 struct MhScenePost {
@@ -204,7 +205,7 @@ static MhScenePost* post_state(mh_ctx* c, int64_t HW) {
     if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->lut, sizeof(float) * (SP_LUT + 4));
     if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->part, sizeof(double) * 4 * SP_NPART);
     if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->stat, sizeof(double) * 8);
-    if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->holes, sizeof(int) * 2);
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->holes, sizeof(int) * 2 * SP_SWEEPS);
     if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->offw, sizeof(float) * SP_MAXOFF);
     if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->offdy, sizeof(int) * SP_MAXOFF);
     if (e == cudaSuccess) e = mh_dev_alloc((void**)&s->offdx, sizeof(int) * SP_MAXOFF);
@@ -295,19 +296,26 @@ int mh_scene_postprocess_dev(mh_ctx* c, const float* depth_dev, const uint8_t* m
     MH_LAUNCHED(c);
     k_sp_erode<<<g2d, 256, 0, st>>>(e1, d.H, d.W, mask_dev, s->msk[0]);
     MH_LAUNCHED(c);
-    // fill-in sweeps until no hole is left (or no hole can be reached any more: an all-hole image)
+    // fill-in sweeps until no hole is left (or no hole can be reached any more: an all-hole image).  SP_SWEEPS sweeps are enqueued per
+    // look at the hole counters: a sweep over an image without holes is a plain copy, so the sweeps past the last useful one change
+    // nothing -- and the host waits for the device once per group instead of once per sweep
     int cur = 0;
     const dim3 gfill(mh_cdiv(d.W, 32), mh_cdiv(d.H, 4));
-    for (int sweep = 0; sweep < d.H + d.W; ++sweep) {
-        MH_CUDA(c, cudaMemsetAsync(s->holes, 0, sizeof(int) * 2, st));
-        k_sp_fill<<<gfill, 128, 0, st>>>(s->dep[cur], s->msk[cur], d.H, d.W, fillin_ksize / 2, s->dep[cur ^ 1], s->msk[cur ^ 1], s->holes);
-        MH_LAUNCHED(c);
-        int h[2];
+    bool done = false;
+    for (int sweep = 0; sweep < d.H + d.W && !done; sweep += SP_SWEEPS) {
+        MH_CUDA(c, cudaMemsetAsync(s->holes, 0, sizeof(int) * 2 * SP_SWEEPS, st));
+        for (int g = 0; g < SP_SWEEPS; ++g) {
+            k_sp_fill<<<gfill, 128, 0, st>>>(s->dep[cur], s->msk[cur], d.H, d.W, fillin_ksize / 2, s->dep[cur ^ 1], s->msk[cur ^ 1], s->holes + 2 * g);
+            MH_LAUNCHED(c);
+            cur ^= 1;
+        }
+        int h[2 * SP_SWEEPS];
         MH_CUDA(c, cudaMemcpyAsync(h, s->holes, sizeof(h), cudaMemcpyDeviceToHost, st));
         MH_CUDA(c, cudaStreamSynchronize(st));
-        cur ^= 1;
-        if (h[0] == 0) break;
-        if (h[1] == 0) MH_FAIL(c, MH_E_STATE, "scene post-processing: %d pixels can never be filled in (empty keep-mask)", h[0]);
+        for (int g = 0; g < SP_SWEEPS && !done; ++g) {
+            if (h[2 * g] == 0) done = true;
+            else if (h[2 * g + 1] == 0) MH_FAIL(c, MH_E_STATE, "scene post-processing: %d pixels can never be filled in (empty keep-mask)", h[2 * g]);
+        }
     }
     s->result = cur;
     s->ready = true;

@@ -66,3 +66,21 @@ print('init loss_2d', float(init_log[0]['loss_2d']), '->', float(init_log[-1]['l
 print('fit log first/last:', {k: (round(log[0][k], 5), round(log[-1][k], 5)) for k in log[0]})
 print('scene points', v['scene_depth'].shape if v['scene_depth'] is not None else None, 'translation error after fit (m, mean)', float(np.abs(v['poses_T'][:, :, 0] - gt).mean()))
 pstats.Stats(pr).sort_stats('cumulative').print_stats(14)
+
+# the per-cycle scene update taken apart (CUDA events on the launch stream, mean of 5)
+st = opt._stream()
+evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+acc = np.zeros(3)
+for _ in range(5):
+    evs[0].record()
+    opt._median_passes(0)
+    evs[1].record()
+    opt.ctx.call('mh_scene_update_from_median', 1, 7, None, st)
+    evs[2].record()
+    opt.ctx.call('mh_fit_cycle_grads', st)
+    evs[3].record()
+    torch.cuda.synchronize()
+    acc += [evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])]
+acc /= 5
+print(f'scene update: temporal median (10 radix passes over {T} frames) {acc[0]:.2f} ms | post-processing + point cloud + contact grids {acc[1]:.2f} ms '
+      f'| gradients of the cycle {acc[2]:.2f} ms')
