@@ -277,6 +277,9 @@ int mh_debug_knn_stats(mh_ctx* ctx, int64_t* out4, void* stream);
  * creates one optimiser per sequence): mh_destroy parks them, mh_create takes buffers of the same size back.  mh_pool_trim returns the
  * parked buffers to the driver (done automatically when an allocation fails), mh_pool_bytes says how much is parked.  MH_POOL=0 in
  * the environment turns the recycling off. */
+/* testing aid, host only: float32 {0, 1} masks (count, N, HW) -> one 32-bit plane per frame (bit n = person n), as mh_ingest_frames packs
+ * them with all cores; returns 1 when a value other than 0 / 1 was seen (mh_finalize_ingest then fails), 0 otherwise */
+int mh_debug_pack_masks(const float* seg_host, int32_t count, int32_t N, int64_t HW, uint32_t* out_host);
 void mh_pool_trim(void);
 int64_t mh_pool_bytes(void);
 /* testing aid: the pose-corrective contraction alone, C (M, 20672) = A (M, 192) . posedirs, HOST pointers, blocking; use_tc = 1 runs

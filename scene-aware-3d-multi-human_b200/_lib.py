@@ -109,6 +109,7 @@ def _load():
         'mh_read_timing': (c_int32, [ctx, c_void_p, ctypes.POINTER(c_int32)]),
         'mh_debug_set_render_caps': (c_int32, [ctx, c_int32, c_int32, c_int32]),
         'mh_debug_knn_stats': (c_int32, [ctx, c_void_p, c_void_p]),
+        'mh_debug_pack_masks': (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_void_p]),
         'mh_pool_trim': (None, []),
         'mh_pool_bytes': (c_int64, []),
         'mh_debug_gemm_fwd': (c_int32, [ctx, c_void_p, c_void_p, c_int32, c_int32]),

@@ -388,6 +388,13 @@ static bool pack_masks_host(const float* seg, int count, int N, int64_t HW, uint
     return bad.load() != 0;
 }
 
+// testing aid (no device involved): the host packing of float32 masks (count, N, HW) into one 32-bit plane per frame; returns 1 when
+// a value other than 0 / 1 was seen, 0 otherwise, MH_E_ARG on bad arguments
+extern "C" int mh_debug_pack_masks(const float* seg, int32_t count, int32_t N, int64_t HW, uint32_t* out) {
+    if (!seg || !out || count < 1 || N < 1 || N > MH_MAXN || HW < 1) return MH_E_ARG;
+    return pack_masks_host(seg, count, N, HW, out) ? 1 : 0;
+}
+
 static int ingest_frames(mh_ctx* c, int32_t t0, int32_t count, const float* depths, const void* seg, int seg_is_u8, const float* pose2d,
                          const float* theta_ref, const float* valid, void* stream) {
     API_BEGIN(c);

@@ -122,3 +122,25 @@ def test_one_euro_over_time_matches_the_reference_filter(pkg):
         assert np.array_equal(got[0], x[0]) and not np.array_equal(got[1:], x[1:])
     one = opt.one_euro_over_time(x[:1], 0.1, 0.1)
     assert np.array_equal(one, x[:1])                                             # a single frame passes through
+
+
+@pytest.mark.parametrize('count,N,HW', [(1, 1, 1), (3, 8, 1000), (2, 32, 4099), (5, 3, 2048 * 3 + 17)])
+def test_host_mask_packing_matches_numpy(pkg, count, N, HW):
+    """The host side of the ingest (``optimizer.py:396-409``): float32 {0., 1.} instance masks -> one 32-bit plane per frame, bit n =
+    person n, packed by all cores with the widest vector unit of the host (function multi-versioning); ragged sizes that straddle
+    the 2048-pixel work items and frame boundaries, and the non-binary flag."""
+    L = _mod(pkg, '_lib')
+    rng = np.random.default_rng(count * 131 + N)
+    seg = (rng.random((count, N, HW)) > 0.6).astype(np.float32)
+    out = np.full((count, HW), 0xdeadbeef, np.uint32)
+    rc = L.lib.mh_debug_pack_masks(L.ptr(seg), count, N, HW, L.ptr(out))
+    assert rc == 0
+    ref = np.zeros((count, HW), np.uint32)
+    for n in range(N):
+        ref |= (seg[:, n] != 0).astype(np.uint32) << np.uint32(n)
+    assert np.array_equal(out, ref)
+    seg[count - 1, N - 1, HW - 1] = 0.5                                        # not a mask value: reported, still counted as set
+    rc = L.lib.mh_debug_pack_masks(L.ptr(seg), count, N, HW, L.ptr(out))
+    assert rc == 1 and (out[count - 1, HW - 1] >> np.uint32(N - 1)) & 1 == 1
+    assert L.lib.mh_debug_pack_masks(L.ptr(seg), 0, N, HW, L.ptr(out)) < 0     # bad arguments
+    assert L.lib.mh_pool_bytes() == 0                                           # nothing parked without a device
