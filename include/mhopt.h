@@ -275,8 +275,8 @@ int mh_debug_set_render_caps(mh_ctx* ctx, int32_t maxbins, int32_t bincap, int32
 int mh_debug_knn_stats(mh_ctx* ctx, int64_t* out4, void* stream);
 /* Device buffers of 256 KB and more are recycled between the contexts of a process (a job that fits many sequences, predict.py:315-357,
  * creates one optimiser per sequence): mh_destroy parks them, mh_create takes buffers of the same size back.  mh_pool_trim returns the
- * parked buffers to the driver (done automatically when an allocation fails), mh_pool_bytes says how much is parked.  MH_POOL=0 in
- * the environment turns the recycling off. */
+ * parked buffers to the driver (done automatically when an allocation fails), mh_pool_bytes says how much is parked (at most 32 GB,
+ * MH_POOL_MAX_GB in the environment).  MH_POOL=0 turns the recycling off. */
 /* testing aid, host only: float32 {0, 1} masks (count, N, HW) -> one 32-bit plane per frame (bit n = person n), as mh_ingest_frames packs
  * them with all cores; returns 1 when a value other than 0 / 1 was seen (mh_finalize_ingest then fails), 0 otherwise */
 int mh_debug_pack_masks(const float* seg_host, int32_t count, int32_t N, int64_t HW, uint32_t* out_host);

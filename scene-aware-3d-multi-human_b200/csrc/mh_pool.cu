@@ -4,7 +4,8 @@
 // cycles.  Buffers of 256 KB and more that a context frees are kept here, keyed by (device, size), and handed to the next request of
 // exactly that size (NOT cleared: every buffer the library needs zeroed is cleared where it is allocated; MH_POOL_POISON=1 fills recycled
 // buffers with 0xff bytes to prove it).  When the device runs out of memory the pool is emptied and the request repeated.  MH_POOL=0 turns
-// the pool off; mh_pool_trim() returns everything to the driver.
+// the pool off; mh_pool_trim() returns everything to the driver; at most 32 GB (MH_POOL_MAX_GB) are parked at a time, so that other
+// allocators of the process (torch's) are not starved by contexts of many different shapes.
 #include "mh_ctx.h"
 
 #include <map>
@@ -17,10 +18,13 @@ struct Pool {
     std::unordered_map<void*, std::pair<int, size_t>> live;          // pooled-size buffers in use: pointer -> (device, bytes)
     std::multimap<std::pair<int, size_t>, void*> idle;                // free buffers
     size_t idle_bytes = 0;
+    size_t cap = (size_t)32 << 30;                                    // most bytes parked at a time (MH_POOL_MAX_GB)
     bool on = true, poison = false;
     Pool() {
         const char* v = getenv("MH_POOL");
         on = !(v && atoi(v) == 0);
+        v = getenv("MH_POOL_MAX_GB");
+        if (v && atof(v) >= 0) cap = (size_t)(atof(v) * (double)(1 << 30));
         v = getenv("MH_POOL_POISON");
         poison = v && atoi(v) != 0;
     }
@@ -83,6 +87,10 @@ cudaError_t mh_dev_free(void* p) {
     {
         std::lock_guard<std::mutex> g(P.m);
         auto it = P.live.find(p);
+        if (it != P.live.end() && P.idle_bytes + it->second.second > P.cap) {      // the pool is full: back to the driver
+            P.live.erase(it);
+            it = P.live.end();
+        }
         if (it != P.live.end()) {
             P.idle.insert({it->second, p});
             P.idle_bytes += it->second.second;
