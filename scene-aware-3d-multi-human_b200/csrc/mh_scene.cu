@@ -91,12 +91,20 @@ __device__ __forceinline__ uint32_t depth_bits(float d, float a, float b) {
     return __float_as_uint(__fdiv_rn(1.0f, __fadd_rn(__fmul_rn(d, a), b)));        // 1 / target_disp, rounded like torch
 }
 
+// The passes over the T frames of a pixel are bound by memory LATENCY when every iteration waits for its own mask byte and then for
+// its depth (one dependent pair in flight per thread: measured 4x off the HBM bound).  MED_U frames are therefore loaded first, both
+// planes unconditionally, with volatile loads the compiler may neither sink below the mask test nor reorder, and judged afterwards.
+#define MED_U 8
+__device__ __forceinline__ float ld_f32_issue(const float* p) { float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
+__device__ __forceinline__ unsigned ld_u8_issue(const uint8_t* p) { unsigned v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
 // ---- depth passes ---------------------------------------------------------------------------------------------------
 // pass 0: valid-frame count.  hist[0] = local count.
 __global__ void k_med_count(const uint8_t* __restrict__ back, int T, int64_t HW, float* __restrict__ hist) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
     int n = 0;
+#pragma unroll 8
     for (int t = 0; t < T; ++t) n += back[(size_t)t * HW + p] != 0;
     hist[p] = (float)n;
 }
@@ -120,13 +128,25 @@ __global__ void k_med_digit_depth(const float* __restrict__ depth, const uint8_t
     const uint32_t himask = shift >= 28 ? 0u : (0xffffffffu << (shift + 4));
     unsigned long long lo = 0ull, hi = 0ull;            // 16 counters of 8 bits would overflow: two words of 4 x 16-bit lanes per half
     unsigned long long lo2 = 0ull, hi2 = 0ull;
-    for (int t = 0; t < T; ++t) {
-        if (!back[(size_t)t * HW + p]) continue;
-        const uint32_t b = depth_bits(depth[(size_t)t * HW + p], ab[2 * t], ab[2 * t + 1]);
-        if ((b & himask) != pre) continue;
-        const uint32_t dg = (b >> shift) & 15u;
-        const unsigned long long one = 1ull << ((dg & 3u) * 16);
-        switch (dg >> 2) { case 0: lo += one; break; case 1: hi += one; break; case 2: lo2 += one; break; default: hi2 += one; }
+    for (int t0 = 0; t0 < T; t0 += MED_U) {
+        unsigned bk[MED_U];
+        float dv[MED_U];
+#pragma unroll
+        for (int j = 0; j < MED_U; ++j) {
+            const size_t o = (size_t)min(t0 + j, T - 1) * HW + p;
+            bk[j] = ld_u8_issue(back + o);
+            dv[j] = ld_f32_issue(depth + o);
+        }
+#pragma unroll
+        for (int j = 0; j < MED_U; ++j) {
+            const int t = t0 + j;
+            if (t >= T || !bk[j]) continue;
+            const uint32_t b = depth_bits(dv[j], ab[2 * t], ab[2 * t + 1]);
+            if ((b & himask) != pre) continue;
+            const uint32_t dg = (b >> shift) & 15u;
+            const unsigned long long one = 1ull << ((dg & 3u) * 16);
+            switch (dg >> 2) { case 0: lo += one; break; case 1: hi += one; break; case 2: lo2 += one; break; default: hi2 += one; }
+        }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -160,10 +180,22 @@ __global__ void k_med_upper_depth(const float* __restrict__ depth, const uint8_t
     const uint32_t m = prefix[p];
     int le = 0;
     uint32_t above = 0x7f800000u;
-    for (int t = 0; t < T; ++t) {
-        if (!back[(size_t)t * HW + p]) continue;
-        const uint32_t b = depth_bits(depth[(size_t)t * HW + p], ab[2 * t], ab[2 * t + 1]);
-        if (b <= m) ++le; else above = min(above, b);
+    for (int t0 = 0; t0 < T; t0 += MED_U) {
+        unsigned bk[MED_U];
+        float dv[MED_U];
+#pragma unroll
+        for (int j = 0; j < MED_U; ++j) {
+            const size_t o = (size_t)min(t0 + j, T - 1) * HW + p;
+            bk[j] = ld_u8_issue(back + o);
+            dv[j] = ld_f32_issue(depth + o);
+        }
+#pragma unroll
+        for (int j = 0; j < MED_U; ++j) {
+            const int t = t0 + j;
+            if (t >= T || !bk[j]) continue;
+            const uint32_t b = depth_bits(dv[j], ab[2 * t], ab[2 * t + 1]);
+            if (b <= m) ++le; else above = min(above, b);
+        }
     }
     aux[p] = (float)le;
     aux[3 * HW + p] = __uint_as_float(above);
