@@ -44,6 +44,7 @@
 #endif
 
 struct MhRenderScratch {
+    int* cost; int* work; bool have_cost;        // cycles each body took in the previous launch, bodies sorted by them (longest first)
     uint16_t* binlist; int bincap;
     uint2* fbin;
     int* wpix; int* wface; float* wz; int wcap;
@@ -64,6 +65,8 @@ struct RenderParams {
     const uint8_t* pose2d_valid; const uint8_t* mask_valid;
     const float* zmin_lin; const float* zmax_lin;
     float* pfout; int* devflags;
+    int* cost;                    // out: clock cycles this launch spent on body i (feeds the next launch's order)
+    const int* work;              // bodies in the order they are handed out (longest first by the previous launch's cycles); NULL: by depth rank
     int nslab;                    // depth slabs of the tile lists (<= 256)
     long long* gsg;               // per-CTA NDC-gradient rows (MH_LD3V 64-bit fixed-point sums each), zero between bodies
     uint16_t* binlist; int bincap;
@@ -381,8 +384,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
         // rasterised first, the small far ones fill the tail
         int t, n;
         if (MODE == 1) { t = wi / P.N; n = wi % P.N; }
+        else if (P.work) { const int iw = P.work[wi]; t = iw / P.N; n = iw - t * P.N; }
         else { t = wi % P.T; n = P.order[t * P.N + wi / P.T]; }
         const int i = t * P.N + n;
+        if (MODE == 0 && tid == 0) { const long long now = clock64(); sint[42] = (int)(now & 0xffffffffll); sint[43] = (int)(now >> 32); }
         const size_t b = (size_t)i + P.N;                                // slot-major body (slot 0 is the halo)
         // ---- P0: TMA bulk copy of the vertex row, then world -> NDC in place ----
         if (tid == 0) {
@@ -851,6 +856,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_render(RenderParams P) {
             dv[3 * v + 1] += -P.k11 * iz * gy;
             dv[3 * v + 2] += (P.k00 * X * gx + P.k11 * Y * gy) * iz * iz + gz;
         }
+        if (MODE == 0 && tid == 0) {
+            const long long t0c = ((long long)sint[43] << 32) | (unsigned)sint[42];
+            P.cost[i] = (int)min(clock64() - t0c, 0x7fffffffll);
+        }
         __syncthreads();
         PROF(6);
     }
@@ -876,6 +885,11 @@ int mh_render_alloc(mh_ctx* c) {
     if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->counter, sizeof(int));
     if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->gsg, n * MH_LD3V * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemset(rs->gsg, 0, n * MH_LD3V * sizeof(long long));
+    const size_t tn = (size_t)c->d.T * c->d.N;
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->cost, tn * sizeof(int));
+    if (e == cudaSuccess) e = mh_dev_alloc((void**)&rs->work, tn * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(rs->cost, 0, tn * sizeof(int));
+    rs->have_cost = false;
     { const char* v = getenv("MH_RENDER_NSLAB"); rs->nslab = v ? std::min(std::max(atoi(v), 1), 256) : R_NSLAB; }     // development switch
     rs->prof = nullptr;
     if (e != cudaSuccess) MH_FAIL(c, MH_E_CUDA, "render scratch: %s", cudaGetErrorString(e));
@@ -889,7 +903,7 @@ int mh_render_alloc(mh_ctx* c) {
 void mh_render_free(mh_ctx* c) {
     if (!c->rs) return;
     if (c->rs->prof) mh_dev_free(c->rs->prof);
-    mh_dev_free(c->rs->fbin); mh_dev_free(c->rs->gsg);
+    mh_dev_free(c->rs->fbin); mh_dev_free(c->rs->gsg); mh_dev_free(c->rs->cost); mh_dev_free(c->rs->work);
     mh_dev_free(c->rs->binlist); mh_dev_free(c->rs->wpix); mh_dev_free(c->rs->wface); mh_dev_free(c->rs->wz); mh_dev_free(c->rs->counter);
     delete c->rs;
     c->rs = nullptr;
@@ -906,6 +920,7 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     P.pfout = c->pfout; P.devflags = c->devflags;
     P.binlist = c->rs->binlist; P.bincap = c->rs->bincap; P.fbin = c->rs->fbin; P.wpix = c->rs->wpix; P.wface = c->rs->wface; P.wz = c->rs->wz; P.wcap = c->rs->wcap;
     P.counter = c->rs->counter; P.gsg = c->rs->gsg; P.nslab = c->rs->nslab;
+    P.cost = c->rs->cost; P.work = nullptr;
     P.maxbins = c->rs->maxbins;
     if (c->rs->bincap_use) P.bincap = c->rs->bincap_use;
     if (c->rs->wcap_use) P.wcap = c->rs->wcap_use;
@@ -922,8 +937,35 @@ static RenderParams render_params(mh_ctx* c, float blur_d, float blur_s) {
     return P;
 }
 
+// hand-out order of the next launch: bodies by the cycles they took in the last one, longest first (ties by index).  Rank sort: every
+// thread counts the bodies ahead of its own -- n^2 compares, 17 M at C3, spread over n threads
+__global__ void __launch_bounds__(256) k_render_rank(const int* __restrict__ cost, int n, int* __restrict__ work) {
+    __shared__ int sc[256];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int ci = i < n ? cost[i] : 0;
+    int rank = 0;
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        __syncthreads();
+        sc[threadIdx.x] = (j0 + threadIdx.x < n) ? cost[j0 + threadIdx.x] : -1;
+        __syncthreads();
+        const int m = min(256, n - j0);
+        for (int k = 0; k < m; ++k) { const int cj = sc[k]; rank += (cj > ci) || (cj == ci && j0 + k < i); }
+    }
+    if (i < n) work[rank] = i;
+}
+
 int mh_render_all(mh_ctx* c, cudaStream_t st) {
     RenderParams P = render_params(c, 1e-4f, 2e-5f);          // optimizer.py:213, 223
+    const int TNb = c->d.T * c->d.N;
+    static const int use_cost = [] { const char* v = getenv("MH_RENDER_COST_ORDER"); return v ? atoi(v) : 1; }();
+    if (use_cost && c->rs->have_cost) {
+        // bodies differ 10x in projected size and a rank holds only a few per CTA when the frames are sharded: the measured cost of
+        // the previous cycle is a far better predictor of this cycle's than the depth rank alone
+        k_render_rank<<<mh_cdiv(TNb, 256), 256, 0, st>>>(c->rs->cost, TNb, c->rs->work);
+        MH_LAUNCHED(c);
+        P.work = c->rs->work;
+    }
+    c->rs->have_cost = true;
     MH_CUDA(c, cudaMemsetAsync(c->rs->counter, 0, sizeof(int), st));
     const int grid = std::min(c->rs->nctas, c->d.T * c->d.N);
     k_render<0><<<grid, R_THREADS, c->rs->smem, st>>>(P);
