@@ -32,6 +32,9 @@ from . import sharding
 from . import smpl_io
 
 L = _lib
+# outputs of the reference's SMPL layer with 17 joints (smpl.py:368-381); 'joints_mupots' only exists there when the layer is given
+# that regressor, which the reference optimiser does not do (optimizer.py:69-72) -- accepted here as an extension
+_SPARSE_REGRESSORS = {'joints_alphapose': 'J_regressor_alphapose', 'joints_h36m17': 'J_regressor_h36m17', 'joints_mupots': 'J_regressor_mupots'}
 _LIB_COMMS = {}              # (process group, rank, world, device) -> handle of mh_comm_create, kept for the life of the process
 
 
@@ -86,12 +89,17 @@ class SMPLOptimizerBase(object):
                  process_group=None, scene_update=True, max_scene_points=None, allow_partial_loader=False):
         self.device_ordinal = _device_ordinal(device)
         self.device = torch.device('cuda', self.device_ordinal)
-        if smpl_sparse_joints_key != 'joints_alphapose':
-            raise NotImplementedError('only the AlphaPose 17-joint regressor is wired into the kernels '
-                                      '(the reference default, optimizer.py:40)')
+        # the sparse joints the 2-D terms compare with ``pose2d`` (``optimizer.py:40, 696, 750``): either 17-joint regressor of the
+        # reference's SMPL layer (``smpl.py:376-381``)
+        if smpl_sparse_joints_key not in _SPARSE_REGRESSORS:
+            raise ValueError(f"smpl_sparse_joints_key must be one of {sorted(_SPARSE_REGRESSORS)} (17-joint regressors, "
+                             f"smpl.py:376-381), got '{smpl_sparse_joints_key}'")
         self.smpl_model_parameters_path = os.path.abspath(smpl_model_parameters_path)
         self.smpl_sparse_joints_key = smpl_sparse_joints_key
-        self.model = smpl_io.load_smpl_model(smpl_model_parameters_path, alphapose_regressor=smpl_J_reg_alphapose_path)
+        self.model = smpl_io.load_smpl_model(smpl_model_parameters_path, alphapose_regressor=smpl_J_reg_alphapose_path,
+                                             h36m_regressor=smpl_J_reg_h37m_path)
+        if _SPARSE_REGRESSORS[smpl_sparse_joints_key] not in self.model:
+            raise FileNotFoundError(f"the regressor of '{smpl_sparse_joints_key}' is not in {smpl_model_parameters_path}")
         self.faces_smpl = self.model['faces']
         w24 = np.ones(24, np.float32) if pose24j_weights is None else np.array(pose24j_weights, np.float32)
         self.pose24j_weights = len(w24) * w24 / np.sum(w24)
@@ -181,7 +189,7 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         self.ctx = L.Context(self.T_local, N, self.img_h, self.img_w, B=Bq, device=self.device_ordinal,
                              rank=self.rank if self._dist else 0, world=self.world if self._dist else 1, t0=self.t0, T_total=T_total,
                              M_max=self.max_scene_points if self.max_scene_points else self.img_h * self.img_w)
-        self.ctx.set_model(self.model)
+        self.ctx.set_model(self.model, _SPARSE_REGRESSORS[self.smpl_sparse_joints_key])
         self.ctx.set_camera(self.cam_K, self.K_ndc, self.cam_dist_coef)
         self.ctx.set_coefs(**self.coefs)
         w = np.ascontiguousarray(self.pose17j_weights, np.float32)

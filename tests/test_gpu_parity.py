@@ -841,3 +841,25 @@ def test_mask_ingest_paths_give_the_same_planes(pkg, L, mode, monkeypatch):
     assert out[mode][2] == out['reference'][2]
     for nm in out[mode][3]:
         assert np.array_equal(out[mode][3][nm], out['reference'][3][nm]), nm
+
+
+def test_sparse_joints_key_selects_the_regressor(pkg, L):
+    """``smpl_sparse_joints_key`` (``optimizer.py:40, 696, 750``): the 2-D terms use the 17 joints of the chosen output of the SMPL
+    layer -- 'joints_alphapose' (default) or 'joints_h36m17' (H36M regressor in the layer's row order, ``smpl.py:240-242``)."""
+    g, data, meta = gh.load_fit('fit_n2.npz')
+    N, T, W, H, batch = meta[:5]
+    with pytest.raises(ValueError, match='smpl_sparse_joints_key'):
+        gh.make_optimizer(pkg, g, data, meta, smpl_sparse_joints_key='joints_smpl24')
+    out = {}
+    for key in ('joints_alphapose', 'joints_h36m17'):
+        opt = gh.make_optimizer(pkg, g, data, meta, smpl_sparse_joints_key=key)
+        gh.prepare(opt, g, data, meta, ingest=False)
+        betas = np.ascontiguousarray(np.tile(g['init_betas'].reshape(1, N, 10), (T, 1, 1)).reshape(T * N, 10), np.float32)
+        poses = np.ascontiguousarray(data['poses_smpl'].reshape(T * N, 72), np.float32)
+        verts, joints = opt.smpl_forward(betas, poses)
+        reg = opt.model['J_regressor_alphapose' if key == 'joints_alphapose' else 'J_regressor_h36m17']
+        ref = np.einsum('jv,bvk->bjk', reg.astype(np.float64), np.asarray(verts, np.float64).reshape(T * N, L.V, 3))
+        assert np.abs(np.asarray(joints).reshape(T * N, 17, 3) - ref).max() <= 5e-6
+        out[key] = np.asarray(joints).copy()
+        opt.ctx.close()
+    assert np.abs(out['joints_alphapose'] - out['joints_h36m17']).max() > 1e-3       # different regressors, different joints

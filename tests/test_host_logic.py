@@ -36,6 +36,10 @@ def test_model_loader_matches_the_oracle_loader(pkg, model_dir):
         assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
     with pytest.raises(FileNotFoundError):
         io.load_smpl_model('/nonexistent/dir')
+    # the 17-joint H36M regressor is stored in H36M order and used in the reference layer's row order (smpl.py:240-242)
+    raw = np.load(os.path.join(model_dir, 'J_regressor_h36m.npy'))
+    assert a['J_regressor_h36m17'].shape == (17, 6890)
+    assert np.array_equal(a['J_regressor_h36m17'][0], raw[6].astype(np.float32)) and np.array_equal(a['J_regressor_h36m17'][14], raw[0].astype(np.float32))
 
 
 def test_fillin_matches_the_reference_loop(pkg):
@@ -144,3 +148,10 @@ def test_host_mask_packing_matches_numpy(pkg, count, N, HW):
     assert rc == 1 and (out[count - 1, HW - 1] >> np.uint32(N - 1)) & 1 == 1
     assert L.lib.mh_debug_pack_masks(L.ptr(seg), 0, N, HW, L.ptr(out)) < 0     # bad arguments
     assert L.lib.mh_pool_bytes() == 0                                           # nothing parked without a device
+
+
+def test_sparse_joints_key_is_validated(pkg, model_dir):
+    """``smpl_sparse_joints_key`` must name a 17-joint output of the reference's SMPL layer (``optimizer.py:40``, ``smpl.py:368-381``)."""
+    with pytest.raises(ValueError, match='smpl_sparse_joints_key'):
+        pkg.SMPLDepthSequenceOptimizer(image_size=(64, 48), num_frames=2, cam_K=np.eye(3, dtype=np.float32), device='cuda:0',
+                                       smpl_model_parameters_path=model_dir, smpl_sparse_joints_key='joints_smpl24')
