@@ -174,11 +174,11 @@ class Context(object):
             pass
 
     # ---- helpers -------------------------------------------------------------------------------
-    def set_model(self, model, regressor='J_regressor_alphapose'):
-        """model: dict of numpy arrays (keys of ``smpl_io.load_smpl_model``); ``regressor``: which 17-joint regressor of the model
-        the 2-D terms use (``smpl_sparse_joints_key`` of the reference, ``optimizer.py:40, 696, 750``)."""
+    def set_model(self, model, reg17=None):
+        """model: dict of numpy arrays (keys of ``smpl_io.load_smpl_model``); ``reg17``: the (17, 6890) regressor of the sparse joints
+        the 2-D terms use (``smpl_sparse_joints_key`` of the reference, ``optimizer.py:40, 696, 750``; default: AlphaPose)."""
         arrs = {k: f32(model[k]) for k in ('v_template', 'shapedirs', 'posedirs', 'J_regressor', 'lbs_weights')}
-        arrs['reg17'] = f32(model[regressor])
+        arrs['reg17'] = f32(model['J_regressor_alphapose'] if reg17 is None else reg17)
         parents = np.ascontiguousarray(model['parents'], dtype=np.int32)
         faces = np.ascontiguousarray(model['faces'], dtype=np.int32)
         assert arrs['v_template'].shape == (V, 3) and arrs['shapedirs'].shape == (V, 3, 10), 'SMPL topology expected'

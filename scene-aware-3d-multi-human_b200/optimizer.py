@@ -189,13 +189,22 @@ class SMPLDepthSequenceOptimizer(SMPLOptimizerBase):
         self.ctx = L.Context(self.T_local, N, self.img_h, self.img_w, B=Bq, device=self.device_ordinal,
                              rank=self.rank if self._dist else 0, world=self.world if self._dist else 1, t0=self.t0, T_total=T_total,
                              M_max=self.max_scene_points if self.max_scene_points else self.img_h * self.img_w)
-        self.ctx.set_model(self.model, _SPARSE_REGRESSORS[self.smpl_sparse_joints_key])
+        self.ctx.set_model(self.model, self.sparse_regressor())
         self.ctx.set_camera(self.cam_K, self.K_ndc, self.cam_dist_coef)
         self.ctx.set_coefs(**self.coefs)
         w = np.ascontiguousarray(self.pose17j_weights, np.float32)
         self.ctx.call('mh_set_joint_weights', w.ctypes.data_as(L.FP))
         self._views = {}
         self._lib_comm = self._dist and self._setup_lib_comm()
+
+    def sparse_regressor(self):
+        """(17, 6890) regressor of ``smpl_sparse_joints_key``.  The layer returns 'joints_h36m17' relative to its pelvis joint
+        (``smpl.py:369-373``: ``joints - joints[:, 14]``), which is the regressor with row 14 subtracted from every row; its rows sum
+        to 0, so the body translation enters the absolute joints once, as ``scale * joints + poses_T`` does (``optimizer.py:750``)."""
+        reg = self.model[_SPARSE_REGRESSORS[self.smpl_sparse_joints_key]]
+        if self.smpl_sparse_joints_key == 'joints_h36m17':
+            reg = np.ascontiguousarray(reg - reg[14:15])
+        return reg
 
     def _setup_lib_comm(self):
         """Hand the per-cycle exchanges (halo frames, all-reduce of the shared leaves) to a communicator the library owns

@@ -845,7 +845,8 @@ def test_mask_ingest_paths_give_the_same_planes(pkg, L, mode, monkeypatch):
 
 def test_sparse_joints_key_selects_the_regressor(pkg, L):
     """``smpl_sparse_joints_key`` (``optimizer.py:40, 696, 750``): the 2-D terms use the 17 joints of the chosen output of the SMPL
-    layer -- 'joints_alphapose' (default) or 'joints_h36m17' (H36M regressor in the layer's row order, ``smpl.py:240-242``)."""
+    layer -- 'joints_alphapose' (default) or 'joints_h36m17' (H36M regressor in the layer's row order, relative to its pelvis joint 14:
+    ``smpl.py:240-242, 369-373``)."""
     g, data, meta = gh.load_fit('fit_n2.npz')
     N, T, W, H, batch = meta[:5]
     with pytest.raises(ValueError, match='smpl_sparse_joints_key'):
@@ -859,6 +860,8 @@ def test_sparse_joints_key_selects_the_regressor(pkg, L):
         verts, joints = opt.smpl_forward(betas, poses)
         reg = opt.model['J_regressor_alphapose' if key == 'joints_alphapose' else 'J_regressor_h36m17']
         ref = np.einsum('jv,bvk->bjk', reg.astype(np.float64), np.asarray(verts, np.float64).reshape(T * N, L.V, 3))
+        if key == 'joints_h36m17':
+            ref = ref - ref[:, 14:15]                                          # as the layer returns them
         assert np.abs(np.asarray(joints).reshape(T * N, 17, 3) - ref).max() <= 5e-6
         out[key] = np.asarray(joints).copy()
         opt.ctx.close()
